@@ -1,0 +1,1 @@
+#include "caml_shim.h"
