@@ -1,0 +1,149 @@
+/* poyb200.h -- C ABI of the B200 (sm_100a) implementation of POY's direct-optimisation alignment path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.  Every batch entry point
+ * replaces one OCaml `external` of the reference (declared in src/sequence.ml, implemented in src/algn.c) and
+ * computes, for every pair of the batch, exactly what that external returns for the pair -- bit for bit,
+ * including traceback tie-breaking.  INTEGRATION.md shows the OCaml-side stubs that bind to it.
+ *
+ *   reference external (file:line)                                    entry point here
+ *   ---------------------------------------------------------------  -------------------------------
+ *   algn_CAML_simple_2          src/algn.c:3409, sequence.ml:457      poyb200_batch_cost_2
+ *   algn_CAML_align_2d          src/algn.c:3987, sequence.ml:744      poyb200_batch_align_2
+ *     (= simple_2 + algn_CAML_backtrack_2d  src/algn.c:3908)
+ *   algn_CAML_ancestor_2        src/algn.c:4288, sequence.ml:919      poyb200_batch_align_2 (WANT_MEDIAN) /
+ *                                                                     poyb200_batch_median_2 (which = 0)
+ *   algn_CAML_median_2_with_gaps src/algn.c:4211, sequence.ml:756     ... (WANT_MEDIANWG) / (which = 1)
+ *   algn_CAML_median_2_no_gaps  src/algn.c:4198, sequence.ml:753      poyb200_batch_median_2 (which = 2)
+ *   algn_CAML_cost_affine_3     src/algn.c:2628, sequence.ml:465      poyb200_batch_cost_affine_3
+ *   algn_CAML_align_affine_3    src/algn.c:2551, sequence.ml:461      poyb200_batch_align_affine_3
+ *
+ * Sequences are the reference's `struct seq` payloads (src/seq.h:48-58): one byte per element (SEQT =
+ * unsigned char), the first element being the leading gap, so a sequence of n bases has length n + 1.
+ * A batch names its operands through a pool: `pool` holds the bytes of all DISTINCT sequences,
+ * `seq_off[s]` / `seq_len[s]` locate sequence s, and pair p aligns sequences pairs[2p] and pairs[2p+1]
+ * (a candidate-edge sweep shares one operand between thousands of pairs; it is uploaded once).
+ *
+ * Operand order follows Sequence.Align (src/sequence.ml:691-723, 813-823, 849-869): the linear kernels put
+ * the longer operand on the rows and break traceback ties with swaped = (len a >= len b); the affine kernels
+ * put the shorter operand (ties: a) on the rows.  Outputs always come back in the caller's (a, b) order.
+ *
+ * Outputs are caller-allocated (the reference's convention, src/sequence.ml:470-474, 816-817): row p of an
+ * output buffer spans [p * out_stride, (p+1) * out_stride) and holds the sequence RIGHT aligned -- the layout
+ * of the reference's `struct seq`, which is filled back to front by seq_prepend (begin = end - len + 1,
+ * src/seq.h:31-36, src/seq.c:147-153) -- and out_len[4p + k] gives its length (k = 0 median, 1 medianwg,
+ * 2 aligned a, 3 aligned b).  out_stride must be >= the largest len a + len b + 2 of the batch.
+ *
+ * Errors: every function returns 0 on success or a negative POYB200_E* code; poyb200_last_error gives the
+ * text (the reference raises OCaml `Failure` through failwith; the stubs in INTEGRATION.md turn a non-zero
+ * return into exactly that).  There is no CPU fallback: without a usable CUDA device poyb200_create fails.
+ */
+#ifndef POYB200_H
+#define POYB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POYB200_OK 0
+#define POYB200_ECUDA (-1)    /* CUDA runtime error (text in poyb200_last_error) */
+#define POYB200_EINVAL (-2)   /* bad argument (NULL where data is needed, stride too small, ...) */
+#define POYB200_ENOCM (-3)    /* no cost matrix loaded */
+#define POYB200_EMODEL (-4)   /* cost_model_type not supported by this entry point (SURVEY.md 8a note) */
+#define POYB200_ENOMEM (-5)   /* device or pinned-host allocation failed */
+#define POYB200_ESEQLEN (-6)  /* a sequence is empty or longer than POYB200_MAX_SEQ_LEN (src/seq.c:370) */
+
+#define POYB200_MAX_SEQ_LEN 16384 /* SHORT_SEQUENCES cap of the reference, src/seq.c:359-377 */
+
+/* what to return from the align entry points */
+#define POYB200_WANT_MEDIAN 1u    /* ancestor_2 (linear) / `median` of align_affine_3 */
+#define POYB200_WANT_MEDIANWG 2u  /* median_2_with_gaps (linear) / `medianwg` */
+#define POYB200_WANT_ALIGNED 4u   /* the two aligned (edited) sequences */
+
+/* Flat image of the reference's `struct cm` (src/cm.h:32-46).  cost/median/worst have (1<<lcm)*(1<<lcm)
+ * entries indexed (a << lcm) + b (src/cm.c:501-504); prepend_cost/tail_cost have 1<<lcm entries. */
+typedef struct poyb200_cm {
+    int32_t a_sz, lcm, gap, cost_model_type, combinations, gap_open, is_metric, all_elements;
+    const int32_t *cost;
+    const uint8_t *median;
+    const int32_t *worst; /* may be NULL: not used by the alignment path */
+    const int32_t *prepend_cost;
+    const int32_t *tail_cost;
+} poyb200_cm;
+
+typedef struct poyb200_batch {
+    /* inputs (host memory; pinned memory from poyb200_host_alloc makes the copies asynchronous) */
+    const uint8_t *pool;
+    size_t pool_bytes;
+    const int64_t *seq_off;
+    const int32_t *seq_len;
+    int32_t n_seqs;
+    const int32_t *pairs; /* 2 * n_pairs sequence indices */
+    int32_t n_pairs;
+    const int32_t *deltaw;       /* linear entry points: `deltawh` of algn_CAML_simple_2, one per pair */
+    const uint8_t *swaped;       /* optional, linear align only: explicit traceback tie flag per pair
+                                    (algn_CAML_backtrack_2d's `swap`); NULL = (len a >= len b) */
+    uint32_t want;               /* POYB200_WANT_* */
+    /* outputs (host memory), NULL when not wanted */
+    int32_t *cost;
+    uint8_t *median, *medianwg, *aligned_a, *aligned_b;
+    int64_t out_stride;
+    int32_t *out_len; /* 4 * n_pairs */
+} poyb200_batch;
+
+typedef struct poyb200_ctx poyb200_ctx;
+
+/* device < 0: keep the calling thread's current CUDA device. */
+int poyb200_create(int device, poyb200_ctx **out);
+void poyb200_destroy(poyb200_ctx *ctx);
+const char *poyb200_last_error(const poyb200_ctx *ctx);
+const char *poyb200_version(void);
+
+/* Copies the tables to the device; replaces cm_CAML_create + the cm_CAML_set_* calls as far as the
+ * alignment path is concerned (src/cm.c:1262, cost_matrix.ml:44-75). */
+int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm);
+
+/* Pinned host memory for batch buffers. */
+void *poyb200_host_alloc(size_t bytes);
+void poyb200_host_free(void *p);
+
+/* --- one-shot batch calls: H2D, kernels, D2H --------------------------------------------------------- */
+int poyb200_batch_cost_2(poyb200_ctx *ctx, const poyb200_batch *b);          /* linear, cost only */
+int poyb200_batch_align_2(poyb200_ctx *ctx, const poyb200_batch *b);         /* linear, cost + traceback + medians */
+int poyb200_batch_cost_affine_3(poyb200_ctx *ctx, const poyb200_batch *b);   /* affine_3, cost only */
+int poyb200_batch_align_affine_3(poyb200_ctx *ctx, const poyb200_batch *b);  /* affine_3, everything */
+
+/* which: 0 algn_ancestor_2, 1 algn_get_median_2d_with_gaps, 2 algn_get_median_2d_no_gaps.
+ * a/b: n rows of `in_stride` bytes holding LEFT-aligned aligned sequences of length len[p] (equal for both,
+ * as Sequence.Align.median_2 demands, src/sequence.ml:909-916); out rows of `out_stride` >= len + 1 bytes,
+ * RIGHT aligned, lengths in out_len[p]. */
+int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride,
+                           const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len);
+
+/* --- split form, used to time the device-resident part on its own ------------------------------------ */
+/* mode: 0 cost_2, 1 align_2, 2 cost_affine_3, 3 align_affine_3 */
+int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b); /* plan + H2D; keeps b for fetch */
+int poyb200_run(poyb200_ctx *ctx);                                      /* kernels only, asynchronous */
+int poyb200_sync(poyb200_ctx *ctx);                                     /* wait for the context's stream */
+int poyb200_fetch(poyb200_ctx *ctx);                                    /* D2H into the staged batch's outputs */
+
+/* --- introspection for benchmarks and tests ----------------------------------------------------------- */
+/* Number of kernels launched by this context so far. */
+int64_t poyb200_launch_count(const poyb200_ctx *ctx);
+/* DP cells the reference visits for one pair: linear (l1 >= l2 stored lengths, deltaw) and
+ * affine_3 (stored lengths, any order). */
+int64_t poyb200_cells_linear(int32_t l1, int32_t l2, int32_t deltaw);
+int64_t poyb200_cells_affine(int32_t la, int32_t lb);
+/* Device time in milliseconds of the kernels of the last poyb200_run, by phase: [0] fill, [1] traceback.
+ * Measured with CUDA events on the context's stream. */
+int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]);
+/* Raw cudaStream_t of the context (as void*), so a caller can bracket poyb200_run with its own events. */
+void *poyb200_stream(poyb200_ctx *ctx);
+/* Measures the INT32 ALU throughput of the device (dependent-free IADD3/VIMNMX mix), in Gop/s. */
+int poyb200_int32_peak(poyb200_ctx *ctx, double *gops_add, double *gops_minmax, double *gops_mix);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,79 @@
+"""ctypes binding of include/poyb200.h.  There is no fallback: if libpoyb200.so is missing or no CUDA device is
+usable, importing the binding or creating a context raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libpoyb200.so")
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+
+
+class CM(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("a_sz", "lcm", "gap", "cost_model_type", "combinations", "gap_open",
+                                          "is_metric", "all_elements")] + [
+        ("cost", i32p), ("median", u8p), ("worst", i32p), ("prepend_cost", i32p), ("tail_cost", i32p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("pool", C.c_void_p), ("pool_bytes", C.c_size_t), ("seq_off", C.c_void_p), ("seq_len", C.c_void_p),
+                ("n_seqs", C.c_int32), ("pairs", C.c_void_p), ("n_pairs", C.c_int32), ("deltaw", C.c_void_p),
+                ("swaped", C.c_void_p), ("want", C.c_uint32), ("cost", C.c_void_p), ("median", C.c_void_p),
+                ("medianwg", C.c_void_p), ("aligned_a", C.c_void_p), ("aligned_b", C.c_void_p),
+                ("out_stride", C.c_int64), ("out_len", C.c_void_p)]
+
+
+EXPORTS = [
+    "poyb200_create", "poyb200_destroy", "poyb200_last_error", "poyb200_version", "poyb200_set_cm",
+    "poyb200_host_alloc", "poyb200_host_free", "poyb200_batch_cost_2", "poyb200_batch_align_2",
+    "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3", "poyb200_batch_median_2", "poyb200_stage",
+    "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
+    "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise RuntimeError(
+            f"{SO} is missing: build it with `python -m poyd_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(SO)
+    L.poyb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.poyb200_destroy.argtypes = [C.c_void_p]
+    L.poyb200_destroy.restype = None
+    L.poyb200_last_error.argtypes = [C.c_void_p]
+    L.poyb200_last_error.restype = C.c_char_p
+    L.poyb200_version.restype = C.c_char_p
+    L.poyb200_set_cm.argtypes = [C.c_void_p, C.POINTER(CM)]
+    L.poyb200_host_alloc.argtypes = [C.c_size_t]
+    L.poyb200_host_alloc.restype = C.c_void_p
+    L.poyb200_host_free.argtypes = [C.c_void_p]
+    L.poyb200_host_free.restype = None
+    for f in ("poyb200_batch_cost_2", "poyb200_batch_align_2", "poyb200_batch_cost_affine_3",
+              "poyb200_batch_align_affine_3"):
+        getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Batch)]
+    L.poyb200_batch_median_2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_int64, C.c_void_p]
+    L.poyb200_stage.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
+    for f in ("poyb200_run", "poyb200_sync", "poyb200_fetch"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.poyb200_launch_count.argtypes = [C.c_void_p]
+    L.poyb200_launch_count.restype = C.c_int64
+    L.poyb200_cells_linear.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.poyb200_cells_linear.restype = C.c_int64
+    L.poyb200_cells_affine.argtypes = [C.c_int32, C.c_int32]
+    L.poyb200_cells_affine.restype = C.c_int64
+    L.poyb200_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.poyb200_stream.argtypes = [C.c_void_p]
+    L.poyb200_stream.restype = C.c_void_p
+    L.poyb200_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L

@@ -1,0 +1,576 @@
+// Host side of the C ABI (include/poyb200.h): planning, device memory, launches.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/poyb200.h"
+#include "generic_kernels.cuh"
+#include "peak.cuh"
+#include "stripe_kernels.cuh"
+#include "trace_kernels.cuh"
+
+using namespace poyb200;
+
+namespace {
+
+enum Mode { MODE_COST_2 = 0, MODE_ALIGN_2 = 1, MODE_COST_AFF = 2, MODE_ALIGN_AFF = 3 };
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Chunk {
+    size_t begin, end;  // task range
+    size_t dir_bytes;
+};
+
+}  // namespace
+
+struct poyb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // cost matrix
+    bool has_cm = false;
+    poyb200_cm hcm{};  // scalars only; pointers below are device pointers
+    DevCM dcm{};
+    DevBuf<int> d_cost, d_prepend, d_tail;
+    DevBuf<uint8_t> d_median;
+    // staged batch
+    bool staged = false;
+    int mode = 0;
+    poyb200_batch hb{};
+    std::vector<Task> tasks;
+    std::vector<Chunk> chunks;
+    std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
+    DevBuf<uint8_t> d_pool, d_dir, d_out[4];
+    DevBuf<Task> d_tasks;
+    DevBuf<int> d_costs, d_outlen, d_lin_state;
+    DevBuf<int4> d_aff_state;
+    long long dstride = 0;
+    size_t dir_budget = 0;
+    int state_stride = 0;
+    // stats
+    int64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms[2] = {0.f, 0.f};
+};
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return (e__ == cudaErrorMemoryAllocation) ? POYB200_ENOMEM : POYB200_ECUDA;    \
+        }                                                                                  \
+    } while (0)
+
+static int fail(poyb200_ctx *ctx, int code, const char *msg) {
+    ctx->err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// geometry: which cells the reference visits
+// ---------------------------------------------------------------------------------------------------------
+struct LinBand {
+    bool full;
+    int dlo, dhi;
+};
+
+// algn_nw_limit (src/algn.c:3265-3266) + algn_fill_plane_2 (:880-966): l1 >= l2 stored lengths.
+static LinBand linear_band(int l1, int l2, int deltaw) {
+    int width = 50 + deltaw, height = (l1 - l2) + 50 + deltaw;
+    if (width > l2) width = l2;
+    if (height > l1) height = l1;
+    LinBand b{false, 0, width - 1};
+    if ((float) l1 >= ((float) 3 / (float) 2) * (float) l2) b.full = true;  // Case 1 :893
+    else if (2 * height < l1) b.dlo = 1 - height;                           // Case 2 :898
+    else if (8 >= l1 - height) b.full = true;                               // Case 3a :936
+    else b.dlo = -((l1 - l2) + width);                                      // Case 3b :938-965
+    if (b.full) {
+        b.dlo = -(l1 - 1);
+        b.dhi = l2 - 1;
+    }
+    return b;
+}
+
+// algn_fill_plane_3_aff (:2435-2445, 2475): rows = shorter; nr, nc = lengths without the leading gap.
+static void affine_band(int nr, int nc, int &dlo, int &dhi) {
+    int e = nc - nr + 8;
+    if (e < 40) e = 40;
+    if (e > nc) e = nc;
+    dlo = -39;
+    dhi = e - 1;
+}
+
+extern "C" int64_t poyb200_cells_linear(int32_t l1, int32_t l2, int32_t deltaw) {
+    if (l1 < l2) std::swap(l1, l2);
+    LinBand b = linear_band(l1, l2, deltaw);
+    if (b.full) return (int64_t) l1 * l2;
+    int64_t n = 0;
+    for (int i = 0; i < l1; i++) {
+        int lo = std::max(0, i + b.dlo), hi = std::min(l2 - 1, i + b.dhi);
+        if (hi >= lo) n += hi - lo + 1;
+    }
+    return n;
+}
+
+extern "C" int64_t poyb200_cells_affine(int32_t la, int32_t lb) {
+    int nr = std::min(la, lb) - 1, nc = std::max(la, lb) - 1;
+    int s = 1, e = nc - nr + 8;
+    if (e < 40) e = 40;
+    if (e > nc) e = nc;
+    int64_t n = nc + 1;  // the initialised row
+    for (int i = 1; i <= nr; i++) {
+        if (i > 40) s++;
+        n += e - s + 2;  // band cells + the left-edge cell
+        if (e < nc) e++;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+extern "C" const char *poyb200_version(void) { return "poyb200 0.1 (sm_100a)"; }
+
+extern "C" int poyb200_create(int device, poyb200_ctx **out) {
+    if (!out) return POYB200_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return POYB200_ECUDA;  // no CPU fallback
+    poyb200_ctx *ctx = new poyb200_ctx();
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) {
+            delete ctx;
+            return POYB200_ECUDA;
+        }
+        ctx->device = device;
+    } else {
+        cudaGetDevice(&ctx->device);
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return POYB200_ECUDA;
+    }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // direction bands of one chunk: at most a third of the free HBM, capped at 48 GB
+    ctx->dir_budget = std::min<size_t>(free_b / 3, (size_t) 48 << 30);
+    if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
+    *out = ctx;
+    return POYB200_OK;
+}
+
+extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
+    ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
+    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release();
+    for (auto &b : ctx->d_out) b.release();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *poyb200_last_error(const poyb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t poyb200_launch_count(const poyb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *poyb200_stream(poyb200_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+
+extern "C" void *poyb200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void poyb200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
+    if (!ctx || !cm || !cm->cost || !cm->median || !cm->prepend_cost || !cm->tail_cost)
+        return ctx ? fail(ctx, POYB200_EINVAL, "poyb200_set_cm: NULL table") : POYB200_EINVAL;
+    if (cm->lcm < 1 || cm->lcm > 8) return fail(ctx, POYB200_EINVAL, "poyb200_set_cm: lcm out of range (SEQT is 8 bit)");
+    cudaSetDevice(ctx->device);
+    const size_t dim = (size_t) 1 << cm->lcm;
+    CK(ctx->d_cost.reserve(dim * dim));
+    CK(ctx->d_median.reserve(dim * dim));
+    CK(ctx->d_prepend.reserve(dim));
+    CK(ctx->d_tail.reserve(dim));
+    CK(cudaMemcpyAsync(ctx->d_cost.p, cm->cost, dim * dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_median.p, cm->median, dim * dim, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_prepend.p, cm->prepend_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tail.p, cm->tail_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hcm = *cm;
+    ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
+    ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
+    ctx->dcm = DevCM{cm->a_sz, cm->lcm, cm->gap, cm->cost_model_type, cm->combinations, cm->gap_open,
+                     ctx->d_cost.p, ctx->d_median.p, ctx->d_prepend.p, ctx->d_tail.p};
+    ctx->has_cm = true;
+    return POYB200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel classes
+// ---------------------------------------------------------------------------------------------------------
+static inline uint32_t round16(uint32_t v) { return (v + 15u) & ~15u; }
+
+// Picks the fill kernel for one pair and fixes the layout of its direction band.
+static void choose_class(Task &t, bool affine, bool bt, int W) {
+    (void) bt;
+    if (stripe_choose(t, affine, W)) return;
+    t.klass = KLASS_GENERIC;
+    t.G = 1;
+    t.twoK = 0xFFFFu;
+    t.BL = round16((uint32_t) (W + 2) / 2 + 1);
+}
+
+static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n) {
+    if (n <= 0) return POYB200_OK;
+    if (klass != KLASS_GENERIC) {
+        cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
+                                      ctx->sm_count, ctx->stream);
+        ctx->launches++;
+        CK(e);
+        return POYB200_OK;
+    }
+    const int warps_per_block = 4;
+    int blocks = std::min((n + warps_per_block - 1) / warps_per_block, ctx->sm_count * 8);
+    const size_t nwarps = (size_t) blocks * warps_per_block;
+    if (affine) {
+        CK(ctx->d_aff_state.reserve(nwarps * ctx->state_stride));
+        if (bt)
+            aff_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
+                                                                      ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+        else
+            aff_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
+                                                                       ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+    } else {
+        CK(ctx->d_lin_state.reserve(nwarps * ctx->state_stride));
+        if (bt)
+            lin_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
+                                                                      ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+        else
+            lin_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
+                                                                       ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return POYB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// planning
+// ---------------------------------------------------------------------------------------------------------
+static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+    const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
+    const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
+    if (!ctx->has_cm) return fail(ctx, POYB200_ENOCM, "no cost matrix loaded (poyb200_set_cm)");
+    if (b->n_pairs < 0 || b->n_seqs < 0) return fail(ctx, POYB200_EINVAL, "negative count");
+    if (b->n_pairs > 0 && (!b->pool || !b->seq_off || !b->seq_len || !b->pairs))
+        return fail(ctx, POYB200_EINVAL, "NULL input array");
+    if (!affine && b->n_pairs > 0 && !b->deltaw) return fail(ctx, POYB200_EINVAL, "linear entry points need deltaw[]");
+    // Sequence.Align diverts Affine to affine_3 (src/sequence.ml:716-723, 851-858); No_Alignment matrices take
+    // the legacy *_aff fill, which this library does not provide (closing note).
+    if (!affine && ctx->hcm.cost_model_type != 0)
+        return fail(ctx, POYB200_EMODEL, "linear entry point called with cost_model_type != 0");
+    if (affine && ctx->hcm.lcm < 4)
+        return fail(ctx, POYB200_EMODEL, "affine_3 indexes cost[(a&15) << lcm | (b&15)]: needs lcm >= 4");
+    for (int s = 0; s < b->n_seqs; s++) {
+        if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN)
+            return fail(ctx, POYB200_ESEQLEN, "sequence empty (no leading gap) or longer than 16384");
+        if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes)
+            return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
+    }
+    if (b->pool_bytes >= ((size_t) 1 << 32)) return fail(ctx, POYB200_EINVAL, "pool larger than 4 GiB");
+    ctx->tasks.resize((size_t) b->n_pairs);
+    long long maxcap = 16;
+    int maxW = 1;
+    for (int p = 0; p < b->n_pairs; p++) {
+        const int a = b->pairs[2 * p], c = b->pairs[2 * p + 1];
+        if (a < 0 || a >= b->n_seqs || c < 0 || c >= b->n_seqs) return fail(ctx, POYB200_EINVAL, "pair index out of range");
+        const int la = b->seq_len[a], lb = b->seq_len[c];
+        Task t{};
+        bool rows_b;
+        if (affine) {
+            rows_b = la > lb;  // shorter operand on the rows, ties keep a (src/algn.c:2595)
+        } else {
+            rows_b = la < lb;  // longer operand on the rows, ties keep a (src/sequence.ml:709-714)
+        }
+        const int r = rows_b ? c : a, col = rows_b ? a : c;
+        t.off_r = (uint32_t) b->seq_off[r];
+        t.off_c = (uint32_t) b->seq_off[col];
+        t.lr = b->seq_len[r];
+        t.lc = b->seq_len[col];
+        t.flags = rows_b ? TF_ROWS_ARE_B : 0;
+        t.pair = (uint32_t) p;
+        if (affine) {
+            affine_band(t.lr - 1, t.lc - 1, t.dlo, t.dhi);
+        } else {
+            LinBand lb2 = linear_band(t.lr, t.lc, b->deltaw[p]);
+            t.dlo = lb2.dlo;
+            t.dhi = lb2.dhi;
+            if (lb2.full) t.flags |= TF_FULL;
+            const bool sw = b->swaped ? (b->swaped[p] != 0) : (la >= lb);  // src/sequence.ml:818
+            if (sw) t.flags |= TF_SWAPED;
+        }
+        const int W = t.dhi - t.dlo + 1;
+        choose_class(t, affine, bt, W);
+        maxW = std::max(maxW, W);
+        maxcap = std::max<long long>(maxcap, (long long) la + lb + 2);
+        ctx->tasks[p] = t;
+    }
+    if (bt && b->n_pairs > 0) {
+        if ((b->want & POYB200_WANT_MEDIAN) && !b->median) return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN without buffer");
+        if ((b->want & POYB200_WANT_MEDIANWG) && !b->medianwg) return fail(ctx, POYB200_EINVAL, "WANT_MEDIANWG without buffer");
+        if ((b->want & POYB200_WANT_ALIGNED) && (!b->aligned_a || !b->aligned_b))
+            return fail(ctx, POYB200_EINVAL, "WANT_ALIGNED without buffers");
+        if (b->want && b->out_stride < maxcap) return fail(ctx, POYB200_EINVAL, "out_stride smaller than len a + len b + 2");
+        if (b->want && !b->out_len) return fail(ctx, POYB200_EINVAL, "out_len is NULL");
+    }
+    ctx->dstride = (maxcap + 15) & ~15ll;
+    ctx->state_stride = maxW + 2;
+    // group by kernel class (stable: keeps the caller's order inside a class), then cut into chunks whose
+    // direction bands fit the budget
+    std::stable_sort(ctx->tasks.begin(), ctx->tasks.end(), [](const Task &x, const Task &y) { return x.klass < y.klass; });
+    ctx->chunks.clear();
+    size_t begin = 0, off = 0;
+    for (size_t k = 0; k < ctx->tasks.size(); k++) {
+        Task &t = ctx->tasks[k];
+        size_t bytes = 0;
+        if (bt) {
+            bytes = (size_t) (t.lr + t.lc - 1) * t.G * t.BL;
+            bytes = (bytes + 15) & ~(size_t) 15;
+        }
+        if (off + bytes > ctx->dir_budget && k > begin) {
+            ctx->chunks.push_back(Chunk{begin, k, off});
+            begin = k;
+            off = 0;
+        }
+        t.dir_off = off;
+        off += bytes;
+    }
+    if (ctx->tasks.size() > begin) ctx->chunks.push_back(Chunk{begin, ctx->tasks.size(), off});
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+    if (!ctx || !b) return POYB200_EINVAL;
+    if (mode < 0 || mode > 3) return fail(ctx, POYB200_EINVAL, "bad mode");
+    cudaSetDevice(ctx->device);
+    ctx->staged = false;
+    int rc = plan(ctx, mode, b);
+    if (rc) return rc;
+    ctx->mode = mode;
+    ctx->hb = *b;
+    const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
+    const size_t n = ctx->tasks.size();
+    CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+    CK(ctx->d_tasks.reserve(n + 1));
+    CK(ctx->d_costs.reserve(n + 1));
+    size_t maxdir = 16;
+    for (auto &c : ctx->chunks) maxdir = std::max(maxdir, c.dir_bytes);
+    if (bt) {
+        CK(ctx->d_dir.reserve(maxdir));
+        CK(ctx->d_outlen.reserve(4 * n + 4));
+        const size_t ob = n * (size_t) ctx->dstride + 16;
+        if (b->want & POYB200_WANT_MEDIAN) CK(ctx->d_out[0].reserve(ob));
+        if (b->want & POYB200_WANT_MEDIANWG) CK(ctx->d_out[1].reserve(ob));
+        if (b->want & POYB200_WANT_ALIGNED) {
+            CK(ctx->d_out[2].reserve(ob));
+            CK(ctx->d_out[3].reserve(ob));
+        }
+    }
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->d_pool.p, b->pool, b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->staged = true;
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_run(poyb200_ctx *ctx) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_run without poyb200_stage");
+    cudaSetDevice(ctx->device);
+    const int mode = ctx->mode;
+    const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
+    const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
+    OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
+                ctx->d_outlen.p, ctx->dstride, ctx->hb.want};
+    const bool single = ctx->chunks.size() == 1;
+    if (single) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (const Chunk &ch : ctx->chunks) {
+        // one fill launch per kernel class present in the chunk
+        size_t k = ch.begin;
+        while (k < ch.end) {
+            size_t e = k;
+            const uint32_t klass = ctx->tasks[k].klass;
+            while (e < ch.end && ctx->tasks[e].klass == klass) e++;
+            int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k));
+            if (rc) return rc;
+            k = e;
+        }
+        if (single) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (bt) {
+            const int nt = (int) (ch.end - ch.begin);
+            const int blocks = (nt + 127) / 128;
+            if (affine)
+                aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
+                                                                      ctx->d_dir.p, out);
+            else
+                lin_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
+                                                                      ctx->d_dir.p, out);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    if (single) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_sync(poyb200_ctx *ctx) {
+    if (!ctx) return POYB200_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
+    if (!ctx || !ms) return POYB200_EINVAL;
+    cudaSetDevice(ctx->device);
+    ms[0] = ms[1] = 0.f;
+    if (ctx->chunks.size() != 1) return POYB200_OK;
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    CK(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_fetch(poyb200_ctx *ctx) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_fetch without poyb200_stage");
+    cudaSetDevice(ctx->device);
+    const poyb200_batch &b = ctx->hb;
+    const size_t n = ctx->tasks.size();
+    const bool bt = (ctx->mode == MODE_ALIGN_2 || ctx->mode == MODE_ALIGN_AFF);
+    if (n == 0) return POYB200_OK;
+    if (b.cost) CK(cudaMemcpyAsync(b.cost, ctx->d_costs.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bt && b.want) {
+        CK(cudaMemcpyAsync(b.out_len, ctx->d_outlen.p, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        uint8_t *dst[4] = {b.median, b.medianwg, b.aligned_a, b.aligned_b};
+        const uint32_t need[4] = {POYB200_WANT_MEDIAN, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
+        // right-aligned device rows -> right-aligned caller rows in one strided copy each
+        const size_t w = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
+        for (int k = 0; k < 4; k++) {
+            if (!(b.want & need[k])) continue;
+            CK(cudaMemcpy2DAsync(dst[k] + (b.out_stride - w), (size_t) b.out_stride, ctx->d_out[k].p + (ctx->dstride - w),
+                                 (size_t) ctx->dstride, w, n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POYB200_OK;
+}
+
+static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+    int rc = poyb200_stage(ctx, mode, b);
+    if (rc) return rc;
+    rc = poyb200_run(ctx);
+    if (rc) return rc;
+    return poyb200_fetch(ctx);
+}
+
+extern "C" int poyb200_batch_cost_2(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_COST_2, b); }
+extern "C" int poyb200_batch_align_2(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_ALIGN_2, b); }
+extern "C" int poyb200_batch_cost_affine_3(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_COST_AFF, b); }
+extern "C" int poyb200_batch_align_affine_3(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_ALIGN_AFF, b); }
+
+extern "C" int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride,
+                                      const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->has_cm) return fail(ctx, POYB200_ENOCM, "no cost matrix loaded (poyb200_set_cm)");
+    if (which < 0 || which > 2 || n < 0) return fail(ctx, POYB200_EINVAL, "bad argument");
+    if (n == 0) return POYB200_OK;
+    if (!a || !b || !len || !out || !out_len) return fail(ctx, POYB200_EINVAL, "NULL array");
+    for (int p = 0; p < n; p++)
+        if (len[p] < 0 || len[p] > in_stride || len[p] + 1 > out_stride)
+            return fail(ctx, POYB200_EINVAL, "row length does not fit the strides");
+    cudaSetDevice(ctx->device);
+    const size_t ib = (size_t) n * in_stride, ob = (size_t) n * out_stride;
+    CK(ctx->d_out[2].reserve(ib + 16));
+    CK(ctx->d_out[3].reserve(ib + 16));
+    CK(ctx->d_out[0].reserve(ob + 16));
+    CK(ctx->d_outlen.reserve(2 * (size_t) n + 4));
+    CK(cudaMemcpyAsync(ctx->d_out[2].p, a, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_out[3].p, b, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_outlen.p + n, len, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    median_2_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which, ctx->dcm, ctx->d_out[2].p, ctx->d_out[3].p, in_stride,
+                                                              ctx->d_outlen.p + n, n, ctx->d_out[0].p, out_stride,
+                                                              ctx->d_outlen.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_out[0].p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_len, ctx->d_outlen.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged = false;
+    return POYB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// INT32 roofline probe
+// ---------------------------------------------------------------------------------------------------------
+template <int KIND>
+static int peak_one(poyb200_ctx *ctx, int *d_out, double ops_per_step, double *gops) {
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        int32_peak_kernel<KIND><<<blocks, threads, 0, ctx->stream>>>(d_out, rep + 1);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (rep > 0 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    const double ops = (double) blocks * threads * PEAK_ITERS * PEAK_CHAINS * ops_per_step;
+    *gops = ops / (best * 1e-3) * 1e-9;
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_int32_peak(poyb200_ctx *ctx, double *gops_add, double *gops_minmax, double *gops_mix) {
+    if (!ctx || !gops_add || !gops_minmax || !gops_mix) return POYB200_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(ctx->d_costs.reserve(64));
+    int rc = peak_one<0>(ctx, ctx->d_costs.p, 2.0, gops_add);
+    if (rc) return rc;
+    rc = peak_one<1>(ctx, ctx->d_costs.p, 3.0, gops_minmax);
+    if (rc) return rc;
+    return peak_one<2>(ctx, ctx->d_costs.p, 3.0, gops_mix);
+}

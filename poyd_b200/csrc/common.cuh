@@ -1,0 +1,73 @@
+// Shared device/host definitions of the sm_100a alignment kernels.
+//
+// Geometry used by every kernel (DESIGN.md "Stripe formulation"): the cells the reference visits form a
+// stripe of diagonals dlo <= j - i <= dhi of the (rows x cols) matrix, swept by anti-diagonals t = i + j.
+// A cell on diagonal d reads its left neighbour from diagonal d-1 and its upper neighbour from d+1, both
+// written at t-1, and its diagonal neighbour from its own diagonal, written at t-2 -- so one value per
+// diagonal is all the DP state there is.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace poyb200 {
+
+constexpr int HIGH_NUM = 1000000;    // src/algn.c:38
+constexpr int LIN_INF = 0x30000000;  // "no neighbour" for the linear kernels (never wins a min, never overflows)
+constexpr int TMPGAP = 16;           // src/algn.c:1711
+
+// linear direction bits, src/matrices.h:22-27
+constexpr int D_ALIGN = 1, D_INSERT = 2, D_DELETE = 4;
+
+// affine direction byte (7 bits): what backtrace_affine (src/algn.c:1983-2097) would decide at this cell
+//   bits 1:0  mode entered from m_todo  : 0 horizontal, 1 align, 2 vertical, 3 diagonal   (priority :2006-2012)
+//   bits 3:2  mode after an align step  : 0 stay align, 1 horizontal, 2 diagonal, 3 vertical (priority :2049-2051)
+//   bit 4 END_HORIZONTAL, bit 5 END_VERTICAL, bit 6 END_BLOCK
+constexpr int AM_H = 0, AM_A = 1, AM_V = 2, AM_D = 3;
+constexpr int AN_A = 0, AN_H = 1, AN_D = 2, AN_V = 3;
+constexpr int AB_ENDH = 16, AB_ENDV = 32, AB_ENDB = 64;
+constexpr int AFF_LEFT_EDGE_BYTE = AM_V | AB_ENDV;   // DO_VERTICAL | END_VERTICAL   (:2476)
+constexpr int AFF_RIGHT_EDGE_BYTE = AM_H | AB_ENDH;  // DO_HORIZONTAL | END_HORIZONTAL (:2530)
+
+// task flags
+constexpr uint32_t TF_ROWS_ARE_B = 1;  // operand b sits on the rows: swap the aligned outputs back
+constexpr uint32_t TF_FULL = 2;        // linear: full matrix (algn_fill_plane), no edge rules
+constexpr uint32_t TF_SWAPED = 4;      // linear traceback tie flag (backtrack_2d `swaped`)
+
+struct Task {
+    uint32_t off_r, off_c;  // pool offsets of the row / column sequence
+    int32_t lr, lc;         // stored lengths (leading gap included)
+    int32_t dlo, dhi;       // stripe of diagonals visited
+    uint32_t flags;
+    uint32_t pair;          // index in the caller's pair list
+    uint64_t dir_off;       // byte offset of this pair's direction band
+    uint32_t G, twoK, BL;   // direction addressing, see dir_index
+    uint32_t klass;         // kernel class chosen by the planner
+};
+
+// Byte index of cell (i, j) inside a pair's direction band: anti-diagonal major, then lane-group chunk.
+// Stripe kernels write one BL-byte chunk per lane per step; the generic kernels use G = 1.
+__host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int j) {
+    uint32_t dd = (uint32_t) ((j - i) - t.dlo);
+    uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
+    return ((uint64_t) (i + j) * t.G + lane) * t.BL + m;
+}
+
+struct DevCM {
+    int a_sz, lcm, gap, cost_model_type, combinations, gap_open;
+    const int *cost;
+    const uint8_t *median;
+    const int *prepend, *tail;
+};
+
+struct OutPtrs {
+    int *cost;
+    uint8_t *median, *medianwg, *al_a, *al_b;
+    int *out_len;
+    long long stride;
+    uint32_t want;
+};
+
+__device__ __forceinline__ int cm_cost(const DevCM &c, int a, int b) { return __ldg(c.cost + (a << c.lcm) + b); }
+__device__ __forceinline__ int cm_median(const DevCM &c, int a, int b) { return __ldg(c.median + (a << c.lcm) + b); }
+
+}  // namespace poyb200

@@ -1,0 +1,230 @@
+// Traceback + median extraction, one thread per pair.  A traceback is a serial pointer chase through the
+// pair's packed direction band; running 10^5..10^6 of them side by side turns that latency into throughput,
+// and the kernel overlaps with the (ALU-bound) fill of the next chunk on another stream.
+#pragma once
+#include "cells.cuh"
+
+namespace poyb200 {
+
+// Writes a sequence right-to-left, exactly like the reference's seq_prepend (src/seq.c:147-153), into a row
+// whose end is 4-byte aligned; bytes are gathered into 32-bit words before they are stored.
+struct RevWriter {
+    uint8_t *base;
+    int pos;  // next byte goes to pos - 1
+    uint32_t acc;
+    int n;
+    __device__ __forceinline__ void init(uint8_t *row, int cap) { base = row; pos = cap; acc = 0; n = 0; }
+    __device__ __forceinline__ void put(int v) {
+        pos--;
+        n++;
+        acc |= ((uint32_t) v & 0xffu) << ((pos & 3) * 8);
+        if ((pos & 3) == 0) {
+            *reinterpret_cast<uint32_t *>(base + pos) = acc;
+            acc = 0;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        for (int k = pos; (k & 3) != 0; k++) base[k] = (uint8_t) (acc >> ((k & 3) * 8));
+    }
+};
+
+// backtrace_affine (src/algn.c:1983-2097).  dcap = device row stride (multiple of 16).
+__global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
+                                                            const uint8_t *__restrict__ pool,
+                                                            const uint8_t *__restrict__ dir, OutPtrs out) {
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= ntasks) return;
+    const Task t = tasks[ti];
+    const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
+    const uint8_t *dbase = dir + t.dir_off;
+    const int dcap = (int) out.stride;
+    const size_t row = (size_t) t.pair * out.stride;
+    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4;
+    RevWriter med, wg, ri, rj;
+    med.init(out.median + (w_med ? row : 0), dcap);
+    wg.init(out.medianwg + (w_wg ? row : 0), dcap);
+    // resi belongs to the row sequence; rows may be the caller's operand b (algn.c:2606-2616)
+    const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
+    ri.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
+    rj.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
+    int i = t.lr - 1, j = t.lc - 1;
+    int ic = si[i], jc = sj[j];
+    int nmed = 0, nwg = 0, nres = 0, med_first = -1;
+    enum { M_TODO, M_VERT, M_HORI, M_DIAG, M_ALGN };
+    int mode = M_TODO;
+#define PUT_MED(v) do { nmed++; med_first = (v); if (w_med) med.put(v); } while (0)
+#define PUT_WG(v) do { nwg++; if (w_wg) wg.put(v); } while (0)
+#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } } while (0)
+    while (i != 0 && j != 0) {
+        const int d = j - i;
+        int b;
+        if (d < t.dlo) b = AFF_LEFT_EDGE_BYTE;
+        else if (d > t.dhi) b = AFF_RIGHT_EDGE_BYTE;
+        else b = __ldg(dbase + dir_index(t, i, j));
+        if (mode == M_TODO) {
+            const int m = b & 3;
+            mode = (m == AM_H) ? M_HORI : (m == AM_A) ? M_ALGN : (m == AM_V) ? M_VERT : M_DIAG;
+        } else if (mode == M_VERT) {
+            if (b & AB_ENDV) mode = M_TODO;
+            if (!(ic & TMPGAP)) { PUT_MED(ic | TMPGAP); PUT_WG(ic | TMPGAP); } else PUT_WG(TMPGAP);
+            PUT_RES(ic, TMPGAP);
+            i--;
+            ic = si[i];
+        } else if (mode == M_HORI) {
+            if (b & AB_ENDH) mode = M_TODO;
+            if (!(jc & TMPGAP)) { PUT_MED(jc | TMPGAP); PUT_WG(jc | TMPGAP); } else PUT_WG(TMPGAP);
+            PUT_RES(TMPGAP, jc);
+            j--;
+            jc = sj[j];
+        } else if (mode == M_DIAG) {
+            if (b & AB_ENDB) mode = M_TODO;
+            PUT_RES(ic, jc);
+            PUT_WG(TMPGAP);
+            i--; j--;
+            ic = si[i]; jc = sj[j];
+        } else {
+            const int nx = (b >> 2) & 3;
+            if (nx == AN_H) mode = M_HORI;
+            else if (nx == AN_D) mode = M_DIAG;
+            else if (nx == AN_V) mode = M_VERT;
+            const int p = cm_median(cm, ic & 15, jc & 15);
+            PUT_MED(p); PUT_WG(p);
+            PUT_RES(ic, jc);
+            i--; j--;
+            ic = si[i]; jc = sj[j];
+        }
+    }
+    while (i != 0) {
+        if (!(ic & TMPGAP)) { PUT_MED(ic | TMPGAP); PUT_WG(ic | TMPGAP); } else PUT_WG(TMPGAP);
+        PUT_RES(ic, TMPGAP);
+        i--;
+        ic = si[i];
+    }
+    while (j != 0) {
+        if (!(jc & TMPGAP)) { PUT_MED(jc | TMPGAP); PUT_WG(jc | TMPGAP); } else PUT_WG(TMPGAP);
+        PUT_RES(TMPGAP, jc);
+        j--;
+        jc = sj[j];
+    }
+    PUT_RES(TMPGAP, TMPGAP);
+    PUT_WG(TMPGAP);
+    if (med_first != TMPGAP) PUT_MED(TMPGAP);  // :2093 (an empty median counts as "not a gap")
+#undef PUT_MED
+#undef PUT_WG
+#undef PUT_RES
+    if (w_med) med.flush();
+    if (w_wg) wg.flush();
+    if (w_al) { ri.flush(); rj.flush(); }
+    int *ol = out.out_len + 4 * (size_t) t.pair;
+    ol[0] = nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
+}
+
+// backtrack_2d, linear branch (src/algn.c:3606-3665), fused with algn_ancestor_2 (:4126-4147, the
+// cost_model != affine branch, the only one a linear alignment can reach) and
+// algn_get_median_2d_with_gaps (:4024-4035) -- what SeqCS.DOS.median asks for (src/seqCS.ml:757-766).
+__global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
+                                                            const uint8_t *__restrict__ pool,
+                                                            const uint8_t *__restrict__ dir, OutPtrs out) {
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= ntasks) return;
+    const Task t = tasks[ti];
+    const uint8_t *s1 = pool + t.off_r, *s2 = pool + t.off_c;
+    const uint8_t *dbase = dir + t.dir_off;
+    const int dcap = (int) out.stride, gap = cm.gap;
+    const size_t row = (size_t) t.pair * out.stride;
+    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4;
+    const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
+    const bool swaped = (t.flags & TF_SWAPED) != 0;
+    RevWriter med, wg, r1, r2;
+    med.init(out.median + (w_med ? row : 0), dcap);
+    wg.init(out.medianwg + (w_wg ? row : 0), dcap);
+    r1.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
+    r2.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
+    int i = t.lr - 1, j = t.lc - 1, n = 0, nmed = 0;
+    const int second = swaped ? D_INSERT : D_DELETE;
+    // `while (end >= beg)` over the row-major matrix: stops after the ALIGN step out of cell (0, 0)
+    while (i >= 0 && j >= 0) {
+        const int m = __ldg(dbase + dir_index(t, i, j));
+        int mv;
+        if (m & D_ALIGN) mv = D_ALIGN;
+        else if (m & second) mv = second;
+        else mv = swaped ? D_DELETE : D_INSERT;
+        int x, y;  // elements of s1 / s2 in this column
+        if (mv == D_ALIGN) { x = s1[i]; y = s2[j]; i--; j--; }
+        else if (mv == D_INSERT) { x = gap; y = s2[j]; j--; }
+        else { x = s1[i]; y = gap; i--; }
+        n++;
+        if (w_al) { r1.put(x); r2.put(y); }
+        const int ea = rows_b ? y : x, eb = rows_b ? x : y;  // caller's operand order
+        const int mm = cm_median(cm, ea, eb);
+        if (w_wg) wg.put(mm);
+        if (mm != gap) { nmed++; if (w_med) med.put(mm); }
+    }
+    nmed++;
+    if (w_med) { med.put(gap); med.flush(); }
+    if (w_wg) wg.flush();
+    if (w_al) { r1.flush(); r2.flush(); }
+    int *ol = out.out_len + 4 * (size_t) t.pair;
+    ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
+}
+
+// Stand-alone medians of already aligned pairs: which 0 algn_ancestor_2 (:4126-4147, including
+// algn_correct_blocks_affine :4080-4124 for combination alphabets under the affine model), 1
+// algn_get_median_2d_with_gaps (:4024), 2 algn_get_median_2d_no_gaps (:4042).  Output right aligned.
+__global__ void __launch_bounds__(128) median_2_kernel(int which, DevCM cm, const uint8_t *__restrict__ a,
+                                                       const uint8_t *__restrict__ b, long long in_stride,
+                                                       const int *__restrict__ len, int n, uint8_t *out,
+                                                       long long out_stride, int *out_len) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint8_t *sa = a + (size_t) p * in_stride, *sb = b + (size_t) p * in_stride;
+    uint8_t *row = out + (size_t) p * out_stride;
+    const int L = len[p], cap = (int) out_stride, gap = cm.gap;
+    int pos = cap;
+    if (which == 1) {
+        for (int i = L - 1; i >= 0; i--) row[--pos] = (uint8_t) cm_median(cm, sa[i], sb[i]);
+    } else if (which == 2) {
+        for (int i = L - 1; i >= 0; i--) {
+            const int m = cm_median(cm, sa[i], sb[i]);
+            if (m != gap) row[--pos] = (uint8_t) m;
+        }
+        row[--pos] = (uint8_t) gap;
+    } else if (!cm.combinations || cm.cost_model_type != 1) {
+        for (int i = L - 1; i >= 0; i--) {
+            const int m = cm_median(cm, sa[i], sb[i]);
+            if (m != gap) row[--pos] = (uint8_t) m;
+        }
+        row[--pos] = (uint8_t) gap;  // nothing equal to gap survived, so "first != gap" always holds
+    } else {
+        // left-to-right block correction into the left part of the row, then compaction to the right
+        int extending_gap = 0, inside_block = 0, prev_block = 0;
+        for (int i = 0; i < L; i++) {
+            const int ab = sa[i], bb = sb[i];
+            int sbv = cm_median(cm, ab, bb);
+            if (!inside_block && (!(ab & gap) || !(bb & gap))) inside_block = 0;
+            else if (inside_block && (!(ab & gap) || !(bb & gap))) inside_block = 0;
+            else if (((ab & gap) || (bb & gap)) && ((ab != gap) || (bb != gap))) inside_block = 1;
+            else inside_block = 0;
+            if (((gap & ab) || (gap & bb)) && !(sbv & gap) && !extending_gap) {
+                prev_block = inside_block;
+                extending_gap = 1;
+            } else if ((gap & ab) && (gap & bb) && (sbv & gap) && (sbv != gap) && extending_gap && inside_block &&
+                       !prev_block) {
+                sbv = (~gap) & sbv;
+                prev_block = 0;
+            } else if ((gap & ab) && (gap & bb) && (1 == extending_gap)) {
+                prev_block = inside_block;
+                extending_gap = 0;
+            }
+            row[i] = (uint8_t) sbv;
+        }
+        for (int i = L - 1; i >= 0; i--) {
+            const int v = row[i];
+            if (v != gap) row[--pos] = (uint8_t) v;  // pos > i always: cap >= L + 1
+        }
+        row[--pos] = (uint8_t) gap;
+    }
+    out_len[p] = cap - pos;
+}
+
+}  // namespace poyb200

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's ``Sequence`` / ``Sequence.Align`` (src/sequence.ml:453-1141) over batches.
+
+Where the reference aligns one pair per call through the OCaml externals ``algn_CAML_*``, a caller here hands
+over a :class:`SeqPool` (the distinct sequences) and a pair list, and every pair gets exactly what the
+reference's function of the same name returns for it.  The functions keep the reference's names, argument
+meaning and selection logic:
+
+* :meth:`Align.cost_2`   -- ``Sequence.Align.cost_2`` (:691-723): affine matrices go to ``cost_2_affine``
+  (``algn_CAML_cost_affine_3``), others to ``algn_CAML_simple_2`` with the Ukkonen ``deltaw`` computed from
+  the gap counts and lengths exactly as :691-714 does.
+* :meth:`Align.align_2`  -- ``Sequence.Align.align_2`` (:849-869): ``align_affine_3`` or
+  ``cost_2`` + ``create_edited_2`` (:813-823).
+* :meth:`Align.align_affine_3` (:469-478), :meth:`Align.median_2` (:907-918),
+  :meth:`Align.median_2_with_gaps` (:895-905), :meth:`Align.ancestor_2` (:922-932),
+  :meth:`Align.full_median_2` (:949-957).
+
+All compute runs in the CUDA library behind include/poyb200.h; nothing here computes an alignment on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence as _Seq
+
+import numpy as np
+
+from . import _lib
+from .cost_matrix import CostMatrix
+
+WANT_MEDIAN, WANT_MEDIANWG, WANT_ALIGNED = 1, 2, 4
+MODE_COST_2, MODE_ALIGN_2, MODE_COST_AFFINE_3, MODE_ALIGN_AFFINE_3 = 0, 1, 2, 3
+
+
+class PoyB200Error(RuntimeError):
+    """Raised where the reference would raise ``Failure`` (failwith) -- plus CUDA errors."""
+
+
+class SeqPool:
+    """The distinct sequences of a batch: one ``uint8`` per element, leading gap included (src/seq.h:48-58).
+
+    Sequence starts are 16-byte aligned so the kernels can stage them with bulk copies."""
+
+    ALIGN = 16
+
+    def __init__(self, seqs: Iterable[np.ndarray]):
+        seqs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        padded = (lens.astype(np.int64) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        off = np.zeros(len(seqs), dtype=np.int64)
+        if len(seqs):
+            off[1:] = np.cumsum(padded)[:-1]
+        pool = np.zeros(int(padded.sum()) + self.ALIGN, dtype=np.uint8)
+        for s, o in zip(seqs, off):
+            pool[o:o + len(s)] = s
+        self.pool, self.off, self.len = pool, off, lens
+
+    @classmethod
+    def from_matrix(cls, mat: np.ndarray, lens: np.ndarray) -> "SeqPool":
+        """Rows of a [n, stride] uint8 matrix, row r holding lens[r] elements; stride must be a multiple of 16."""
+        self = cls.__new__(cls)
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        assert mat.shape[1] % cls.ALIGN == 0
+        self.pool = mat.reshape(-1)
+        self.off = np.arange(mat.shape[0], dtype=np.int64) * mat.shape[1]
+        self.len = np.ascontiguousarray(lens, dtype=np.int32)
+        return self
+
+    def __len__(self) -> int:
+        return len(self.len)
+
+    def seq(self, i: int) -> np.ndarray:
+        return self.pool[self.off[i]:self.off[i] + self.len[i]]
+
+    def count(self, gap: int) -> np.ndarray:
+        """``Sequence.count gap s`` = seq_CAML_count (src/seq.c:570-582) for every sequence: the number of
+        elements with ``code land gap <> 0`` (a bitwise test even for sequential alphabets)."""
+        hit = (self.pool & np.uint8(gap)) != 0
+        cs = np.concatenate([[0], np.cumsum(hit, dtype=np.int64)])
+        return (cs[self.off + self.len] - cs[self.off]).astype(np.int32)
+
+
+@dataclass
+class Aligned:
+    """Result of an align call.  Rows are right aligned in [n, stride] arrays (the layout of the reference's
+    ``struct seq``: begin = end - len + 1); use :meth:`get` for one trimmed sequence."""
+
+    cost: np.ndarray
+    lens: Optional[np.ndarray] = None  # [n, 4]: median, medianwg, aligned a, aligned b
+    median: Optional[np.ndarray] = None
+    medianwg: Optional[np.ndarray] = None
+    aligned_a: Optional[np.ndarray] = None
+    aligned_b: Optional[np.ndarray] = None
+
+    _COL = {"median": 0, "medianwg": 1, "aligned_a": 2, "aligned_b": 3}
+
+    def get(self, what: str, p: int) -> np.ndarray:
+        buf = getattr(self, what)
+        n = int(self.lens[p, self._COL[what]])
+        return buf[p, buf.shape[1] - n:]
+
+
+def deltaw_calc(s1len: np.ndarray, s2len: np.ndarray, deltaw: Optional[np.ndarray]) -> np.ndarray:
+    """``deltaw_calc`` of Sequence.Align.cost_2 (src/sequence.ml:692-702), s1len >= s2len."""
+    dif = s1len - s2len
+    lower = (s1len.astype(np.float64) * 0.10).astype(np.int64)  # int_of_float truncates
+    if deltaw is None:
+        return np.where(dif < lower, lower // 2, 2).astype(np.int32)
+    return np.where(dif < lower, lower, deltaw).astype(np.int32)
+
+
+class Align:
+    """``Sequence.Align`` bound to one cost matrix and one GPU."""
+
+    def __init__(self, cm: CostMatrix, device: int = -1):
+        self.L = _lib.lib()
+        self.cm = cm
+        h = C.c_void_p()
+        rc = self.L.poyb200_create(device, C.byref(h))
+        if rc != 0:
+            raise PoyB200Error(f"poyb200_create failed ({rc}): no usable CUDA device; there is no CPU fallback")
+        self.h = h
+        self._set_cm(cm)
+        self._keep = None
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.poyb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PoyB200Error(f"poyb200 error {rc}: {self.L.poyb200_last_error(self.h).decode()}")
+
+    def _set_cm(self, cm: CostMatrix) -> None:
+        self._tabs = [np.ascontiguousarray(cm.cost, np.int32), np.ascontiguousarray(cm.median, np.uint8),
+                      np.ascontiguousarray(cm.worst, np.int32), np.ascontiguousarray(cm.prepend_cost, np.int32),
+                      np.ascontiguousarray(cm.tail_cost, np.int32)]
+        c = _lib.CM(cm.a_sz, cm.lcm, cm.gap, cm.cost_model_type, cm.combinations, cm.gap_open, cm.is_metric,
+                    cm.all_elements, self._tabs[0].ctypes.data_as(_lib.i32p), self._tabs[1].ctypes.data_as(_lib.u8p),
+                    self._tabs[2].ctypes.data_as(_lib.i32p), self._tabs[3].ctypes.data_as(_lib.i32p),
+                    self._tabs[4].ctypes.data_as(_lib.i32p))
+        self._check(self.L.poyb200_set_cm(self.h, C.byref(c)))
+
+    @property
+    def is_affine(self) -> bool:
+        return self.cm.cost_model_type == 1
+
+    # ---- deltaw exactly as Sequence.Align.cost_2 computes it -------------------------------------------
+    def deltaw_for(self, pool: SeqPool, pairs: np.ndarray, deltaw: Optional[np.ndarray] = None) -> np.ndarray:
+        cnt = pool.count(self.cm.gap)
+        la, lb = pool.len[pairs[:, 0]].astype(np.int64), pool.len[pairs[:, 1]].astype(np.int64)
+        gaps = np.maximum(cnt[pairs[:, 0]], cnt[pairs[:, 1]])
+        return (gaps + deltaw_calc(np.maximum(la, lb), np.minimum(la, lb), deltaw)).astype(np.int32)
+
+    # ---- batch plumbing -----------------------------------------------------------------------------
+    def make_batch(self, pool: SeqPool, pairs, deltaw=None, swaped=None, want: int = 0, outputs: bool = True):
+        """Builds the C batch descriptor (and output arrays).  Returns (batch, Aligned)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = len(pairs)
+        keep = [pool.pool, pool.off, pool.len, pairs]
+        b = _lib.Batch()
+        b.pool, b.pool_bytes = pool.pool.ctypes.data, pool.pool.nbytes
+        b.seq_off, b.seq_len, b.n_seqs = pool.off.ctypes.data, pool.len.ctypes.data, len(pool)
+        b.pairs, b.n_pairs = pairs.ctypes.data, n
+        if deltaw is not None:
+            deltaw = np.ascontiguousarray(deltaw, dtype=np.int32)
+            keep.append(deltaw)
+            b.deltaw = deltaw.ctypes.data
+        if swaped is not None:
+            swaped = np.ascontiguousarray(swaped, dtype=np.uint8)
+            keep.append(swaped)
+            b.swaped = swaped.ctypes.data
+        res = Aligned(cost=np.zeros(n, np.int32))
+        b.cost = res.cost.ctypes.data
+        b.want = want
+        if want and outputs:
+            stride = 16
+            if n:
+                stride = int((pool.len[pairs[:, 0]].astype(np.int64) + pool.len[pairs[:, 1]]).max()) + 2
+            stride = (stride + 15) // 16 * 16
+            res.lens = np.zeros((n, 4), np.int32)
+            b.out_len, b.out_stride = res.lens.ctypes.data, stride
+            if want & WANT_MEDIAN:
+                res.median = np.zeros((n, stride), np.uint8)
+                b.median = res.median.ctypes.data
+            if want & WANT_MEDIANWG:
+                res.medianwg = np.zeros((n, stride), np.uint8)
+                b.medianwg = res.medianwg.ctypes.data
+            if want & WANT_ALIGNED:
+                res.aligned_a = np.zeros((n, stride), np.uint8)
+                res.aligned_b = np.zeros((n, stride), np.uint8)
+                b.aligned_a, b.aligned_b = res.aligned_a.ctypes.data, res.aligned_b.ctypes.data
+        self._keep = keep
+        return b, res
+
+    # ---- Sequence.Align ------------------------------------------------------------------------------
+    def cost_2(self, pool: SeqPool, pairs, deltaw: Optional[np.ndarray] = None, raw_deltaw: bool = False) -> np.ndarray:
+        """``Sequence.Align.cost_2 ?deltaw s1 s2 m1 m2`` for every pair (src/sequence.ml:716-723).
+
+        raw_deltaw=True passes ``deltaw`` straight to ``algn_CAML_simple_2`` (the external's own argument)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        if self.is_affine:
+            b, res = self.make_batch(pool, pairs)
+            self._check(self.L.poyb200_batch_cost_affine_3(self.h, C.byref(b)))
+        else:
+            dw = np.asarray(deltaw, np.int32) if raw_deltaw else self.deltaw_for(pool, pairs, deltaw)
+            b, res = self.make_batch(pool, pairs, deltaw=dw)
+            self._check(self.L.poyb200_batch_cost_2(self.h, C.byref(b)))
+        return res.cost
+
+    def align_affine_3(self, pool: SeqPool, pairs, want: int = WANT_MEDIAN | WANT_MEDIANWG | WANT_ALIGNED) -> Aligned:
+        """``Sequence.Align.align_affine_3 si sj cm`` (src/sequence.ml:469-478): median, resi, resj, cost,
+        medianwg for every pair."""
+        b, res = self.make_batch(pool, pairs, want=want)
+        self._check(self.L.poyb200_batch_align_affine_3(self.h, C.byref(b)))
+        return res
+
+    def align_2(self, pool: SeqPool, pairs, want: int = WANT_ALIGNED, deltaw: Optional[np.ndarray] = None,
+                raw_deltaw: bool = False, swaped: Optional[np.ndarray] = None) -> Aligned:
+        """``Sequence.Align.align_2 s1 s2 c m`` (src/sequence.ml:849-861) for every pair; with WANT_MEDIAN /
+        WANT_MEDIANWG also ``ancestor_2`` / ``median_2_with_gaps`` of the aligned pair, which is what
+        ``SeqCS.DOS.median`` computes next (src/seqCS.ml:757-766)."""
+        if self.is_affine:
+            return self.align_affine_3(pool, pairs, want)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        dw = np.asarray(deltaw, np.int32) if raw_deltaw else self.deltaw_for(pool, pairs, deltaw)
+        b, res = self.make_batch(pool, pairs, deltaw=dw, swaped=swaped, want=want)
+        self._check(self.L.poyb200_batch_align_2(self.h, C.byref(b)))
+        return res
+
+    def _median(self, which: int, a: np.ndarray, b: np.ndarray, lens: np.ndarray):
+        a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        if a.shape != b.shape:
+            raise ValueError("The size of the sequences is not the same.")  # Invalid_Argument, sequence.ml:903
+        n, stride = a.shape
+        ostride = (stride + 1 + 15) // 16 * 16
+        out, olen = np.zeros((n, ostride), np.uint8), np.zeros(n, np.int32)
+        self._check(self.L.poyb200_batch_median_2(self.h, which, a.ctypes.data, b.ctypes.data, stride, lens.ctypes.data, n,
+                                                  out.ctypes.data, ostride, olen.ctypes.data))
+        return out, olen
+
+    def ancestor_2(self, a, b, lens):
+        """``Sequence.Align.ancestor_2`` (src/sequence.ml:922-932) on rows of LEFT-aligned aligned sequences."""
+        return self._median(0, a, b, lens)
+
+    def median_2_with_gaps(self, a, b, lens):
+        """``Sequence.Align.median_2_with_gaps`` (src/sequence.ml:895-905)."""
+        return self._median(1, a, b, lens)
+
+    def median_2(self, a, b, lens):
+        """``Sequence.Align.median_2`` (src/sequence.ml:907-918)."""
+        return self._median(2, a, b, lens)
+
+    def full_median_2(self, pool: SeqPool, pairs):
+        """``Sequence.Align.full_median_2`` (src/sequence.ml:949-957): the affine median, or align_2 followed
+        by median_2 (no gaps).  Returns (rows, lens), rows right aligned."""
+        if self.is_affine:
+            r = self.align_affine_3(pool, pairs, WANT_MEDIAN)
+            return r.median, r.lens[:, 0].copy()
+        r = self.align_2(pool, pairs, WANT_ALIGNED)
+        n, stride = r.aligned_a.shape
+        la = r.lens[:, 2]
+        a, b = np.zeros_like(r.aligned_a), np.zeros_like(r.aligned_b)
+        for p in range(n):  # left align for the median call (host-side plumbing only)
+            a[p, :la[p]] = r.aligned_a[p, stride - la[p]:]
+            b[p, :la[p]] = r.aligned_b[p, stride - la[p]:]
+        return self.median_2(a, b, la)
+
+    # ---- split calls for benchmarks ----------------------------------------------------------------------
+    def stage(self, mode: int, batch) -> None:
+        self._check(self.L.poyb200_stage(self.h, mode, C.byref(batch)))
+
+    def run(self) -> None:
+        self._check(self.L.poyb200_run(self.h))
+
+    def sync(self) -> None:
+        self._check(self.L.poyb200_sync(self.h))
+
+    def fetch(self) -> None:
+        self._check(self.L.poyb200_fetch(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.poyb200_launch_count(self.h))
+
+    def last_run_ms(self):
+        ms = (C.c_float * 2)()
+        self._check(self.L.poyb200_last_run_ms(self.h, ms))
+        return float(ms[0]), float(ms[1])
+
+    def int32_peak(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.L.poyb200_int32_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+
+def cells_linear(l1: int, l2: int, deltaw: int) -> int:
+    """DP cells ``algn_fill_plane_2`` visits for stored lengths l1, l2."""
+    return int(_lib.lib().poyb200_cells_linear(int(l1), int(l2), int(deltaw)))
+
+
+def cells_affine(la: int, lb: int) -> int:
+    """DP cells ``algn_fill_plane_3_aff`` visits (band + left-edge cells + the initialised row)."""
+    return int(_lib.lib().poyb200_cells_affine(int(la), int(lb)))

@@ -1,0 +1,60 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/poyb200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "poyb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(poyb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from poyd_b200 import build, _lib
+
+    so = build.build()
+    L = ctypes.CDLL(so)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/poyb200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "poyd_b200/_lib.py EXPORTS out of sync with the header"
+
+
+def test_no_device_is_a_loud_error():
+    """Without a CUDA device the product must fail, not fall back (this test runs on the CPU-only box)."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a GPU is present")
+    from poyd_b200 import cost_matrix, sequence
+
+    try:
+        sequence.Align(cost_matrix.default_nucleotides())
+    except sequence.PoyB200Error as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("Align() succeeded without a GPU")
+
+
+def test_cells_formula_matches_survey_check_values():
+    """SURVEY.md 8d check values for cells(): measured there on the compiled reference."""
+    from poyd_b200 import sequence as S
+
+    assert S.cells_linear(501, 501, 26) == 69951
+    assert S.cells_linear(501, 476, 26) == 78076
+    assert S.cells_linear(501, 451, 3) == 67149
+    assert S.cells_linear(301, 301, 16) == 35141
+    assert S.cells_linear(301, 301, 271) == 90601
+    assert S.cells_linear(1501, 1501, 76) == 361001
+    assert S.cells_linear(1501, 1401, 76) == 476001
+    assert S.cells_affine(501, 501) == 38941
+    assert S.cells_affine(476, 501) == 37616
+    assert S.cells_affine(451, 501) == 43793
+    assert S.cells_affine(301, 301) == 22741
+    assert S.cells_affine(1501, 1501) == 119941

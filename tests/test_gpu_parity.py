@@ -1,0 +1,186 @@
+"""GPU parity tests: every result of the CUDA path, called through the C ABI, against the CPU checker
+(the compiled reference algn.c when oracle/_ref is present, else the plain-C port) on the same seeded inputs.
+Bar: bit-exact costs, aligned sequences and medians, including traceback tie-breaking."""
+import numpy as np
+import pytest
+
+from helpers import assert_aligned_equal
+
+pytestmark = pytest.mark.gpu
+
+ALL = 7  # WANT_MEDIAN | WANT_MEDIANWG | WANT_ALIGNED
+
+
+@pytest.fixture(scope="module")
+def S():
+    from poyd_b200 import sequence
+
+    return sequence
+
+
+def _affine_cases():
+    from poyd_b200 import cost_matrix as CM
+
+    return [("sub1_indel2_go3", CM.nucleotides(1, 2, 3)), ("sub2_indel1_go1", CM.nucleotides(2, 1, 1)),
+            ("sub3_indel1_go5", CM.nucleotides(3, 1, 5))]
+
+
+def _linear_cases():
+    from poyd_b200 import cost_matrix as CM
+
+    return [("dna_1_2", CM.default_nucleotides(), "dna"), ("dna_1_1", CM.nucleotides(1, 1), "dna"),
+            ("dna_3_1", CM.nucleotides(3, 1), "dna"), ("protein_1_2", CM.default_aminoacids(), "protein")]
+
+
+@pytest.mark.parametrize("gap_amb", [0.0, 0.12])
+def test_affine_align_ragged(S, checker_factory, gap_amb):
+    from poyd_b200 import synth
+
+    for name, cm in _affine_cases():
+        pool, pairs = synth.ragged_batch(600, max_len=260, seed=11, gap_ambiguity=gap_amb)
+        al = S.Align(cm)
+        g = al.align_affine_3(pool, pairs, ALL)
+        o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs)
+        assert_aligned_equal(g, o, label=f"affine {name} gapamb={gap_amb}")
+        gc = al.cost_2(pool, pairs)
+        oc = checker_factory(cm).batch(2, pool.pool, pool.off, pool.len, pairs)["cost"]
+        assert np.array_equal(gc, oc), f"cost_affine_3 {name}"
+        al.close()
+
+
+def test_affine_headline_shape(S, checker_factory):
+    """configs[1] shape: 500 bp parents, 10 % substitutions, 2 % indels, gap opening 3."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    for gap_amb, seed in ((0.0, 2), (0.10, 3)):
+        pool, pairs = synth.pair_batch(1500, 500, seed=seed, min_len=450, ambiguity=0.005 if gap_amb else 0.0,
+                                       gap_ambiguity=gap_amb)
+        al = S.Align(cm)
+        g = al.align_affine_3(pool, pairs, ALL)
+        o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
+        assert_aligned_equal(g, o, label=f"cfg2 gapamb={gap_amb}")
+        oc = checker_factory(cm).batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
+        assert np.array_equal(al.cost_2(pool, pairs), oc)
+        al.close()
+
+
+def test_affine_empty_and_tiny(S, checker_factory):
+    from poyd_b200 import cost_matrix as CM
+
+    cm = CM.nucleotides(1, 2, 3)
+    seqs = [np.array([16], np.uint8), np.array([16, 1], np.uint8), np.array([16, 17], np.uint8),
+            np.array([16, 1, 2, 4, 8], np.uint8), np.array([16, 8, 4, 18, 1, 1, 1], np.uint8),
+            np.array([16] + [1] * 45, np.uint8), np.array([16] + [2] * 41, np.uint8)]
+    pool = S.SeqPool(seqs)
+    pairs = np.array([(a, b) for a in range(len(seqs)) for b in range(len(seqs))], np.int32)
+    al = S.Align(cm)
+    g = al.align_affine_3(pool, pairs, ALL)
+    o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs)
+    assert_aligned_equal(g, o, label="affine tiny")
+    al.close()
+
+
+def test_linear_align_ragged(S, checker_factory):
+    from poyd_b200 import synth
+
+    for name, cm, alph in _linear_cases():
+        pool, pairs = synth.ragged_batch(500, max_len=240, seed=5, alphabet=alph, gap_ambiguity=0.03 if alph == "dna" else 0)
+        al = S.Align(cm)
+        dw = al.deltaw_for(pool, pairs)
+        g = al.align_2(pool, pairs, ALL)
+        o = checker_factory(cm).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw)
+        assert_aligned_equal(g, o, label=f"linear {name}")
+        gc = al.cost_2(pool, pairs)
+        assert np.array_equal(gc, o["cost"]), f"cost_2 {name}"
+        # the candidate-edge sweep hint of SeqCS.DOS.distance: deltaw = max 8 |la - lb| (src/seqCS.ml:856-866)
+        la, lb = pool.len[pairs[:, 0]], pool.len[pairs[:, 1]]
+        hint = np.maximum(8, np.abs(la - lb)).astype(np.int32)
+        dw2 = al.deltaw_for(pool, pairs, hint)
+        oc2 = checker_factory(cm).batch(0, pool.pool, pool.off, pool.len, pairs, deltaw=dw2)["cost"]
+        assert np.array_equal(al.cost_2(pool, pairs, deltaw=hint), oc2), f"cost_2 with deltaw hint {name}"
+        al.close()
+
+
+def test_linear_explicit_bands(S, checker_factory):
+    """deltaw is an input of the external (algn_CAML_simple_2): sweep it directly, narrow to full."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.default_nucleotides()
+    pool, pairs = synth.pair_batch(300, 300, seed=9, min_len=240)
+    al = S.Align(cm)
+    for dwv in (0, 3, 16, 60, 271):
+        dw = np.full(len(pairs), dwv, np.int32)
+        g = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
+        o = checker_factory(cm).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw)
+        assert_aligned_equal(g, o, label=f"linear deltaw={dwv}")
+    al.close()
+
+
+def test_protein_config_shapes(S, checker_factory):
+    """configs[2]: 300 aa pairs, 22x22 matrix; (3a) deltaw as the product computes it (full matrix, SURVEY.md
+    A15 quirk) and (3b) an explicit band of 16."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.default_aminoacids()
+    pool, pairs = synth.pair_batch(400, 300, seed=3, alphabet="protein", subst=0.15, indel=0.02)
+    al = S.Align(cm)
+    dwa = al.deltaw_for(pool, pairs)
+    assert dwa.min() > 200  # the quirk: 18 of the 21 residue codes share a bit with gap code 22
+    for dw in (dwa, np.full(len(pairs), 16, np.int32)):
+        g = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
+        o = checker_factory(cm).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=8)
+        assert_aligned_equal(g, o, label="protein")
+    al.close()
+
+
+def test_median_2_entry_points(S, checker_factory):
+    from poyd_b200 import cost_matrix as CM, synth
+
+    for cm in (CM.default_nucleotides(), CM.nucleotides(1, 2, 3), CM.default_aminoacids()):
+        alph = "dna" if cm.combinations else "protein"
+        pool, pairs = synth.ragged_batch(200, max_len=120, seed=21, alphabet=alph, gap_ambiguity=0.1 if alph == "dna" else 0)
+        chk = checker_factory(cm)
+        lin = cm if cm.cost_model_type == 0 else CM.nucleotides(1, 2)
+        src = checker_factory(lin).batch(1, pool.pool, pool.off, pool.len, pairs,
+                                         deltaw=np.full(len(pairs), 30, np.int32))
+        a, b, ln = src["ra"], src["rb"], src["lens"][:, 2].copy()
+        stride = (a.shape[1] + 15) // 16 * 16
+        a = np.pad(a, ((0, 0), (0, stride - a.shape[1])))
+        b = np.pad(b, ((0, 0), (0, stride - b.shape[1])))
+        al = S.Align(cm)
+        for which, fn in ((0, al.ancestor_2), (1, al.median_2_with_gaps), (2, al.median_2)):
+            out, olen = fn(a, b, ln)
+            for p in range(len(pairs)):
+                exp = chk.median_2(which, a[p, :ln[p]], b[p, :ln[p]])
+                got = out[p, out.shape[1] - olen[p]:]
+                assert np.array_equal(got, exp), f"median_2 which={which} pair {p}"
+        al.close()
+
+
+def test_shared_operand_sweep(S, checker_factory):
+    """Candidate-edge sweep: one clade sequence against many edges -- the pool holds each sequence once."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    pool, _ = synth.pair_batch(64, 400, seed=17, min_len=350)
+    pairs = np.array([(0, k) for k in range(1, len(pool))], np.int32)
+    al = S.Align(cm)
+    oc = checker_factory(cm).batch(2, pool.pool, pool.off, pool.len, pairs)["cost"]
+    assert np.array_equal(al.cost_2(pool, pairs), oc)
+    al.close()
+
+
+def test_error_paths(S):
+    from poyd_b200 import cost_matrix as CM
+
+    al = S.Align(CM.nucleotides(1, 2, 3))
+    pool = S.SeqPool([np.array([16, 1, 2], np.uint8), np.array([16, 1], np.uint8)])
+    with pytest.raises(S.PoyB200Error):
+        al.cost_2(pool, np.array([[0, 5]], np.int32))  # pair index out of range
+    lin = S.Align(CM.default_nucleotides())
+    b, _ = lin.make_batch(pool, np.array([[0, 1]], np.int32))
+    with pytest.raises(S.PoyB200Error):
+        lin._check(lin.L.poyb200_batch_cost_2(lin.h, __import__("ctypes").byref(b)))  # deltaw missing
+    al.close()
+    lin.close()
