@@ -70,6 +70,8 @@ struct poyb200_ctx {
     long long dstride = 0;
     size_t dir_budget = 0;
     int state_stride = 0;
+    int stripe_seq_bytes = 16;
+    bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
     // stats
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -181,6 +183,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     // direction bands of one chunk: at most a third of the free HBM, capped at 48 GB
     ctx->dir_budget = std::min<size_t>(free_b / 3, (size_t) 48 << 30);
     if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
+    if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     *out = ctx;
     return POYB200_OK;
 }
@@ -242,10 +245,11 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
 static inline uint32_t round16(uint32_t v) { return (v + 15u) & ~15u; }
 
 // Picks the fill kernel for one pair and fixes the layout of its direction band.
-static void choose_class(Task &t, bool affine, bool bt, int W) {
+static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, bool allow_stripe) {
     (void) bt;
-    if (stripe_choose(t, affine, W)) return;
+    if (allow_stripe && stripe_choose(t, affine, W, cm)) return;
     t.klass = KLASS_GENERIC;
+    t.dbase = t.dlo;
     t.G = 1;
     t.twoK = 0xFFFFu;
     t.BL = round16((uint32_t) (W + 2) / 2 + 1);
@@ -255,7 +259,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     if (n <= 0) return POYB200_OK;
     if (klass != KLASS_GENERIC) {
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stream);
+                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -311,7 +315,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     if (b->pool_bytes >= ((size_t) 1 << 32)) return fail(ctx, POYB200_EINVAL, "pool larger than 4 GiB");
     ctx->tasks.resize((size_t) b->n_pairs);
     long long maxcap = 16;
-    int maxW = 1;
+    int maxW = 1, max_stripe_len = 16;
     for (int p = 0; p < b->n_pairs; p++) {
         const int a = b->pairs[2 * p], c = b->pairs[2 * p + 1];
         if (a < 0 || a >= b->n_seqs || c < 0 || c >= b->n_seqs) return fail(ctx, POYB200_EINVAL, "pair index out of range");
@@ -341,8 +345,9 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             if (sw) t.flags |= TF_SWAPED;
         }
         const int W = t.dhi - t.dlo + 1;
-        choose_class(t, affine, bt, W);
-        maxW = std::max(maxW, W);
+        choose_class(t, affine, bt, W, ctx->dcm, ctx->allow_stripe);
+        if (t.klass != KLASS_GENERIC) max_stripe_len = std::max(max_stripe_len, std::max(t.lr, t.lc));
+        else maxW = std::max(maxW, W);
         maxcap = std::max<long long>(maxcap, (long long) la + lb + 2);
         ctx->tasks[p] = t;
     }
@@ -356,6 +361,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     }
     ctx->dstride = (maxcap + 15) & ~15ll;
     ctx->state_stride = maxW + 2;
+    ctx->stripe_seq_bytes = (max_stripe_len + 15) & ~15;
     // group by kernel class (stable: keeps the caller's order inside a class), then cut into chunks whose
     // direction bands fit the budget
     std::stable_sort(ctx->tasks.begin(), ctx->tasks.end(), [](const Task &x, const Task &y) { return x.klass < y.klass; });

@@ -41,13 +41,14 @@ struct Task {
     uint32_t pair;          // index in the caller's pair list
     uint64_t dir_off;       // byte offset of this pair's direction band
     uint32_t G, twoK, BL;   // direction addressing, see dir_index
+    int32_t dbase;          // diagonal held by lane 0, slot 0 (= dlo for the generic kernels)
     uint32_t klass;         // kernel class chosen by the planner
 };
 
 // Byte index of cell (i, j) inside a pair's direction band: anti-diagonal major, then lane-group chunk.
 // Stripe kernels write one BL-byte chunk per lane per step; the generic kernels use G = 1.
 __host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int j) {
-    uint32_t dd = (uint32_t) ((j - i) - t.dlo);
+    uint32_t dd = (uint32_t) ((j - i) - t.dbase);
     uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
     return ((uint64_t) (i + j) * t.G + lane) * t.BL + m;
 }

@@ -184,3 +184,56 @@ def test_error_paths(S):
         lin._check(lin.L.poyb200_batch_cost_2(lin.h, __import__("ctypes").byref(b)))  # deltaw missing
     al.close()
     lin.close()
+
+
+def _pairs_with_length_gap(rng, n, diffs, base_lo=30, base_hi=260, gap_amb=0.08):
+    seqs = []
+    for k in range(n):
+        la = int(rng.integers(base_lo, base_hi))
+        lb = la + int(diffs[k % len(diffs)])
+        a = rng.choice(np.array([1, 2, 4, 8], np.uint8), size=la)
+        b = rng.choice(np.array([1, 2, 4, 8], np.uint8), size=lb)
+        m = min(la, lb)
+        keep = rng.random(m) < 0.8
+        b[:m][keep] = a[:m][keep]  # related prefix so that the band matters
+        for s in (a, b):
+            s[rng.random(len(s)) < gap_amb] |= 16
+        a = np.concatenate([[16], a]).astype(np.uint8)
+        b = np.concatenate([[16], b]).astype(np.uint8)
+        seqs += ([a, b] if k % 2 == 0 else [b, a])
+    return seqs
+
+
+def test_affine_every_stripe_shape(S, checker_factory, monkeypatch):
+    """Length differences that select each register-stripe shape (W = 39 + max(40, |dl| + 8)), the spare-diagonal
+    (LOW) variants, and the generic kernel beyond the widest shape; then the same batch forced through the generic
+    kernels only."""
+    from poyd_b200 import cost_matrix as CM
+
+    cm = CM.nucleotides(1, 2, 3)
+    rng = np.random.default_rng(31)
+    diffs = [0, 5, 32, 33, 40, 49, 50, 80, 81, 120, 145, 146, 200, 209, 210, 300, 337, 338, 400, 465, 466, 520, 700]
+    pool = S.SeqPool(_pairs_with_length_gap(rng, 4 * len(diffs), diffs))
+    pairs = np.arange(2 * 4 * len(diffs), dtype=np.int32).reshape(-1, 2)
+    chk = checker_factory(cm)
+    o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
+    oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
+    for force in ("0", "1"):
+        monkeypatch.setenv("POYB200_FORCE_GENERIC", force)
+        al = S.Align(cm)
+        g = al.align_affine_3(pool, pairs, ALL)
+        assert_aligned_equal(g, o, label=f"affine shapes force_generic={force}")
+        assert np.array_equal(al.cost_2(pool, pairs), oc), f"affine cost shapes force_generic={force}"
+        al.close()
+
+
+def test_affine_generic_matches_on_headline_shape(S, checker_factory, monkeypatch):
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    pool, pairs = synth.pair_batch(300, 500, seed=8, min_len=450, gap_ambiguity=0.05)
+    o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
+    monkeypatch.setenv("POYB200_FORCE_GENERIC", "1")
+    al = S.Align(cm)
+    assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), o, label="generic kernel, cfg2 shape")
+    al.close()
