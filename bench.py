@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the batched pairwise median DP (BASELINE.json `metric`) on N B200s.
+
+A step = one pass of the hot path (algn_CAML_align_affine_3 for every pair: affine fill in the reference's band,
+traceback, median / medianwg / aligned pair) over one batch of synthetic pairs -- configs[1] of BASELINE.json:
+500 bp DNA, 10 % substitutions, 2 % indels, subst 1 / indel 2 / gap opening 3.
+
+  value      cells / second with the batch already resident in HBM (kernels only, CUDA events, max over ranks)
+  e2e        the same metric through the C ABI with HOST buffers: plan + H2D + kernels + D2H every step
+  roofline   the dominant kernel (the affine stripe fill) against the measured HBM peak, as the contract asks,
+             plus `roofline_int32`: the same kernel against the measured INT32 ALU throughput, which is the
+             bound that actually applies to this integer min-plus recurrence (BASELINE.json north_star)
+  cpu_baseline  the compiled reference algn.c (oracle/_ref) on all host cores, on a bounded sample
+
+`--impl reference` times the reference's own CPU implementation instead (the driver computes the ratio).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GCUPS (band cells/s, batched pairwise affine median DP: align_affine_3 fill + traceback + median)"
+UNIT = "GCUPS"
+OPS_PER_CELL = 50  # integer ops per affine_3 cell with traceback, counted from src/algn.c
+
+
+def workload(n_pairs: int, seed: int):
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512)
+    return cm, pool, pairs
+
+
+def total_cells(pool, pairs) -> int:
+    """Cells the reference visits for the batch: a pure function of the two lengths."""
+    from poyd_b200 import sequence as S
+
+    la, lb = pool.len[pairs[:, 0]], pool.len[pairs[:, 1]]
+    key = la.astype(np.int64) * 65536 + lb
+    uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    per = np.array([S.cells_affine(int(k >> 16), int(k & 65535)) for k in uniq], dtype=np.int64)
+    return int((per * cnt).sum())
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(cm, pool, pairs, sample: int, threads: int, steps: int = 1, warmup: int = 0):
+    """Times the reference's CPU implementation (compiled algn.c if oracle/_ref exists, else the port)."""
+    from oracle import oracle
+
+    oracle.build(ref=True)
+    chk = oracle.best_checker(cm)
+    sample = min(sample, len(pairs))
+    sub = pairs[:sample]
+    cells = total_cells(pool, sub)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        chk.batch(3, pool.pool, pool.off, pool.len, sub, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": cells / sec * 1e-9, "unit": UNIT, "cores": threads, "kind": chk.kind,
+            "sample": f"first {sample} pairs of the workload, all outputs, {threads} threads"}, sec
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            # median over the samples taken under load (above 60 % of the maximum seen)
+            hi = [x for x in sm if x >= 0.6 * max(sm)]
+            out["sm_mhz"] = float(np.median(hi))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = host_threads()
+
+    if args.impl == "reference":
+        # rank 0 alone runs the CPU arm; the other ranks exit without work
+        if rank != 0:
+            return
+        sample = args.cpu_sample or max(2000, 1500 * threads)
+        cm, pool, pairs = workload(sample, seed=2)
+        base, sec = cpu_arm(cm, pool, pairs, sample, threads, steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "configs[1]: DNA pairs 500 bp, affine gaps (1/2, gap opening 3), "
+                                       "align_affine_3 with all outputs", "pairs_per_step": sample,
+                           "note": "CPU arm: bounded sample of the same workload per step"},
+                "cpu_baseline": dict(base),
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from poyd_b200 import build as _build, sequence as S
+
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+
+    cm, pool, pairs = workload(args.pairs, seed=2 + rank)  # pair shards: each rank owns its own pairs
+    cells = total_cells(pool, pairs)
+    al = S.Align(cm, device=local_rank)
+    want = S.WANT_MEDIAN | S.WANT_MEDIANWG | S.WANT_ALIGNED
+
+    # pinned host buffers for the end-to-end leg
+    def pinned(arr):
+        return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+
+    ppool = S.SeqPool.__new__(S.SeqPool)
+    keep = [pinned(pool.pool), pinned(pool.off), pinned(pool.len), pinned(pairs)]
+    ppool.pool, ppool.off, ppool.len = keep[0].numpy(), keep[1].numpy(), keep[2].numpy()
+    ppairs = keep[3].numpy()
+    batch, res = al.make_batch(ppool, ppairs, want=want, outputs=False)
+    n = len(ppairs)
+    stride = 1008
+    out_t = {k: torch.empty((n, stride), dtype=torch.uint8, pin_memory=True) for k in ("median", "medianwg", "a", "b")}
+    cost_t = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    lens_t = torch.empty((n, 4), dtype=torch.int32, pin_memory=True)
+    batch.cost, batch.out_len, batch.out_stride = cost_t.data_ptr(), lens_t.data_ptr(), stride
+    batch.median, batch.medianwg = out_t["median"].data_ptr(), out_t["medianwg"].data_ptr()
+    batch.aligned_a, batch.aligned_b = out_t["a"].data_ptr(), out_t["b"].data_ptr()
+    h2d = int(ppool.pool.nbytes + n * 56)
+    d2h = int(4 * n * stride + n * 4 + n * 16)
+
+    stream = torch.cuda.ExternalStream(al.L.poyb200_stream(al.h), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident leg: stage once, time K passes of the kernels ------------------------------------
+    al.stage(S.MODE_ALIGN_AFFINE_3, batch)
+    al.sync()
+    for _ in range(args.warmup):
+        al.run()
+    al.sync()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = al.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fill_ms, trace_ms = 0.0, 0.0
+    e0.record(stream)
+    for _ in range(args.steps):
+        al.run()
+    e1.record(stream)
+    al.sync()
+    barrier()
+    launches = al.launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    f_ms, t_ms = al.last_run_ms()  # the last pass, per phase
+    fill_launches = max(1, (launches // args.steps) // 2)
+    dev_ms_max = max_over_ranks(dev_ms)
+    total_cells_all = sum_over_ranks(float(cells))
+    value = total_cells_all / (dev_ms_max * 1e-3) * 1e-9
+
+    # ---- end-to-end leg: host buffers in, host buffers out, every step ---------------------------------------
+    for _ in range(max(1, args.warmup - 1)):
+        al.stage(S.MODE_ALIGN_AFFINE_3, batch)
+        al.run()
+        al.fetch()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        al.stage(S.MODE_ALIGN_AFFINE_3, batch)
+        al.run()
+        al.fetch()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    e2e_max = max_over_ranks(e2e_s)
+    e2e_value = total_cells_all / e2e_max * 1e-9
+    checksum = int(cost_t.numpy().astype(np.int64).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    add_g, mm_g, mix_g = al.int32_peak()
+    # algorithmic bytes of the fill kernel per pair: both operands in, one direction byte per band cell out
+    # (the band is re-read by the traceback kernel, not by this one)
+    alg_bytes = float(pool.len[pairs[:, 0]].astype(np.int64).sum() + pool.len[pairs[:, 1]].astype(np.int64).sum()) + float(cells)
+    fill_s = f_ms * 1e-3
+    roof = {"bound": "hbm", "achieved": alg_bytes / fill_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+            "kernel": "aff_stripe_kernel<5,8,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
+            "note": "integer min-plus recurrence: ALU-bound, see roofline_int32"}
+    gops = cells * OPS_PER_CELL / fill_s * 1e-9
+    roof_int = {"bound": "int32_alu", "achieved": gops, "peak": add_g, "unit": "Gop/s", "frac": gops / add_g,
+                "ops_per_cell": OPS_PER_CELL, "peak_source": "measured live: dependent-free add.s32 chains (poyb200_int32_peak)",
+                "peak_minmax_gops": mm_g, "peak_minplus_mix_gops": mix_g, "kernel_gcups": cells / fill_s * 1e-9}
+    base = None
+    if not args.skip_cpu:
+        sample = args.cpu_sample or max(2000, 1500 * threads)
+        base, _ = cpu_arm(cm, pool, pairs, sample, threads)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, "
+                               "gap opening 3), align_affine_3 = fill + traceback + median/medianwg/aligned pair",
+                   "pairs_per_gpu_per_step": n, "cells_per_gpu_per_step": cells, "sharding": f"pairs x{world}",
+                   "l2": "inputs (pool + direction bands, > 1 GB) exceed the 126 MB L2 between iterations"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_max * 1e3, "outputs": "cost, median, medianwg, aligned a, aligned b (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "phase_ms": {"fill": f_ms, "traceback": t_ms},
+        "roofline": roof, "roofline_int32": roof_int, "clocks": clocks, "cost_checksum": checksum,
+    }
+    if base is not None:
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    al.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

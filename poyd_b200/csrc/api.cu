@@ -75,7 +75,9 @@ struct poyb200_ctx {
     // stats
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float ms[2] = {0.f, 0.f};
+    std::vector<cudaEvent_t> chunk_ev;  // 3 per chunk: before fill, after fill, after traceback
+    size_t timed_chunks = 0;
+    bool timing = true;                 // POYB200_TIMING=0 drops the per-chunk events
 };
 
 #define CK(call)                                                                           \
@@ -184,6 +186,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     ctx->dir_budget = std::min<size_t>(free_b / 3, (size_t) 48 << 30);
     if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
+    if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
     *out = ctx;
     return POYB200_OK;
 }
@@ -197,6 +200,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->chunk_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -430,9 +434,15 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want};
-    const bool single = ctx->chunks.size() == 1;
-    if (single) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    while (ctx->timing && ctx->chunk_ev.size() < 3 * ctx->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->chunk_ev.push_back(e);
+    }
+    ctx->timed_chunks = ctx->timing ? ctx->chunks.size() : 0;
+    size_t ci = 0;
     for (const Chunk &ch : ctx->chunks) {
+        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci], ctx->stream));
         // one fill launch per kernel class present in the chunk
         size_t k = ch.begin;
         while (k < ch.end) {
@@ -443,7 +453,7 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
             if (rc) return rc;
             k = e;
         }
-        if (single) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 1], ctx->stream));
         if (bt) {
             const int nt = (int) (ch.end - ch.begin);
             const int blocks = (nt + 127) / 128;
@@ -456,8 +466,9 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
             ctx->launches++;
             CK(cudaGetLastError());
         }
+        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 2], ctx->stream));
+        ci++;
     }
-    if (single) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     return POYB200_OK;
 }
 
@@ -472,10 +483,14 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
     if (!ctx || !ms) return POYB200_EINVAL;
     cudaSetDevice(ctx->device);
     ms[0] = ms[1] = 0.f;
-    if (ctx->chunks.size() != 1) return POYB200_OK;
-    CK(cudaEventSynchronize(ctx->ev[2]));
-    CK(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
-    CK(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+    for (size_t c = 0; c < ctx->timed_chunks; c++) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventSynchronize(ctx->chunk_ev[3 * c + 2]));
+        CK(cudaEventElapsedTime(&a, ctx->chunk_ev[3 * c], ctx->chunk_ev[3 * c + 1]));
+        CK(cudaEventElapsedTime(&b, ctx->chunk_ev[3 * c + 1], ctx->chunk_ev[3 * c + 2]));
+        ms[0] += a;
+        ms[1] += b;
+    }
     return POYB200_OK;
 }
 
