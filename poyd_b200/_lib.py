@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libpoyb200.so")
+SO = os.environ.get("POYB200_SO") or os.path.join(HERE, "libpoyb200.so")  # override: experiments only
 
 u8p = C.POINTER(C.c_uint8)
 i32p = C.POINTER(C.c_int32)

@@ -71,6 +71,7 @@ struct poyb200_ctx {
     size_t dir_budget = 0;
     int state_stride = 0;
     int stripe_seq_bytes = 16;
+    int trace_threads_per_sm = 512;
     bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
     // stats
     int64_t launches = 0;
@@ -187,6 +188,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
+    if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
     *out = ctx;
     return POYB200_OK;
 }
@@ -375,8 +377,8 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         Task &t = ctx->tasks[k];
         size_t bytes = 0;
         if (bt) {
-            bytes = (size_t) (t.lr + t.lc - 1) * t.G * t.BL;
-            bytes = (bytes + 15) & ~(size_t) 15;
+            bytes = (size_t) dir_bytes(t);
+            bytes = (bytes + 63) & ~(size_t) 63;
         }
         if (off + bytes > ctx->dir_budget && k > begin) {
             ctx->chunks.push_back(Chunk{begin, k, off});
@@ -456,7 +458,9 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
         if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 1], ctx->stream));
         if (bt) {
             const int nt = (int) (ch.end - ch.begin);
-            const int blocks = (nt + 127) / 128;
+            // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
+            // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
+            const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
             if (affine)
                 aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
                                                                       ctx->d_dir.p, out);

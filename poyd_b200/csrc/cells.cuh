@@ -87,7 +87,7 @@ __device__ __forceinline__ int aff_cell(int ehl, int cbl, int evu, int cbu, int 
         // ASSIGN_MINIMUM :2251-2280, read with priority H > A > V > D (:2006-2012)
         const int f = min(min(eh, ev), min(eb, cb));
         const int mode = (eh == f) ? AM_H : (cb == f) ? AM_A : (ev == f) ? AM_V : AM_D;
-        byte |= mode | (nxt << 2);
+        byte |= (mode << 2) | nxt;
     }
     return byte;
 }

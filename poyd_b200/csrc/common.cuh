@@ -19,14 +19,16 @@ constexpr int TMPGAP = 16;           // src/algn.c:1711
 constexpr int D_ALIGN = 1, D_INSERT = 2, D_DELETE = 4;
 
 // affine direction byte (7 bits): what backtrace_affine (src/algn.c:1983-2097) would decide at this cell
-//   bits 1:0  mode entered from m_todo  : 0 horizontal, 1 align, 2 vertical, 3 diagonal   (priority :2006-2012)
-//   bits 3:2  mode after an align step  : 0 stay align, 1 horizontal, 2 diagonal, 3 vertical (priority :2049-2051)
+//   bits 1:0  mode after an align step  : 0 horizontal, 1 diagonal, 2 vertical, 3 stay align (priority :2049-2051)
+//   bits 3:2  mode entered from m_todo  : 0 horizontal, 1 align, 2 vertical, 3 diagonal     (priority :2006-2012)
 //   bit 4 END_HORIZONTAL, bit 5 END_VERTICAL, bit 6 END_BLOCK
+// The two 2-bit codes are the tie-break priorities themselves, so the stripe kernels get them for free as the
+// low bits of a min over tagged keys (stripe_kernels.cuh).
+constexpr int AN_H = 0, AN_D = 1, AN_V = 2, AN_A = 3;
 constexpr int AM_H = 0, AM_A = 1, AM_V = 2, AM_D = 3;
-constexpr int AN_A = 0, AN_H = 1, AN_D = 2, AN_V = 3;
 constexpr int AB_ENDH = 16, AB_ENDV = 32, AB_ENDB = 64;
-constexpr int AFF_LEFT_EDGE_BYTE = AM_V | AB_ENDV;   // DO_VERTICAL | END_VERTICAL   (:2476)
-constexpr int AFF_RIGHT_EDGE_BYTE = AM_H | AB_ENDH;  // DO_HORIZONTAL | END_HORIZONTAL (:2530)
+constexpr int AFF_LEFT_EDGE_BYTE = (AM_V << 2) | AB_ENDV;   // DO_VERTICAL | END_VERTICAL   (:2476)
+constexpr int AFF_RIGHT_EDGE_BYTE = (AM_H << 2) | AB_ENDH;  // DO_HORIZONTAL | END_HORIZONTAL (:2530)
 
 // task flags
 constexpr uint32_t TF_ROWS_ARE_B = 1;  // operand b sits on the rows: swap the aligned outputs back
@@ -47,10 +49,17 @@ struct Task {
 
 // Byte index of cell (i, j) inside a pair's direction band: anti-diagonal major, then lane-group chunk.
 // Stripe kernels write one BL-byte chunk per lane per step; the generic kernels use G = 1.
+// Anti-diagonals are tiled by 8: the 8 chunks a lane writes during steps 8k..8k+7 are contiguous (one 64-byte
+// line for BL = 8), so a traceback, which moves one or two anti-diagonals per step and drifts slowly across
+// diagonals, stays inside a line for several steps.
 __host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int j) {
-    uint32_t dd = (uint32_t) ((j - i) - t.dbase);
-    uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
-    return ((uint64_t) (i + j) * t.G + lane) * t.BL + m;
+    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j);
+    const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
+    return ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
+}
+// Bytes of one pair's direction band (T runs over 0 .. lr + lc - 2).
+__host__ __device__ __forceinline__ uint64_t dir_bytes(const Task &t) {
+    return (uint64_t) ((t.lr + t.lc - 1 + 7) >> 3) * 8 * t.G * t.BL;
 }
 
 struct DevCM {

@@ -39,47 +39,78 @@ constexpr int N_AFF_SHAPES = sizeof(AFF_SHAPES) / sizeof(AFF_SHAPES[0]);
 constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared memory
 
 constexpr int STRIPE_WARPS = 4;
+#ifndef STRIPE_MIN_BLOCKS
+#define STRIPE_MIN_BLOCKS 3
+#endif
+constexpr int STRIPE_LUT_BYTES = 16 * 17 * 8;  // == 16 * LUT_ROW_BYTES
+constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4;
+
+// All DP values are carried multiplied by 4, and each of the four states keeps a constant 2-bit tag in its low
+// bits: EH 0, CB 1, EV 2, EB 3.  The tags are the tie-break priorities of the reference's traceback:
+//   * ASSIGN_MINIMUM keeps every minimal state and backtrace_affine reads them H > A > V > D (:2006-2012), so
+//     min(EH, CB, EV, EB) over the tagged values yields the mode in its low two bits;
+//   * FILL_CLOSE_BLOCK_DIAGONAL keeps every minimal predecessor, read H > D > V > A (:2049-2051); the four
+//     candidates inherit the tags of the states they start from (0, 3, 2, 1) and two of them are re-tagged by
+//     +-2 (folded into constants), so the min yields that choice too.
+// Comparisons the reference makes between two candidates (extend < open) always see equal tags, so they are
+// exact.  HIGH_NUM becomes 4 000 000; nothing comes near 2^31.
+constexpr int HIGH4 = 4 * HIGH_NUM;
+constexpr int TAG_EH = 0, TAG_CB = 1, TAG_EV = 2, TAG_EB = 3;
+constexpr int LUT_ROW_BYTES = 17 * 8;  // 16 int2 entries + 1 pad: spreads the rows over the shared-memory banks
 
 struct AffWinRow {
-    int vx, gopge, gop, lut, gm;  // lut = (si & 15) << 4, gm = -(si has the gap bit)
+    int vx4;       // 4 * si_vertical_extension
+    int gopge4p1;  // 4 * (si_gap_opening + si_gap_extension) + 1   (CB tag 1 -> EV tag 2)
+    int gop4;      // 4 * si_gap_opening
+    int lut;       // byte offset of the row (si & 15) in the cost LUT
+    int gm;        // -1 when si carries the gap bit
 };
 struct AffWinCol {
-    int hx, gopg, gop, lut, gm;  // lut = sj & 15
+    int hx4;       // 4 * sj_horizontal_extension[j]
+    int gopg4m1;   // 4 * (gap_open_prec[j] + gap_row[j]) - 1       (CB tag 1 -> EH tag 0)
+    int gop4;      // 4 * gap_open_prec[j]
+    int lut;       // byte offset of the column (sj & 15) inside a LUT row
+    int gm;
 };
 
-// Fast form of aff_cell for DNA matrices (lcm = 5, gap = 16 = TMPGAP, codes < 32), where "has the gap bit",
-// "si_base != si_no_gap" and "si & TMPGAP" are the same predicate.
+// One interior cell on tagged, x4 values, for DNA matrices (lcm = 5, gap = 16 = TMPGAP, codes < 32), where "has
+// the gap bit", "si_base != si_no_gap" and "si & TMPGAP" are the same predicate.  d = {4*cost, 4*cost - 2}.
+// Returns the direction byte (common.cuh).
 template <bool BT>
 __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, int cbd, int evd, int ehd, int ebd,
-                                            const AffWinRow &r, const AffWinCol &c, int dcost, int go, int &cb, int &ev,
+                                            const AffWinRow &r, const AffWinCol &c, int2 d, int go8, int &cb, int &ev,
                                             int &eh, int &eb) {
-    int byte;
-    int x = ehl + c.hx, y = cbl + c.gopg;
+    int byte = 0;
+    // FILL_EXTEND_HORIZONTAL :1765-1787 -- extend wins only when strictly cheaper
+    int x = ehl + c.hx4, y = cbl + c.gopg4m1;
     eh = min(x, y);
-    byte = (x < y) ? 0 : AB_ENDH;
-    x = evu + r.vx;
-    y = cbu + r.gopge;
+    if (BT) byte = (x < y) ? 0 : AB_ENDH;
+    // FILL_EXTEND_VERTICAL :1813-1830
+    x = evu + r.vx4;
+    y = cbu + r.gopge4p1;
     ev = min(x, y);
-    byte |= (x < y) ? 0 : AB_ENDV;
-    const int bothm = r.gm & c.gm;          // -1 when both carry the gap bit
-    const int dg = HIGH_NUM & ~bothm;       // 0 or HIGH_NUM
+    if (BT) byte |= (x < y) ? 0 : AB_ENDV;
+    // FILL_EXTEND_BLOCK_DIAGONAL :1861-1882 / _NOBT :1837-1854
+    const int bothm = r.gm & c.gm;     // -1 when both carry the gap bit
+    const int dg = HIGH4 & ~bothm;     // 0 or 4*HIGH_NUM
     if (BT) {
-        eb = min(ebd, cbd) + dg;            // ext and open share the addend (:1871-1872)
-        byte |= (ebd < cbd) ? 0 : AB_ENDB;
+        const int c2 = cbd + 2;        // CB tag 1 -> EB tag 3
+        eb = min(ebd, c2) + dg;        // extend and open share the addend (:1871-1872)
+        byte |= (ebd < c2) ? 0 : AB_ENDB;
     } else {
-        const int odg = dg | ((2 * go) & bothm);  // both ? 2*go : HIGH_NUM  (:1846)
-        eb = min(ebd + dg, cbd + odg);
+        const int odg = dg | (go8 & bothm);  // both ? 2*go : HIGH_NUM (:1846; its flag2 can never hold with flag)
+        eb = min(ebd + dg, cbd + odg + 2);
     }
-    const int a0 = cbd + dcost;
-    const int a1 = evd + dcost + (c.gop & r.gm);
-    const int a2 = ehd + dcost + (r.gop & c.gm);
-    const int a3 = ebd + dcost + max(r.gop, c.gop);
-    cb = min(min(a0, a1), min(a2, a3));
+    // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977, candidates tagged H 0, D 1, V 2, A 3
+    const int a2 = ehd + d.x + (r.gop4 & c.gm);
+    const int a3 = ebd + d.y + max(r.gop4, c.gop4);
+    const int a1 = evd + d.x + (c.gop4 & r.gm);
+    const int a0 = cbd + d.x + 2;
+    const int ck = min(min(a0, a1), min(a2, a3));
+    cb = (ck & ~3) | TAG_CB;
     if (BT) {
-        const int nxt = (a2 == cb) ? AN_H : (a3 == cb) ? AN_D : (a1 == cb) ? AN_V : AN_A;
-        const int f = min(min(eh, ev), min(eb, cb));
-        const int mode = (eh == f) ? AM_H : (cb == f) ? AM_A : (ev == f) ? AM_V : AM_D;
-        byte |= mode | (nxt << 2);
+        const int fk = min(min(eh, ev), min(eb, cb));  // ASSIGN_MINIMUM :2251-2280
+        byte |= (ck & 3) | ((fk & 3) << 2);
     }
     return byte;
 }
@@ -87,7 +118,6 @@ __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, 
 template <int K, int G, bool BT, bool LOW>
 struct AffStripe {
     static constexpr int Q = 2 * K;
-    static constexpr int BL = (K <= 4) ? 4 : 8;
 
     // per-lane state
     int cb[Q], ev[Q], eh[Q], eb[Q];
@@ -96,20 +126,20 @@ struct AffStripe {
     int last_ci, last_cj;  // codes of the newest row / column in the windows
     // per-pair constants
     const uint8_t *si, *sj;  // shared memory copies
-    const int *lut, *prep, *get;
-    int nr, nc, go, lane, qlow;
-    unsigned gmask;
+    const uint8_t *lut;      // int2 entries, rows of LUT_ROW_BYTES
+    const int *prep, *get;   // 4 * prepend[c], 4 * cost[c][gap]
+    int nr, nc, go4, lane, qlow;
 
     __device__ __forceinline__ AffWinRow make_row(int i) {
         const int ii = min(max(i, 0), nr);
         const int ci = si[ii], pi = last_ci;
         last_ci = ci;
         AffWinRow r;
-        const int ge = get[ci];
-        r.gop = (!(pi & 16) && (ci & 16)) ? 0 : go;
-        r.vx = (i > 1 && (pi & 16) && !(ci & 16)) ? r.gop + ge : ge;
-        r.gopge = r.gop + ge;
-        r.lut = (ci & 15) << 4;
+        const int ge4 = get[ci];
+        r.gop4 = (!(pi & 16) && (ci & 16)) ? 0 : go4;  // HAS_GAP_OPENING :1730
+        r.vx4 = (i > 1 && (pi & 16) && !(ci & 16)) ? r.gop4 + ge4 : ge4;  // :2483-2485
+        r.gopge4p1 = r.gop4 + ge4 + 1;
+        r.lut = (ci & 15) * LUT_ROW_BYTES;
         r.gm = -((ci >> 4) & 1);
         return r;
     }
@@ -118,11 +148,11 @@ struct AffStripe {
         const int cj = sj[jj], pj = last_cj;
         last_cj = cj;
         AffWinCol c;
-        const int g = prep[cj];
-        c.gop = (!(pj & 16) && (cj & 16)) ? 0 : go;
-        c.hx = ((pj & 16) && !(cj & 16) && j != 1) ? c.gop + g : g;
-        c.gopg = c.gop + g;
-        c.lut = cj & 15;
+        const int g4 = prep[cj];
+        c.gop4 = (!(pj & 16) && (cj & 16)) ? 0 : go4;
+        c.hx4 = ((pj & 16) && !(cj & 16) && j != 1) ? c.gop4 + g4 : g4;  // :2454-2458
+        c.gopg4m1 = c.gop4 + g4 - 1;
+        c.lut = (cj & 15) * 8;
         c.gm = -((cj >> 4) & 1);
         return c;
     }
@@ -151,81 +181,80 @@ struct AffStripe {
                                            int &ncb, int &nev, int &neh, int &neb) {
         if (LOW) {
             if (q < qlow) {  // below the stripe: the left-edge rule (:2486-2494)
-                ncb = HIGH_NUM; neh = HIGH_NUM; neb = HIGH_NUM;
-                nev = evu + r.vx;
+                ncb = HIGH4 + TAG_CB; neh = HIGH4 + TAG_EH; neb = HIGH4 + TAG_EB;
+                nev = evu + r.vx4;
             }
         }
         if (BOUNDARY) {
             if (i == 0) {
                 if (j == 0) {  // :2194-2198
-                    ncb = 0; neb = 0; neh = go; nev = go;
+                    ncb = TAG_CB; neb = TAG_EB; neh = go4 + TAG_EH; nev = go4 + TAG_EV;
                 } else {       // :2212-2217
-                    const int rr = ehl + (c.gopg - c.gop);
-                    neh = rr; ncb = rr; nev = HIGH_NUM; neb = HIGH_NUM;
+                    const int rr = ehl + (c.gopg4m1 + 1 - c.gop4);
+                    neh = rr; ncb = rr + TAG_CB; nev = HIGH4 + TAG_EV; neb = HIGH4 + TAG_EB;
                 }
             } else if (j == 0) {  // column 0 = the left-edge cells of rows 1..39 (:2486-2494)
-                ncb = HIGH_NUM; neh = HIGH_NUM; neb = HIGH_NUM;
-                nev = evu + r.vx;
+                ncb = HIGH4 + TAG_CB; neh = HIGH4 + TAG_EH; neb = HIGH4 + TAG_EB;
+                nev = evu + r.vx4;
             }
         }
     }
 
-    // One double step.  Returns the packed direction bytes of the even step in lo and of the odd step in hi.
+    // One double step; the K direction bytes of each step come back as two 32-bit words (bytes 0-3, 4-7).
     template <bool BOUNDARY>
-    __device__ __forceinline__ void double_step(int i0, int j0, unsigned long long &dir_even, unsigned long long &dir_odd) {
+    __device__ __forceinline__ void double_step(int i0, int j0, uint32_t (&de)[2], uint32_t (&dod)[2]) {
+        const int go8 = 2 * go4;
         // ---- even step: q = 2m, cell (i0 - m, j0 + m)
-        int in_eh = __shfl_up_sync(gmask, eh[Q - 1], 1, G);
-        int in_cb = __shfl_up_sync(gmask, cb[Q - 1], 1, G);
-        if (lane == 0) { in_eh = HIGH_NUM; in_cb = HIGH_NUM; }  // the left-edge cells (:2487, :2494)
-        unsigned long long de = 0, dod = 0;
+        int in_eh = __shfl_up_sync(0xffffffffu, eh[Q - 1], 1, G);
+        int in_cb = __shfl_up_sync(0xffffffffu, cb[Q - 1], 1, G);
+        if (lane == 0) { in_eh = HIGH4 + TAG_EH; in_cb = HIGH4 + TAG_CB; }  // the left-edge cells (:2487, :2494)
+        de[0] = de[1] = dod[0] = dod[1] = 0;
 #pragma unroll
         for (int m = 0; m < K; m++) {
             const int q = 2 * m;
             const int ehl = (m == 0) ? in_eh : eh[q - 1], cbl = (m == 0) ? in_cb : cb[q - 1];
             const int evu = ev[q + 1], cbu = cb[q + 1];
-            const int dcost = lut[R[m].lut + C[m].lut];
+            const int2 d = *reinterpret_cast<const int2 *>(lut + R[m].lut + C[m].lut);
             int ncb, nev, neh, neb;
-            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m], dcost, go, ncb, nev,
+            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m], d, go8, ncb, nev,
                                               neh, neb);
             fixups<BOUNDARY>(q, i0 - m, j0 + m, ehl, evu, R[m], C[m], ncb, nev, neh, neb);
             cb[q] = ncb; ev[q] = nev; eh[q] = neh; eb[q] = neb;
-            if (BT) de |= (unsigned long long) byte << (8 * m);
+            if (BT) de[m >> 2] |= (uint32_t) byte << (8 * (m & 3));
         }
         // ---- odd step: q = 2m + 1, cell (i0 - m, j0 + m + 1)
-        int in_ev = __shfl_down_sync(gmask, ev[0], 1, G);
-        int in_cbu = __shfl_down_sync(gmask, cb[0], 1, G);
+        const int in_ev = __shfl_down_sync(0xffffffffu, ev[0], 1, G);
+        const int in_cbu = __shfl_down_sync(0xffffffffu, cb[0], 1, G);
 #pragma unroll
         for (int m = 0; m < K; m++) {
             const int q = 2 * m + 1;
             const int ehl = eh[q - 1], cbl = cb[q - 1];
             const int evu = (m == K - 1) ? in_ev : ev[q + 1], cbu = (m == K - 1) ? in_cbu : cb[q + 1];
-            const int dcost = lut[R[m].lut + C[m + 1].lut];
+            const int2 d = *reinterpret_cast<const int2 *>(lut + R[m].lut + C[m + 1].lut);
             int ncb, nev, neh, neb;
-            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m + 1], dcost, go, ncb,
+            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m + 1], d, go8, ncb,
                                               nev, neh, neb);
             if (m == K - 1) {
                 if (lane == G - 1) {  // diagonal dhi + 1: poisoned (:2531-2535)
-                    ncb = HIGH_NUM; nev = HIGH_NUM; neh = HIGH_NUM; neb = HIGH_NUM;
+                    ncb = HIGH4 + TAG_CB; nev = HIGH4 + TAG_EV; neh = HIGH4 + TAG_EH; neb = HIGH4 + TAG_EB;
                 }
             }
             fixups<BOUNDARY>(q, i0 - m, j0 + m + 1, ehl, evu, R[m], C[m + 1], ncb, nev, neh, neb);
             cb[q] = ncb; ev[q] = nev; eh[q] = neh; eb[q] = neb;
-            if (BT) dod |= (unsigned long long) byte << (8 * m);
+            if (BT) dod[m >> 2] |= (uint32_t) byte << (8 * (m & 3));
         }
-        dir_even = de;
-        dir_odd = dod;
     }
 };
 
 template <int BL>
-__device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long v) {
-    if (BL == 4) *reinterpret_cast<uint32_t *>(p) = (uint32_t) v;
-    else *reinterpret_cast<unsigned long long *>(p) = v;
+__device__ __forceinline__ void store_dir(uint8_t *p, const uint32_t (&v)[2]) {
+    if (BL == 4) *reinterpret_cast<uint32_t *>(p) = v[0];
+    else *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
 }
 
 // seq_bytes: shared-memory bytes reserved per operand (multiple of 16, >= the longest sequence of the launch).
 template <int K, int G, bool BT>
-__global__ void __launch_bounds__(STRIPE_WARPS * 32) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
+__global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                        const uint8_t *__restrict__ pool,
                                                                        uint8_t *__restrict__ dir, int *__restrict__ out_cost,
                                                                        int seq_bytes) {
@@ -233,20 +262,22 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32) aff_stripe_kernel(const Tas
     constexpr int Q = 2 * K;
     constexpr int BL = (K <= 4) ? 4 : 8;
     extern __shared__ __align__(16) uint8_t smem[];
-    int *s_lut = reinterpret_cast<int *>(smem);  // 256 ints: cost[(a & 15) << lcm | (b & 15)]
-    int *s_prep = s_lut + 256;                    // 32 ints
-    int *s_get = s_prep + 32;                     // 32 ints: cost[c << lcm | gap]
+    uint8_t *s_lut = smem;  // 16 rows of LUT_ROW_BYTES: int2 {4*cost, 4*cost - 2} for cost[(a & 15) << lcm | (b & 15)]
+    int *s_prep = reinterpret_cast<int *>(smem + STRIPE_LUT_BYTES);  // 32 ints: 4 * prepend[c]
+    int *s_get = s_prep + 32;                                         // 32 ints: 4 * cost[c << lcm | gap]
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_get + 32);
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_lut[k] = __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
+        *reinterpret_cast<int2 *>(s_lut + (k >> 4) * LUT_ROW_BYTES + (k & 15) * 8) = make_int2(c4, c4 - 2);
+    }
     for (int k = threadIdx.x; k < 32; k += blockDim.x) {
-        s_prep[k] = __ldg(cm.prepend + k);
-        s_get[k] = __ldg(cm.cost + (k << cm.lcm) + cm.gap);
+        s_prep[k] = 4 * __ldg(cm.prepend + k);
+        s_get[k] = 4 * __ldg(cm.cost + (k << cm.lcm) + cm.gap);
     }
     __syncthreads();
 
     const int warp_in_block = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
     const int grp = lane32 / G, lane = lane32 % G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     uint8_t *my_seq = s_seq + (size_t) ((warp_in_block * GPW + grp) * 2) * seq_bytes;
     const int warp_global = blockIdx.x * STRIPE_WARPS + warp_in_block;
     const int total_warps = gridDim.x * STRIPE_WARPS;
@@ -298,41 +329,45 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32) aff_stripe_kernel(const Tas
             AffStripe<K, G, BT, LOW> S;
             S.si = my_seq; S.sj = my_seq + seq_bytes;
             S.lut = s_lut; S.prep = s_prep; S.get = s_get;
-            S.nr = nr; S.nc = nc; S.go = cm.gap_open; S.lane = lane; S.gmask = gmask;
+            S.nr = nr; S.nc = nc; S.go4 = 4 * cm.gap_open; S.lane = lane;
             S.qlow = min(max(qlow_all - lane * Q, 0), Q);
 #pragma unroll
-            for (int q = 0; q < Q; q++) { S.cb[q] = HIGH_NUM; S.ev[q] = HIGH_NUM; S.eh[q] = HIGH_NUM; S.eb[q] = HIGH_NUM; }
+            for (int q = 0; q < Q; q++) {
+                S.cb[q] = HIGH4 + TAG_CB; S.ev[q] = HIGH4 + TAG_EV; S.eh[q] = HIGH4 + TAG_EH; S.eb[q] = HIGH4 + TAG_EB;
+            }
             int u = u_begin;
             int i0 = u - lane * K, j0 = u + d0 + lane * K;
             S.init_windows(i0, j0);
             int u_b = max(G * K, 1 - d0);  // from here on every lane has i >= 1 and j >= 1 (warp-uniform maximum)
 #pragma unroll
             for (int o = G; o < 32; o <<= 1) u_b = max(u_b, __shfl_xor_sync(0xffffffffu, u_b, o));
-            auto emit = [&](unsigned long long de, unsigned long long dod) {
+            // chunk address of (step T, this lane): tiles of 8 steps, see dir_index (common.cuh)
+            auto chunk = [&](int T) { return dbase + (((size_t) (T >> 3) * G + lane) * 8 + (T & 7)) * BL; };
+            auto emit = [&](const uint32_t (&de)[2], const uint32_t (&dod)[2]) {
                 if (BT) {
                     const int te = 2 * u + d0;
                     if (u >= u_first && u <= u_last) {
-                        if (te >= 0) store_dir<BL>(dbase + ((size_t) te * G + lane) * BL, de);
-                        if (te + 1 <= nr + nc) store_dir<BL>(dbase + ((size_t) (te + 1) * G + lane) * BL, dod);
+                        if (te >= 0) store_dir<BL>(chunk(te), de);
+                        if (te + 1 <= nr + nc) store_dir<BL>(chunk(te + 1), dod);
                     }
                 }
                 if (u == u_last && lane == lane_f) {
                     int r = 0;
 #pragma unroll
                     for (int q = 0; q < Q; q++)
-                        if (q == q_f) r = min(min(S.cb[q], S.ev[q]), min(S.eh[q], S.eb[q]));
+                        if (q == q_f) r = min(min(S.cb[q], S.ev[q]), min(S.eh[q], S.eb[q])) >> 2;
                     result = r;
                 }
             };
             for (; u < min(u_b, u_end + 1); u++) {
-                unsigned long long de, dod;
+                uint32_t de[2], dod[2];
                 S.template double_step<true>(i0, j0, de, dod);
                 emit(de, dod);
                 i0++; j0++;
                 S.slide_windows(i0, j0);
             }
             for (; u <= u_end; u++) {
-                unsigned long long de, dod;
+                uint32_t de[2], dod[2];
                 S.template double_step<false>(i0, j0, de, dod);
                 emit(de, dod);
                 i0++; j0++;
@@ -377,7 +412,7 @@ template <int K, int G>
 static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                                        int *cost, int sm_count, int seq_bytes, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
-    const size_t smem = (256 + 64) * sizeof(int) + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
+    const size_t smem = STRIPE_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
     auto kern = bt ? aff_stripe_kernel<K, G, true> : aff_stripe_kernel<K, G, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

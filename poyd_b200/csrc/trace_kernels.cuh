@@ -19,7 +19,7 @@ struct RevWriter {
         n++;
         acc |= ((uint32_t) v & 0xffu) << ((pos & 3) * 8);
         if ((pos & 3) == 0) {
-            *reinterpret_cast<uint32_t *>(base + pos) = acc;
+            __stcs(reinterpret_cast<uint32_t *>(base + pos), acc);  // streaming: written once, read by the host
             acc = 0;
         }
     }
@@ -32,8 +32,7 @@ struct RevWriter {
 __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
                                                             const uint8_t *__restrict__ dir, OutPtrs out) {
-    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= ntasks) return;
+  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
     const Task t = tasks[ti];
     const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
         else if (d > t.dhi) b = AFF_RIGHT_EDGE_BYTE;
         else b = __ldg(dbase + dir_index(t, i, j));
         if (mode == M_TODO) {
-            const int m = b & 3;
+            const int m = (b >> 2) & 3;
             mode = (m == AM_H) ? M_HORI : (m == AM_A) ? M_ALGN : (m == AM_V) ? M_VERT : M_DIAG;
         } else if (mode == M_VERT) {
             if (b & AB_ENDV) mode = M_TODO;
@@ -83,7 +82,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
             i--; j--;
             ic = si[i]; jc = sj[j];
         } else {
-            const int nx = (b >> 2) & 3;
+            const int nx = b & 3;
             if (nx == AN_H) mode = M_HORI;
             else if (nx == AN_D) mode = M_DIAG;
             else if (nx == AN_V) mode = M_VERT;
@@ -117,6 +116,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     if (w_al) { ri.flush(); rj.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
+  }
 }
 
 // backtrack_2d, linear branch (src/algn.c:3606-3665), fused with algn_ancestor_2 (:4126-4147, the
@@ -125,8 +125,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
 __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
                                                             const uint8_t *__restrict__ dir, OutPtrs out) {
-    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= ntasks) return;
+  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
     const Task t = tasks[ti];
     const uint8_t *s1 = pool + t.off_r, *s2 = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;
@@ -166,6 +165,7 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     if (w_al) { r1.flush(); r2.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
+  }
 }
 
 // Stand-alone medians of already aligned pairs: which 0 algn_ancestor_2 (:4126-4147, including
