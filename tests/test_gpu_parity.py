@@ -237,3 +237,51 @@ def test_affine_generic_matches_on_headline_shape(S, checker_factory, monkeypatc
     al = S.Align(cm)
     assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), o, label="generic kernel, cfg2 shape")
     al.close()
+
+
+def test_gpu_replays_reference_golden(S):
+    """The committed fixtures (outputs of the compiled reference) through the C ABI: needs no checker at all."""
+    import os
+
+    from golden_util import golden_files, load
+
+    for path in golden_files():
+        cm, pool, pairs, mode, deltaw, ref = load(path)
+        al = S.Align(cm)
+        name = os.path.basename(path)
+        if mode == 3:
+            assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), ref, label=name)
+        elif mode == 2:
+            assert np.array_equal(al.cost_2(pool, pairs), ref["cost"]), name
+        elif mode == 1:
+            assert_aligned_equal(al.align_2(pool, pairs, ALL, deltaw=deltaw, raw_deltaw=True), ref, label=name)
+            assert np.array_equal(al.cost_2(pool, pairs, deltaw=deltaw, raw_deltaw=True), ref["cost"]), name
+        al.close()
+
+
+def test_large_batch_properties(S):
+    """BASELINE.json size (1M pairs is run by bench.py; here 120k): size-independent properties.
+    * symmetry of the cost-only kernel in its operands (the C stub orders them by length, src/algn.c:2661);
+    * the traceback cost never exceeds ... equals the recomputed cost of its own alignment under the linear
+      model is not defined for affine_3, so the checked invariants are structural: aligned rows have equal
+      length, removing gaps from them gives back the inputs, and medianwg has that same length."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    pool, pairs = synth.pair_batch(120_000, 500, seed=41, min_len=450)
+    al = S.Align(cm)
+    c1 = al.cost_2(pool, pairs)
+    c2 = al.cost_2(pool, pairs[:, ::-1].copy())
+    assert np.array_equal(c1, c2)
+    r = al.align_affine_3(pool, pairs, ALL)
+    assert (r.lens[:, 2] == r.lens[:, 3]).all() and (r.lens[:, 1] == r.lens[:, 2]).all()
+    assert (r.lens[:, 0] <= r.lens[:, 1]).all()
+    stride = r.aligned_a.shape[1]
+    rng = np.random.default_rng(0)
+    for p in rng.integers(0, len(pairs), size=400):
+        for buf, k, s in ((r.aligned_a, 2, pairs[p, 0]), (r.aligned_b, 3, pairs[p, 1])):
+            row = buf[p, stride - r.lens[p, k]:]
+            body = row[1:]
+            assert row[0] == 16
+            assert np.array_equal(body[body != 16], pool.seq(s)[1:])
+    al.close()
