@@ -253,16 +253,18 @@ def main():
     value = total_cells_all / (dev_ms_max * 1e-3) * 1e-9
 
     # ---- end-to-end leg: host buffers in, host buffers out, every step ---------------------------------------
+    import ctypes
+
+    def e2e_call():
+        # the call a user of the C ABI makes: host buffers in, host buffers out
+        al._check(al.L.poyb200_batch_align_affine_3(al.h, ctypes.byref(batch)))
+
     for _ in range(max(1, args.warmup - 1)):
-        al.stage(S.MODE_ALIGN_AFFINE_3, batch)
-        al.run()
-        al.fetch()
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        al.stage(S.MODE_ALIGN_AFFINE_3, batch)
-        al.run()
-        al.fetch()
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
     barrier()

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/poyb200.h"
@@ -72,6 +73,12 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     int trace_threads_per_sm = 512;
+    int host_threads = 8;
+    size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
+    bool in_order = true;           // tasks[k].pair == k
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_done;
     bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
     // stats
     int64_t launches = 0;
@@ -181,6 +188,10 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
         return POYB200_ECUDA;
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
+    ctx->host_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // direction bands of one chunk: at most a third of the free HBM, capped at 48 GB
@@ -189,6 +200,8 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
+    if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
+    if (const char *s = getenv("POYB200_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(s));
     *out = ctx;
     return POYB200_OK;
 }
@@ -203,6 +216,10 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     for (auto &b : ctx->d_out) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->chunk_ev) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_done) cudaEventDestroy(e);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -298,6 +315,19 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
 // ---------------------------------------------------------------------------------------------------------
 // planning
 // ---------------------------------------------------------------------------------------------------------
+// Runs fn(lo, hi, slot) over [0, n) on up to `ctx->host_threads` threads.
+template <typename F>
+static void parallel_for(int nthreads, size_t n, F fn) {
+    if (nthreads <= 1 || n < 65536) {
+        fn((size_t) 0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([=] { fn(n * t / nthreads, n * (t + 1) / nthreads, t); });
+    for (auto &x : th) x.join();
+}
+
 static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
@@ -312,50 +342,79 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         return fail(ctx, POYB200_EMODEL, "linear entry point called with cost_model_type != 0");
     if (affine && ctx->hcm.lcm < 4)
         return fail(ctx, POYB200_EMODEL, "affine_3 indexes cost[(a&15) << lcm | (b&15)]: needs lcm >= 4");
-    for (int s = 0; s < b->n_seqs; s++) {
-        if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN)
-            return fail(ctx, POYB200_ESEQLEN, "sequence empty (no leading gap) or longer than 16384");
-        if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes)
-            return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
-    }
     if (b->pool_bytes >= ((size_t) 1 << 32)) return fail(ctx, POYB200_EINVAL, "pool larger than 4 GiB");
+    const int NT = ctx->host_threads;
+    struct Part {
+        int err = 0;
+        long long maxcap = 16;
+        int maxW = 1, max_stripe_len = 16;
+        bool in_order_class = true;
+        uint32_t klass_or = 0, klass_and = 0xffffffffu;
+    };
+    std::vector<Part> parts((size_t) std::max(1, NT));
+    parallel_for(NT, (size_t) b->n_seqs, [&](size_t lo, size_t hi, int slot) {
+        for (size_t s = lo; s < hi; s++) {
+            if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN) parts[slot].err = POYB200_ESEQLEN;
+            else if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes) parts[slot].err = POYB200_EINVAL;
+        }
+    });
+    for (auto &pt : parts) {
+        if (pt.err == POYB200_ESEQLEN) return fail(ctx, POYB200_ESEQLEN, "sequence empty (no leading gap) or longer than 16384");
+        if (pt.err) return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
+    }
     ctx->tasks.resize((size_t) b->n_pairs);
+    const DevCM dcm = ctx->dcm;
+    const bool allow_stripe = ctx->allow_stripe;
+    parallel_for(NT, (size_t) b->n_pairs, [&](size_t lo, size_t hi, int slot) {
+        Part &pt = parts[slot];
+        for (size_t p = lo; p < hi; p++) {
+            const int a = b->pairs[2 * p], c = b->pairs[2 * p + 1];
+            if (a < 0 || a >= b->n_seqs || c < 0 || c >= b->n_seqs) {
+                pt.err = POYB200_EINVAL;
+                return;
+            }
+            const int la = b->seq_len[a], lb = b->seq_len[c];
+            Task t{};
+            // affine_3: shorter operand on the rows, ties keep a (src/algn.c:2595); linear: longer operand on the
+            // rows, ties keep a (src/sequence.ml:709-714)
+            const bool rows_b = affine ? (la > lb) : (la < lb);
+            const int r = rows_b ? c : a, col = rows_b ? a : c;
+            t.off_r = (uint32_t) b->seq_off[r];
+            t.off_c = (uint32_t) b->seq_off[col];
+            t.lr = b->seq_len[r];
+            t.lc = b->seq_len[col];
+            t.flags = rows_b ? TF_ROWS_ARE_B : 0;
+            t.pair = (uint32_t) p;
+            if (affine) {
+                affine_band(t.lr - 1, t.lc - 1, t.dlo, t.dhi);
+            } else {
+                LinBand lb2 = linear_band(t.lr, t.lc, b->deltaw[p]);
+                t.dlo = lb2.dlo;
+                t.dhi = lb2.dhi;
+                if (lb2.full) t.flags |= TF_FULL;
+                const bool sw = b->swaped ? (b->swaped[p] != 0) : (la >= lb);  // src/sequence.ml:818
+                if (sw) t.flags |= TF_SWAPED;
+            }
+            const int W = t.dhi - t.dlo + 1;
+            choose_class(t, affine, bt, W, dcm, allow_stripe);
+            if (t.klass != KLASS_GENERIC) pt.max_stripe_len = std::max(pt.max_stripe_len, std::max(t.lr, t.lc));
+            else pt.maxW = std::max(pt.maxW, W);
+            pt.maxcap = std::max<long long>(pt.maxcap, (long long) la + lb + 2);
+            pt.klass_or |= t.klass;
+            pt.klass_and &= t.klass;
+            ctx->tasks[p] = t;
+        }
+    });
     long long maxcap = 16;
     int maxW = 1, max_stripe_len = 16;
-    for (int p = 0; p < b->n_pairs; p++) {
-        const int a = b->pairs[2 * p], c = b->pairs[2 * p + 1];
-        if (a < 0 || a >= b->n_seqs || c < 0 || c >= b->n_seqs) return fail(ctx, POYB200_EINVAL, "pair index out of range");
-        const int la = b->seq_len[a], lb = b->seq_len[c];
-        Task t{};
-        bool rows_b;
-        if (affine) {
-            rows_b = la > lb;  // shorter operand on the rows, ties keep a (src/algn.c:2595)
-        } else {
-            rows_b = la < lb;  // longer operand on the rows, ties keep a (src/sequence.ml:709-714)
-        }
-        const int r = rows_b ? c : a, col = rows_b ? a : c;
-        t.off_r = (uint32_t) b->seq_off[r];
-        t.off_c = (uint32_t) b->seq_off[col];
-        t.lr = b->seq_len[r];
-        t.lc = b->seq_len[col];
-        t.flags = rows_b ? TF_ROWS_ARE_B : 0;
-        t.pair = (uint32_t) p;
-        if (affine) {
-            affine_band(t.lr - 1, t.lc - 1, t.dlo, t.dhi);
-        } else {
-            LinBand lb2 = linear_band(t.lr, t.lc, b->deltaw[p]);
-            t.dlo = lb2.dlo;
-            t.dhi = lb2.dhi;
-            if (lb2.full) t.flags |= TF_FULL;
-            const bool sw = b->swaped ? (b->swaped[p] != 0) : (la >= lb);  // src/sequence.ml:818
-            if (sw) t.flags |= TF_SWAPED;
-        }
-        const int W = t.dhi - t.dlo + 1;
-        choose_class(t, affine, bt, W, ctx->dcm, ctx->allow_stripe);
-        if (t.klass != KLASS_GENERIC) max_stripe_len = std::max(max_stripe_len, std::max(t.lr, t.lc));
-        else maxW = std::max(maxW, W);
-        maxcap = std::max<long long>(maxcap, (long long) la + lb + 2);
-        ctx->tasks[p] = t;
+    uint32_t k_or = 0, k_and = 0xffffffffu;
+    for (auto &pt : parts) {
+        if (pt.err) return fail(ctx, POYB200_EINVAL, "pair index out of range");
+        maxcap = std::max(maxcap, pt.maxcap);
+        maxW = std::max(maxW, pt.maxW);
+        max_stripe_len = std::max(max_stripe_len, pt.max_stripe_len);
+        k_or |= pt.klass_or;
+        k_and &= pt.klass_and;
     }
     if (bt && b->n_pairs > 0) {
         if ((b->want & POYB200_WANT_MEDIAN) && !b->median) return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN without buffer");
@@ -368,9 +427,12 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     ctx->dstride = (maxcap + 15) & ~15ll;
     ctx->state_stride = maxW + 2;
     ctx->stripe_seq_bytes = (max_stripe_len + 15) & ~15;
-    // group by kernel class (stable: keeps the caller's order inside a class), then cut into chunks whose
-    // direction bands fit the budget
-    std::stable_sort(ctx->tasks.begin(), ctx->tasks.end(), [](const Task &x, const Task &y) { return x.klass < y.klass; });
+    // Group by kernel class (stable: keeps the caller's order inside a class).  A batch of one class -- the usual
+    // case -- stays in the caller's order, which lets results leave chunk by chunk while later chunks compute.
+    ctx->in_order = (b->n_pairs == 0) || (k_or == k_and);
+    if (!ctx->in_order)
+        std::stable_sort(ctx->tasks.begin(), ctx->tasks.end(), [](const Task &x, const Task &y) { return x.klass < y.klass; });
+    // cut into chunks: direction bands within the budget, and at most chunk_pairs pairs (pipelining granularity)
     ctx->chunks.clear();
     size_t begin = 0, off = 0;
     for (size_t k = 0; k < ctx->tasks.size(); k++) {
@@ -380,7 +442,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             bytes = (size_t) dir_bytes(t);
             bytes = (bytes + 63) & ~(size_t) 63;
         }
-        if (off + bytes > ctx->dir_budget && k > begin) {
+        if (k > begin && (off + bytes > ctx->dir_budget || k - begin >= ctx->chunk_pairs)) {
             ctx->chunks.push_back(Chunk{begin, k, off});
             begin = k;
             off = 0;
@@ -427,51 +489,63 @@ extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b)
     return POYB200_OK;
 }
 
-extern "C" int poyb200_run(poyb200_ctx *ctx) {
-    if (!ctx) return POYB200_EINVAL;
-    if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_run without poyb200_stage");
-    cudaSetDevice(ctx->device);
+// Fill + traceback of one chunk on the compute stream.
+static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     const int mode = ctx->mode;
     const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
+    const Chunk &ch = ctx->chunks[ci];
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want};
+    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci], ctx->stream));
+    // one fill launch per kernel class present in the chunk
+    size_t k = ch.begin;
+    while (k < ch.end) {
+        size_t e = k;
+        const uint32_t klass = ctx->tasks[k].klass;
+        while (e < ch.end && ctx->tasks[e].klass == klass) e++;
+        int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k));
+        if (rc) return rc;
+        k = e;
+    }
+    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 1], ctx->stream));
+    if (bt) {
+        const int nt = (int) (ch.end - ch.begin);
+        // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
+        // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
+        const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
+        if (affine)
+            aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
+                                                                  ctx->d_dir.p, out);
+        else
+            lin_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
+                                                                  ctx->d_dir.p, out);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 2], ctx->stream));
+    return POYB200_OK;
+}
+
+static int prepare_events(poyb200_ctx *ctx) {
     while (ctx->timing && ctx->chunk_ev.size() < 3 * ctx->chunks.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->chunk_ev.push_back(e);
     }
     ctx->timed_chunks = ctx->timing ? ctx->chunks.size() : 0;
-    size_t ci = 0;
-    for (const Chunk &ch : ctx->chunks) {
-        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci], ctx->stream));
-        // one fill launch per kernel class present in the chunk
-        size_t k = ch.begin;
-        while (k < ch.end) {
-            size_t e = k;
-            const uint32_t klass = ctx->tasks[k].klass;
-            while (e < ch.end && ctx->tasks[e].klass == klass) e++;
-            int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k));
-            if (rc) return rc;
-            k = e;
-        }
-        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 1], ctx->stream));
-        if (bt) {
-            const int nt = (int) (ch.end - ch.begin);
-            // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
-            // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
-            const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
-            if (affine)
-                aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                      ctx->d_dir.p, out);
-            else
-                lin_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                      ctx->d_dir.p, out);
-            ctx->launches++;
-            CK(cudaGetLastError());
-        }
-        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 2], ctx->stream));
-        ci++;
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_run(poyb200_ctx *ctx) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_run without poyb200_stage");
+    cudaSetDevice(ctx->device);
+    int rc = prepare_events(ctx);
+    if (rc) return rc;
+    for (size_t ci = 0; ci < ctx->chunks.size(); ci++) {
+        rc = run_chunk(ctx, ci);
+        if (rc) return rc;
     }
     return POYB200_OK;
 }
@@ -498,37 +572,70 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
     return POYB200_OK;
 }
 
+// D2H of the results of pairs [lo, hi) on stream st (rows of one pair range are contiguous on both sides).
+static int fetch_range(poyb200_ctx *ctx, size_t lo, size_t hi, cudaStream_t st) {
+    const poyb200_batch &b = ctx->hb;
+    const bool bt = (ctx->mode == MODE_ALIGN_2 || ctx->mode == MODE_ALIGN_AFF);
+    const size_t n = hi - lo;
+    if (n == 0) return POYB200_OK;
+    if (b.cost) CK(cudaMemcpyAsync(b.cost + lo, ctx->d_costs.p + lo, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (bt && b.want) {
+        CK(cudaMemcpyAsync(b.out_len + 4 * lo, ctx->d_outlen.p + 4 * lo, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        uint8_t *dst[4] = {b.median, b.medianwg, b.aligned_a, b.aligned_b};
+        const uint32_t need[4] = {POYB200_WANT_MEDIAN, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
+        // right-aligned device rows -> right-aligned caller rows
+        const size_t w = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
+        for (int k = 0; k < 4; k++) {
+            if (!(b.want & need[k])) continue;
+            uint8_t *d = dst[k] + lo * (size_t) b.out_stride;
+            const uint8_t *src = ctx->d_out[k].p + lo * (size_t) ctx->dstride;
+            if (ctx->dstride == b.out_stride)
+                CK(cudaMemcpyAsync(d, src, n * (size_t) ctx->dstride, cudaMemcpyDeviceToHost, st));
+            else
+                CK(cudaMemcpy2DAsync(d + (b.out_stride - w), (size_t) b.out_stride, src + (ctx->dstride - w),
+                                     (size_t) ctx->dstride, w, n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    return POYB200_OK;
+}
+
 extern "C" int poyb200_fetch(poyb200_ctx *ctx) {
     if (!ctx) return POYB200_EINVAL;
     if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_fetch without poyb200_stage");
     cudaSetDevice(ctx->device);
-    const poyb200_batch &b = ctx->hb;
-    const size_t n = ctx->tasks.size();
-    const bool bt = (ctx->mode == MODE_ALIGN_2 || ctx->mode == MODE_ALIGN_AFF);
-    if (n == 0) return POYB200_OK;
-    if (b.cost) CK(cudaMemcpyAsync(b.cost, ctx->d_costs.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (bt && b.want) {
-        CK(cudaMemcpyAsync(b.out_len, ctx->d_outlen.p, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        uint8_t *dst[4] = {b.median, b.medianwg, b.aligned_a, b.aligned_b};
-        const uint32_t need[4] = {POYB200_WANT_MEDIAN, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
-        // right-aligned device rows -> right-aligned caller rows in one strided copy each
-        const size_t w = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
-        for (int k = 0; k < 4; k++) {
-            if (!(b.want & need[k])) continue;
-            CK(cudaMemcpy2DAsync(dst[k] + (b.out_stride - w), (size_t) b.out_stride, ctx->d_out[k].p + (ctx->dstride - w),
-                                 (size_t) ctx->dstride, w, n, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-    }
+    int rc = fetch_range(ctx, 0, ctx->tasks.size(), ctx->stream);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return POYB200_OK;
 }
 
+// One-shot call: results of a chunk leave on the copy-out stream while the next chunks compute.
 static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     int rc = poyb200_stage(ctx, mode, b);
     if (rc) return rc;
-    rc = poyb200_run(ctx);
+    if (!ctx->in_order || ctx->chunks.size() < 2) {
+        rc = poyb200_run(ctx);
+        if (rc) return rc;
+        return poyb200_fetch(ctx);
+    }
+    rc = prepare_events(ctx);
     if (rc) return rc;
-    return poyb200_fetch(ctx);
+    while (ctx->ev_done.size() < ctx->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_done.push_back(e);
+    }
+    for (size_t ci = 0; ci < ctx->chunks.size(); ci++) {
+        rc = run_chunk(ctx, ci);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[ci], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[ci], 0));
+        rc = fetch_range(ctx, ctx->chunks[ci].begin, ctx->chunks[ci].end, ctx->s_out);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_out));
+    return POYB200_OK;
 }
 
 extern "C" int poyb200_batch_cost_2(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_COST_2, b); }
