@@ -58,3 +58,19 @@ def test_cells_formula_matches_survey_check_values():
     assert S.cells_affine(451, 501) == 43793
     assert S.cells_affine(301, 301) == 22741
     assert S.cells_affine(1501, 1501) == 119941
+
+
+def test_ocaml_stubs_compile_against_reference_headers():
+    """stubs/poyb200_stubs.c (the OCaml-side binding of INTEGRATION.md) must compile against the reference's own
+    seq.h / cm.h and the stand-in OCaml headers.  Needs /root/reference (this container only)."""
+    import subprocess
+
+    import pytest
+
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference headers not present")
+    cmd = ["gcc", "-std=gnu99", "-fgnu89-inline", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-variable",
+           "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + ref, "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "stubs", "poyb200_stubs.c")]
+    subprocess.check_call(cmd)
