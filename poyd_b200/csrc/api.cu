@@ -10,6 +10,7 @@
 #include "generic_kernels.cuh"
 #include "peak.cuh"
 #include "stripe_kernels.cuh"
+#include "lin_stripe_kernels.cuh"
 #include "trace_kernels.cuh"
 
 using namespace poyb200;
@@ -73,6 +74,7 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     int trace_threads_per_sm = 512;
+    int custom_tail = 0;  // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int host_threads = 8;
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
     bool in_order = true;           // tasks[k].pair == k
@@ -252,6 +254,9 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     CK(cudaMemcpyAsync(ctx->d_prepend.p, cm->prepend_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tail.p, cm->tail_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->custom_tail = 0;
+    for (size_t a2 = 0; a2 < dim; a2++)
+        if (cm->tail_cost[a2] != cm->cost[(a2 << cm->lcm) + cm->gap]) ctx->custom_tail = 1;
     ctx->hcm = *cm;
     ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
     ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
@@ -270,7 +275,8 @@ static inline uint32_t round16(uint32_t v) { return (v + 15u) & ~15u; }
 // Picks the fill kernel for one pair and fixes the layout of its direction band.
 static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, bool allow_stripe) {
     (void) bt;
-    if (allow_stripe && stripe_choose(t, affine, W, cm)) return;
+    if (allow_stripe && affine && stripe_choose(t, affine, W, cm)) return;
+    if (allow_stripe && !affine && lin_stripe_choose(t, W, cm)) return;
     t.klass = KLASS_GENERIC;
     t.dbase = t.dlo;
     t.G = 1;
@@ -280,6 +286,13 @@ static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, 
 
 static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n) {
     if (n <= 0) return POYB200_OK;
+    if (klass >= KLASS_LIN_BASE) {
+        cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
+                                          ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, ctx->stream);
+        ctx->launches++;
+        CK(e);
+        return POYB200_OK;
+    }
     if (klass != KLASS_GENERIC) {
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
                                       ctx->sm_count, ctx->stripe_seq_bytes, ctx->stream);

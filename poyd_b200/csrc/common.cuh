@@ -34,6 +34,7 @@ constexpr int AFF_RIGHT_EDGE_BYTE = (AM_H << 2) | AB_ENDH;  // DO_HORIZONTAL | E
 constexpr uint32_t TF_ROWS_ARE_B = 1;  // operand b sits on the rows: swap the aligned outputs back
 constexpr uint32_t TF_FULL = 2;        // linear: full matrix (algn_fill_plane), no edge rules
 constexpr uint32_t TF_SWAPED = 4;      // linear traceback tie flag (backtrack_2d `swaped`)
+constexpr uint32_t TF_DIR2 = 8;        // direction band holds 2-bit resolved moves (linear stripe kernels)
 
 struct Task {
     uint32_t off_r, off_c;  // pool offsets of the row / column sequence
@@ -56,6 +57,14 @@ __host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int
     const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j);
     const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
     return ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
+}
+// Direction code of cell (i, j): a byte, or a 2-bit field of a 32-bit chunk (TF_DIR2).
+__device__ __forceinline__ int dir_fetch(const Task &t, const uint8_t *dbase, int i, int j) {
+    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j);
+    const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
+    const uint64_t chunk = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL;
+    if (t.flags & TF_DIR2) return (__ldg(dbase + chunk + (m >> 2)) >> ((m & 3) * 2)) & 3;
+    return __ldg(dbase + chunk + m);
 }
 // Bytes of one pair's direction band (T runs over 0 .. lr + lc - 2).
 __host__ __device__ __forceinline__ uint64_t dir_bytes(const Task &t) {

@@ -143,9 +143,12 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     const int second = swaped ? D_INSERT : D_DELETE;
     // `while (end >= beg)` over the row-major matrix: stops after the ALIGN step out of cell (0, 0)
     while (i >= 0 && j >= 0) {
-        const int m = __ldg(dbase + dir_index(t, i, j));
+        const int m = dir_fetch(t, dbase, i, j);
         int mv;
-        if (m & D_ALIGN) mv = D_ALIGN;
+        if (t.flags & TF_DIR2) {
+            // the stripe kernels resolved the tie already: 0 ALIGN, 1 the preferred gap move, 2 the other one
+            mv = (m == 0) ? D_ALIGN : (m == 1) ? second : (swaped ? D_DELETE : D_INSERT);
+        } else if (m & D_ALIGN) mv = D_ALIGN;
         else if (m & second) mv = second;
         else mv = swaped ? D_DELETE : D_INSERT;
         int x, y;  // elements of s1 / s2 in this column

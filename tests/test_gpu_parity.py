@@ -285,3 +285,63 @@ def test_large_batch_properties(S):
             assert row[0] == 16
             assert np.array_equal(body[body != 16], pool.seq(s)[1:])
     al.close()
+
+
+def test_linear_custom_tail_and_prepend_costs(S, checker_factory, monkeypatch):
+    """Cost_matrix.fill_tail / fill_prepend (src/cost_matrix.ml:418-460) make tail_cost[a] differ from cost(a, gap): the
+    last-column rule (algn_fill_last_column) and the first-column / first-row costs then really matter."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.default_nucleotides().clone()
+    rng = np.random.default_rng(12)
+    cm.tail_cost[1:32] = rng.integers(0, 4, size=31)
+    cm.prepend_cost[1:32] = rng.integers(0, 4, size=31)
+    pool, pairs = synth.ragged_batch(400, max_len=200, seed=15, gap_ambiguity=0.02)
+    chk = checker_factory(cm)
+    for force in ("0", "1"):
+        monkeypatch.setenv("POYB200_FORCE_GENERIC", force)
+        al = S.Align(cm)
+        for dwv in (2, 20, 200):
+            dw = np.full(len(pairs), dwv, np.int32)
+            g = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
+            o = chk.batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=4)
+            assert_aligned_equal(g, o, label=f"custom tail deltaw={dwv} force_generic={force}")
+        al.close()
+
+
+def test_linear_generic_matches_stripe(S, checker_factory, monkeypatch):
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.default_nucleotides()
+    pool, pairs = synth.pair_batch(300, 500, seed=6, min_len=450)
+    chk = checker_factory(cm)
+    monkeypatch.setenv("POYB200_FORCE_GENERIC", "1")
+    al = S.Align(cm)
+    dw = al.deltaw_for(pool, pairs)
+    o = chk.batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=8)
+    assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear generic cfg2-lin")
+    al.close()
+    monkeypatch.setenv("POYB200_FORCE_GENERIC", "0")
+    al = S.Align(cm)
+    assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear stripe cfg2-lin")
+    # explicit swaped flag of the external (algn_CAML_backtrack_2d): both values, on equal-length operands
+    same = np.nonzero(pool.len[pairs[:, 0]] == pool.len[pairs[:, 1]])[0][:64]
+    if len(same):
+        sub = pairs[same]
+        for flag in (0, 1):
+            g = al.align_2(pool, sub, 4, deltaw=dw[same], raw_deltaw=True, swaped=np.full(len(sub), flag, np.uint8))
+            ref = checker_factory(cm)
+            for k, (a, b) in enumerate(sub):
+                if hasattr(ref, "L") and ref.kind == "reference":
+                    import ctypes as C
+
+                    s1, s2 = np.ascontiguousarray(pool.seq(a)), np.ascontiguousarray(pool.seq(b))
+                    cap = len(s1) + len(s2)
+                    r1, r2, rl = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8), C.c_int(0)
+                    ref.L.ref_align_2(ref.h, ref.ws, s1.ctypes.data_as(C.POINTER(C.c_uint8)), len(s1),
+                                      s2.ctypes.data_as(C.POINTER(C.c_uint8)), len(s2), int(dw[same][k]), flag,
+                                      r1.ctypes.data_as(C.POINTER(C.c_uint8)), r2.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                      C.byref(rl))
+                    assert np.array_equal(g.get("aligned_a", k), r1[: rl.value]), (flag, k)
+                    assert np.array_equal(g.get("aligned_b", k), r2[: rl.value]), (flag, k)
+    al.close()
