@@ -34,22 +34,54 @@ UNIT = "GCUPS"
 OPS_PER_CELL = 50  # integer ops per affine_3 cell with traceback, counted from src/algn.c
 
 
-def workload(n_pairs: int, seed: int):
-    from poyd_b200 import cost_matrix as CM, synth
+WORKLOADS = {
+    # name: (description, mode, ops per cell)
+    "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
+                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50),
+    "linear500": ("cfg 2-lin: DNA pairs 500 bp, linear gaps (subst 1, indel 2), deltaw as Sequence.Align.cost_2 computes it, "
+                  "align_2 + ancestor_2 + median_2_with_gaps", 1, 10),
+    "protein300": ("configs[2] (3a): protein pairs 300 aa, 22x22 matrix 1/2, deltaw as the product computes it "
+                   "(full matrix, SURVEY.md A15), align_2 + medians", 1, 10),
+    "protein300_band16": ("configs[2] (3b): protein pairs 300 aa, explicit deltaw 16, align_2 + medians", 1, 10),
+}
 
-    cm = CM.nucleotides(1, 2, 3)
-    pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512)
-    return cm, pool, pairs
+
+def workload(n_pairs: int, seed: int, name: str = "affine500"):
+    """Returns (cm, pool, pairs, deltaw or None)."""
+    from poyd_b200 import cost_matrix as CM, sequence as S, synth
+
+    if name == "affine500":
+        cm = CM.nucleotides(1, 2, 3)
+        pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512)
+        return cm, pool, pairs, None
+    if name == "linear500":
+        cm = CM.default_nucleotides()
+        pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512)
+    else:
+        cm = CM.default_aminoacids()
+        pool, pairs = synth.pair_batch(n_pairs, 300, seed=seed, alphabet="protein", subst=0.15, indel=0.02, stride=304)
+    if name == "protein300_band16":
+        return cm, pool, pairs, np.full(len(pairs), 16, np.int32)
+    cnt = pool.count(cm.gap)
+    la, lb = pool.len[pairs[:, 0]].astype(np.int64), pool.len[pairs[:, 1]].astype(np.int64)
+    dw = np.maximum(cnt[pairs[:, 0]], cnt[pairs[:, 1]]) + S.deltaw_calc(np.maximum(la, lb), np.minimum(la, lb), None)
+    return cm, pool, pairs, dw.astype(np.int32)
 
 
-def total_cells(pool, pairs) -> int:
-    """Cells the reference visits for the batch: a pure function of the two lengths."""
+def total_cells(pool, pairs, deltaw=None) -> int:
+    """Cells the reference visits for the batch: a pure function of the two lengths (and deltaw), SURVEY.md 8d."""
     from poyd_b200 import sequence as S
 
-    la, lb = pool.len[pairs[:, 0]], pool.len[pairs[:, 1]]
-    key = la.astype(np.int64) * 65536 + lb
-    uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
-    per = np.array([S.cells_affine(int(k >> 16), int(k & 65535)) for k in uniq], dtype=np.int64)
+    la, lb = pool.len[pairs[:, 0]].astype(np.int64), pool.len[pairs[:, 1]].astype(np.int64)
+    if deltaw is None:
+        key = la * 65536 + lb
+        uniq, cnt = np.unique(key, return_counts=True)
+        per = np.array([S.cells_affine(int(k >> 16), int(k & 65535)) for k in uniq], dtype=np.int64)
+    else:
+        l1, l2 = np.maximum(la, lb), np.minimum(la, lb)
+        key = (l1 * 65536 + l2) * 65536 + deltaw.astype(np.int64)
+        uniq, cnt = np.unique(key, return_counts=True)
+        per = np.array([S.cells_linear(int(k >> 32), int((k >> 16) & 65535), int(k & 65535)) for k in uniq], dtype=np.int64)
     return int((per * cnt).sum())
 
 
@@ -60,7 +92,7 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_arm(cm, pool, pairs, sample: int, threads: int, steps: int = 1, warmup: int = 0):
+def cpu_arm(cm, pool, pairs, sample: int, threads: int, steps: int = 1, warmup: int = 0, deltaw=None, mode: int = 3):
     """Times the reference's CPU implementation (compiled algn.c if oracle/_ref exists, else the port)."""
     from oracle import oracle
 
@@ -68,11 +100,12 @@ def cpu_arm(cm, pool, pairs, sample: int, threads: int, steps: int = 1, warmup: 
     chk = oracle.best_checker(cm)
     sample = min(sample, len(pairs))
     sub = pairs[:sample]
-    cells = total_cells(pool, sub)
+    dws = None if deltaw is None else deltaw[:sample]
+    cells = total_cells(pool, sub, dws)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        chk.batch(3, pool.pool, pool.off, pool.len, sub, nthreads=threads)
+        chk.batch(mode, pool.pool, pool.off, pool.len, sub, deltaw=dws, nthreads=threads)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -139,6 +172,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS),
+                    help="affine500 is the headline configuration; the others are reported in DESIGN.md")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,13 +186,13 @@ def main():
         if rank != 0:
             return
         sample = args.cpu_sample or max(2000, 1500 * threads)
-        cm, pool, pairs = workload(sample, seed=2)
-        base, sec = cpu_arm(cm, pool, pairs, sample, threads, steps=args.steps, warmup=args.warmup)
+        cm, pool, pairs, dw = workload(sample, seed=2, name=args.workload)
+        base, sec = cpu_arm(cm, pool, pairs, sample, threads, steps=args.steps, warmup=args.warmup, deltaw=dw,
+                            mode=WORKLOADS[args.workload][1])
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": "configs[1]: DNA pairs 500 bp, affine gaps (1/2, gap opening 3), "
-                                       "align_affine_3 with all outputs", "pairs_per_step": sample,
+                "config": {"workload": WORKLOADS[args.workload][0], "pairs_per_step": sample,
                            "note": "CPU arm: bounded sample of the same workload per step"},
                 "cpu_baseline": dict(base),
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -180,8 +215,9 @@ def main():
     if world > 1:
         dist.barrier()
 
-    cm, pool, pairs = workload(args.pairs, seed=2 + rank)  # pair shards: each rank owns its own pairs
-    cells = total_cells(pool, pairs)
+    cm, pool, pairs, dw = workload(args.pairs, seed=2 + rank, name=args.workload)  # each rank owns its own pairs
+    wl_desc, wl_mode, ops_per_cell = WORKLOADS[args.workload]
+    cells = total_cells(pool, pairs, dw)
     al = S.Align(cm, device=local_rank)
     want = S.WANT_MEDIAN | S.WANT_MEDIANWG | S.WANT_ALIGNED
 
@@ -193,16 +229,18 @@ def main():
     keep = [pinned(pool.pool), pinned(pool.off), pinned(pool.len), pinned(pairs)]
     ppool.pool, ppool.off, ppool.len = keep[0].numpy(), keep[1].numpy(), keep[2].numpy()
     ppairs = keep[3].numpy()
-    batch, res = al.make_batch(ppool, ppairs, want=want, outputs=False)
+    if dw is not None:
+        keep.append(pinned(dw))
+    batch, res = al.make_batch(ppool, ppairs, deltaw=None if dw is None else keep[-1].numpy(), want=want, outputs=False)
     n = len(ppairs)
-    stride = 1008
+    stride = (int((ppool.len[ppairs[:, 0]].astype(np.int64) + ppool.len[ppairs[:, 1]]).max()) + 2 + 15) // 16 * 16
     out_t = {k: torch.empty((n, stride), dtype=torch.uint8, pin_memory=True) for k in ("median", "medianwg", "a", "b")}
     cost_t = torch.empty(n, dtype=torch.int32, pin_memory=True)
     lens_t = torch.empty((n, 4), dtype=torch.int32, pin_memory=True)
     batch.cost, batch.out_len, batch.out_stride = cost_t.data_ptr(), lens_t.data_ptr(), stride
     batch.median, batch.medianwg = out_t["median"].data_ptr(), out_t["medianwg"].data_ptr()
     batch.aligned_a, batch.aligned_b = out_t["a"].data_ptr(), out_t["b"].data_ptr()
-    h2d = int(ppool.pool.nbytes + n * 56)
+    h2d = int(ppool.pool.nbytes + n * 64)
     d2h = int(4 * n * stride + n * 4 + n * 16)
 
     stream = torch.cuda.ExternalStream(al.L.poyb200_stream(al.h), device=torch.device("cuda", local_rank))
@@ -228,7 +266,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident leg: stage once, time K passes of the kernels ------------------------------------
-    al.stage(S.MODE_ALIGN_AFFINE_3, batch)
+    al.stage(wl_mode, batch)
     al.sync()
     for _ in range(args.warmup):
         al.run()
@@ -257,7 +295,8 @@ def main():
 
     def e2e_call():
         # the call a user of the C ABI makes: host buffers in, host buffers out
-        al._check(al.L.poyb200_batch_align_affine_3(al.h, ctypes.byref(batch)))
+        fn = al.L.poyb200_batch_align_affine_3 if wl_mode == 3 else al.L.poyb200_batch_align_2
+        al._check(fn(al.h, ctypes.byref(batch)))
 
     for _ in range(max(1, args.warmup - 1)):
         e2e_call()
@@ -292,22 +331,21 @@ def main():
     fill_s = f_ms * 1e-3
     roof = {"bound": "hbm", "achieved": alg_bytes / fill_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
-            "kernel": "aff_stripe_kernel<5,8,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
+            "kernel": "aff_stripe_kernel<5,8,true>" if wl_mode == 3 else "lin_stripe_kernel<K,G,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
             "note": "integer min-plus recurrence: ALU-bound, see roofline_int32"}
-    gops = cells * OPS_PER_CELL / fill_s * 1e-9
+    gops = cells * ops_per_cell / fill_s * 1e-9
     roof_int = {"bound": "int32_alu", "achieved": gops, "peak": add_g, "unit": "Gop/s", "frac": gops / add_g,
-                "ops_per_cell": OPS_PER_CELL, "peak_source": "measured live: dependent-free add.s32 chains (poyb200_int32_peak)",
+                "ops_per_cell": ops_per_cell, "peak_source": "measured live: dependent-free add.s32 chains (poyb200_int32_peak)",
                 "peak_minmax_gops": mm_g, "peak_minplus_mix_gops": mix_g, "kernel_gcups": cells / fill_s * 1e-9}
     base = None
     if not args.skip_cpu:
         sample = args.cpu_sample or max(2000, 1500 * threads)
-        base, _ = cpu_arm(cm, pool, pairs, sample, threads)
+        base, _ = cpu_arm(cm, pool, pairs, sample, threads, deltaw=dw, mode=wl_mode)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, "
-                               "gap opening 3), align_affine_3 = fill + traceback + median/medianwg/aligned pair",
+        "config": {"workload": wl_desc,
                    "pairs_per_gpu_per_step": n, "cells_per_gpu_per_step": cells, "sharding": f"pairs x{world}",
                    "l2": "inputs (pool + direction bands, > 1 GB) exceed the 126 MB L2 between iterations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
