@@ -137,8 +137,11 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const 
     const int dim = 1 << cm.lcm, row_ints = dim + 1;
     int *s_lut = reinterpret_cast<int *>(smem);
     int *s_gaprow = s_lut + dim * row_ints, *s_gapcol = s_gaprow + dim, *s_prep = s_gapcol + dim, *s_tail = s_prep + dim;
-    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_tail + dim);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_tail + dim + (((dim * (row_ints + 4)) & 1) ? 1 : 0));  // 8-byte aligned
+    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_bar + STRIPE_WARPS * 4);
     s_seq += (16 - ((uintptr_t) s_seq & 15)) & 15;
+    if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
+    uint32_t bar_phase = 0;
     for (int k = threadIdx.x; k < dim * dim; k += blockDim.x)
         s_lut[(k >> cm.lcm) * row_ints + (k & (dim - 1))] = 4 * __ldg(cm.cost + k);
     for (int k = threadIdx.x; k < dim; k += blockDim.x) {
@@ -162,23 +165,9 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const 
         if (valid) t = tasks[ti];
         else { t = Task{}; t.lr = 1; t.lc = 1; t.dhi = 0; t.dlo = 0; }
         const int nr = t.lr - 1, nc = t.lc - 1;
-        {
-            const uint8_t *gr = pool + t.off_r, *gc = pool + t.off_c;
-            if (valid) {
-                if ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0) {
-                    for (int k = lane * 16; k < t.lr; k += G * 16)
-                        *reinterpret_cast<uint4 *>(my_seq + k) = __ldg(reinterpret_cast<const uint4 *>(gr + k));
-                    for (int k = lane * 16; k < t.lc; k += G * 16)
-                        *reinterpret_cast<uint4 *>(my_seq + seq_bytes + k) = __ldg(reinterpret_cast<const uint4 *>(gc + k));
-                } else {
-                    for (int k = lane; k < t.lr; k += G) my_seq[k] = __ldg(gr + k);
-                    for (int k = lane; k < t.lc; k += G) my_seq[seq_bytes + k] = __ldg(gc + k);
-                }
-            } else if (lane == 0) {
-                my_seq[0] = (uint8_t) cm.gap;
-                my_seq[seq_bytes] = (uint8_t) cm.gap;
-            }
-        }
+        __syncwarp();
+        stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
+                      &s_bar[warp_in_block * GPW + grp], bar_phase, cm.gap);
         __syncwarp();
 
         const int d0 = t.dhi + 1 - Q * G;
@@ -266,7 +255,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const 
 // ---- host side -----------------------------------------------------------------------------------------
 static inline size_t lin_table_bytes(int lcm) {
     const size_t dim = (size_t) 1 << lcm;
-    return (dim * (dim + 1) + 4 * dim) * sizeof(int) + 16;
+    return (dim * (dim + 1) + 4 * dim + 1) * sizeof(int) + STRIPE_WARPS * 4 * 8 + 16;
 }
 
 static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {

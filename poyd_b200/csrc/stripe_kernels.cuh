@@ -43,7 +43,62 @@ constexpr int STRIPE_WARPS = 4;
 #define STRIPE_MIN_BLOCKS 3
 #endif
 constexpr int STRIPE_LUT_BYTES = 16 * 17 * 8;  // == 16 * LUT_ROW_BYTES
-constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4;
+constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * 8;
+
+// ---- HBM -> shared-memory staging with the bulk-copy engine (TMA, cp.async.bulk) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "POYB200_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra POYB200_DONE;\n"
+        "bra POYB200_WAIT;\n"
+        "POYB200_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Stages the two operands of a group's pair: one elected lane issues two bulk copies that complete on the group's
+// mbarrier, every lane of the group waits on it.  Needs 16-byte aligned sources (SeqPool guarantees that); otherwise
+// plain loads.  `phase` is the group's barrier parity and flips whenever the barrier was used.
+template <int G>
+__device__ __forceinline__ void stage_pair(uint8_t *dst_r, uint8_t *dst_c, const uint8_t *gr, const uint8_t *gc, int lr, int lc,
+                                           int lane, bool valid, uint64_t *bar, uint32_t &phase, int pad_code) {
+    if (valid) {
+        if ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0) {
+            if (lane == 0) {
+                const uint32_t br = (uint32_t) (lr + 15) & ~15u, bc = (uint32_t) (lc + 15) & ~15u;
+                // the previous pair's reads of these buffers went through the generic proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, br + bc);
+                bulk_g2s(dst_r, gr, br, bar);
+                bulk_g2s(dst_c, gc, bc, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int k = lane; k < lr; k += G) dst_r[k] = __ldg(gr + k);
+            for (int k = lane; k < lc; k += G) dst_c[k] = __ldg(gc + k);
+        }
+    } else if (lane == 0) {
+        dst_r[0] = (uint8_t) pad_code;
+        dst_c[0] = (uint8_t) pad_code;
+    }
+}
 
 // All DP values are carried multiplied by 4, and each of the four states keeps a constant 2-bit tag in its low
 // bits: EH 0, CB 1, EV 2, EB 3.  The tags are the tie-break priorities of the reference's traceback:
@@ -265,7 +320,10 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
     uint8_t *s_lut = smem;  // 16 rows of LUT_ROW_BYTES: int2 {4*cost, 4*cost - 2} for cost[(a & 15) << lcm | (b & 15)]
     int *s_prep = reinterpret_cast<int *>(smem + STRIPE_LUT_BYTES);  // 32 ints: 4 * prepend[c]
     int *s_get = s_prep + 32;                                         // 32 ints: 4 * cost[c << lcm | gap]
-    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_get + 32);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_get + 32);  // one mbarrier per group
+    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_bar + STRIPE_WARPS * 4);
+    if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
+    uint32_t bar_phase = 0;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
         *reinterpret_cast<int2 *>(s_lut + (k >> 4) * LUT_ROW_BYTES + (k & 15) * 8) = make_int2(c4, c4 - 2);
@@ -290,23 +348,9 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
         else { t = Task{}; t.lr = 1; t.lc = 1; t.dhi = -1; t.dlo = -39; }
         const int nr = t.lr - 1, nc = t.lc - 1;
         // stage both operands in shared memory
-        {
-            const uint8_t *gr = pool + t.off_r, *gc = pool + t.off_c;
-            if (valid) {
-                if ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0) {
-                    for (int k = lane * 16; k < t.lr; k += G * 16)
-                        *reinterpret_cast<uint4 *>(my_seq + k) = __ldg(reinterpret_cast<const uint4 *>(gr + k));
-                    for (int k = lane * 16; k < t.lc; k += G * 16)
-                        *reinterpret_cast<uint4 *>(my_seq + seq_bytes + k) = __ldg(reinterpret_cast<const uint4 *>(gc + k));
-                } else {
-                    for (int k = lane; k < t.lr; k += G) my_seq[k] = __ldg(gr + k);
-                    for (int k = lane; k < t.lc; k += G) my_seq[seq_bytes + k] = __ldg(gc + k);
-                }
-            } else if (lane == 0) {
-                my_seq[0] = 16;
-                my_seq[seq_bytes] = 16;
-            }
-        }
+        __syncwarp();
+        stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
+                      &s_bar[warp_in_block * GPW + grp], bar_phase, 16);
         __syncwarp();
 
         const int d0 = t.dhi + 2 - Q * G;
