@@ -74,6 +74,7 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     int trace_threads_per_sm = 512;
+    int allow_noeb = 1;   // POYB200_NOEB=0 disables the no-gap-bit fast path of the affine stripe kernels
     int custom_tail = 0;  // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int host_threads = 8;
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
@@ -201,6 +202,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
+    if (const char *s = getenv("POYB200_NOEB")) ctx->allow_noeb = atoi(s);
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
     if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
     if (const char *s = getenv("POYB200_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(s));
@@ -295,7 +297,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     }
     if (klass != KLASS_GENERIC) {
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->stream);
+                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -719,3 +721,9 @@ extern "C" int poyb200_int32_peak(poyb200_ctx *ctx, double *gops_add, double *go
     if (rc) return rc;
     return peak_one<2>(ctx, ctx->d_costs.p, 3.0, gops_mix);
 }
+
+#ifdef POYB200_EXP_DEBUG
+extern "C" int poyb200_debug_counters(int *out) {
+    return (int) cudaMemcpyFromSymbol(out, g_dbg, sizeof(int) * 4);
+}
+#endif

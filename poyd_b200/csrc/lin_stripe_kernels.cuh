@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const 
         stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
                       &s_bar[warp_in_block * GPW + grp], bar_phase, cm.gap);
         __syncwarp();
+        __syncwarp();
 
         const int d0 = t.dhi + 1 - Q * G;
         const int u_first = (-d0) >> 1;

@@ -29,6 +29,9 @@
 
 namespace poyb200 {
 
+#ifdef POYB200_EXP_DEBUG
+__device__ int g_dbg[4];
+#endif
 constexpr uint32_t KLASS_GENERIC = 0;
 // klass = 1 + index into this table (affine stripe shapes).  LOW is chosen at run time per pair.
 struct StripeShape {
@@ -58,46 +61,53 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// One poll of the barrier: true once the phase with the given parity has completed.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "POYB200_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra POYB200_DONE;\n"
-        "bra POYB200_WAIT;\n"
-        "POYB200_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return done != 0;
 }
 
 // Stages the two operands of a group's pair: one elected lane issues two bulk copies that complete on the group's
-// mbarrier, every lane of the group waits on it.  Needs 16-byte aligned sources (SeqPool guarantees that); otherwise
-// plain loads.  `phase` is the group's barrier parity and flips whenever the barrier was used.
+// mbarrier.  The wait is WARP-UNIFORM: every lane polls its own group's barrier and the loop runs until a vote says all
+// of them are through.  (Per-lane polling loops let the lanes of a warp leave at different polls; the warp then kept
+// running as separate fragments and issued every later instruction once per fragment -- a 2x slowdown, measured.)
+// Needs 16-byte aligned sources (SeqPool guarantees that); otherwise plain loads.  `phase` is the group's barrier
+// parity and flips whenever the barrier was used.  Must be called by all 32 lanes.
 template <int G>
 __device__ __forceinline__ void stage_pair(uint8_t *dst_r, uint8_t *dst_c, const uint8_t *gr, const uint8_t *gc, int lr, int lc,
                                            int lane, bool valid, uint64_t *bar, uint32_t &phase, int pad_code) {
-    if (valid) {
-        if ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0) {
-            if (lane == 0) {
-                const uint32_t br = (uint32_t) (lr + 15) & ~15u, bc = (uint32_t) (lc + 15) & ~15u;
-                // the previous pair's reads of these buffers went through the generic proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(bar, br + bc);
-                bulk_g2s(dst_r, gr, br, bar);
-                bulk_g2s(dst_c, gc, bc, bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-        } else {
-            for (int k = lane; k < lr; k += G) dst_r[k] = __ldg(gr + k);
-            for (int k = lane; k < lc; k += G) dst_c[k] = __ldg(gc + k);
+    const bool bulk = valid && ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0);
+    if (bulk) {
+        if (lane == 0) {
+            const uint32_t br = (uint32_t) (lr + 15) & ~15u, bc = (uint32_t) (lc + 15) & ~15u;
+            // the previous pair's reads of these buffers went through the generic proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, br + bc);
+            bulk_g2s(dst_r, gr, br, bar);
+            bulk_g2s(dst_c, gc, bc, bar);
         }
+    } else if (valid) {
+        for (int k = lane; k < lr; k += G) dst_r[k] = __ldg(gr + k);
+        for (int k = lane; k < lc; k += G) dst_c[k] = __ldg(gc + k);
     } else if (lane == 0) {
         dst_r[0] = (uint8_t) pad_code;
         dst_c[0] = (uint8_t) pad_code;
     }
+    bool done;
+    do {
+        done = bulk ? mbar_try_wait(bar, phase) : true;
+    } while (!__all_sync(0xffffffffu, done));
+    if (bulk) phase ^= 1u;
+    __syncwarp();
 }
 
 // All DP values are carried multiplied by 4, and each of the four states keeps a constant 2-bit tag in its low
@@ -131,7 +141,12 @@ struct AffWinCol {
 // One interior cell on tagged, x4 values, for DNA matrices (lcm = 5, gap = 16 = TMPGAP, codes < 32), where "has
 // the gap bit", "si_base != si_no_gap" and "si & TMPGAP" are the same predicate.  d = {4*cost, 4*cost - 2}.
 // Returns the direction byte (common.cuh).
-template <bool BT>
+//
+// NOEB: neither operand carries a gap bit beyond its leading element and gap_open > 0.  Then `both` is false in every
+// cell, the block-diagonal state is >= HIGH_NUM everywhere except the origin, its only finite use -- the
+// ALIGN_TO_DIAGONAL candidate of cell (1, 1), worth cost + gap_open against ALIGN_TO_ALIGN's cost -- loses strictly, and
+// it can never be the minimal state of a cell the traceback visits: the whole EB state is dropped.
+template <bool BT, bool NOEB>
 __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, int cbd, int evd, int ehd, int ebd,
                                             const AffWinRow &r, const AffWinCol &c, int2 d, int go8, int &cb, int &ev,
                                             int &eh, int &eb) {
@@ -145,6 +160,19 @@ __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, 
     y = cbu + r.gopge4p1;
     ev = min(x, y);
     if (BT) byte |= (x < y) ? 0 : AB_ENDV;
+    if (NOEB) {
+        const int a2 = ehd + d.x + (r.gop4 & c.gm);
+        const int a1 = evd + d.x + (c.gop4 & r.gm);
+        const int a0 = cbd + d.x + 2;
+        const int ck = min(a0, min(a1, a2));
+        cb = (ck & ~3) | TAG_CB;
+        eb = ebd;
+        if (BT) {
+            const int fk = min(eh, min(ev, cb));
+            byte |= (ck & 3) | ((fk & 3) << 2) | AB_ENDB;
+        }
+        return byte;
+    }
     // FILL_EXTEND_BLOCK_DIAGONAL :1861-1882 / _NOBT :1837-1854
     const int bothm = r.gm & c.gm;     // -1 when both carry the gap bit
     const int dg = HIGH4 & ~bothm;     // 0 or 4*HIGH_NUM
@@ -170,7 +198,7 @@ __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, 
     return byte;
 }
 
-template <int K, int G, bool BT, bool LOW>
+template <int K, int G, bool BT, bool LOW, bool NOEB>
 struct AffStripe {
     static constexpr int Q = 2 * K;
 
@@ -271,7 +299,7 @@ struct AffStripe {
             const int evu = ev[q + 1], cbu = cb[q + 1];
             const int2 d = *reinterpret_cast<const int2 *>(lut + R[m].lut + C[m].lut);
             int ncb, nev, neh, neb;
-            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m], d, go8, ncb, nev,
+            const int byte = aff_cell_dna<BT, NOEB>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m], d, go8, ncb, nev,
                                               neh, neb);
             fixups<BOUNDARY>(q, i0 - m, j0 + m, ehl, evu, R[m], C[m], ncb, nev, neh, neb);
             cb[q] = ncb; ev[q] = nev; eh[q] = neh; eb[q] = neb;
@@ -287,7 +315,7 @@ struct AffStripe {
             const int evu = (m == K - 1) ? in_ev : ev[q + 1], cbu = (m == K - 1) ? in_cbu : cb[q + 1];
             const int2 d = *reinterpret_cast<const int2 *>(lut + R[m].lut + C[m + 1].lut);
             int ncb, nev, neh, neb;
-            const int byte = aff_cell_dna<BT>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m + 1], d, go8, ncb,
+            const int byte = aff_cell_dna<BT, NOEB>(ehl, cbl, evu, cbu, cb[q], ev[q], eh[q], eb[q], R[m], C[m + 1], d, go8, ncb,
                                               nev, neh, neb);
             if (m == K - 1) {
                 if (lane == G - 1) {  // diagonal dhi + 1: poisoned (:2531-2535)
@@ -312,7 +340,7 @@ template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                        const uint8_t *__restrict__ pool,
                                                                        uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                       int seq_bytes) {
+                                                                       int seq_bytes, int allow_noeb) {
     constexpr int GPW = 32 / G;  // groups (pairs) per warp
     constexpr int Q = 2 * K;
     constexpr int BL = (K <= 4) ? 4 : 8;
@@ -352,6 +380,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
         stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
                       &s_bar[warp_in_block * GPW + grp], bar_phase, 16);
         __syncwarp();
+        __syncwarp();
 
         const int d0 = t.dhi + 2 - Q * G;
         const int u_first = (-d0) >> 1;  // first double step: t = 2u + d0 in {-1, 0}
@@ -368,9 +397,10 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
         const int dd_f = (nc - nr) - d0, lane_f = dd_f / Q, q_f = dd_f % Q;
         int result = 0;
 
-        auto run = [&](auto lowtag) {
+        auto run = [&](auto lowtag, auto noebtag) {
             constexpr bool LOW = decltype(lowtag)::value;
-            AffStripe<K, G, BT, LOW> S;
+            constexpr bool NOEB = decltype(noebtag)::value;
+            AffStripe<K, G, BT, LOW, NOEB> S;
             S.si = my_seq; S.sj = my_seq + seq_bytes;
             S.lut = s_lut; S.prep = s_prep; S.get = s_get;
             S.nr = nr; S.nc = nc; S.go4 = 4 * cm.gap_open; S.lane = lane;
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
                     int r = 0;
 #pragma unroll
                     for (int q = 0; q < Q; q++)
-                        if (q == q_f) r = min(min(S.cb[q], S.ev[q]), min(S.eh[q], S.eb[q])) >> 2;
+                        if (q == q_f) r = (NOEB ? min(S.cb[q], min(S.ev[q], S.eh[q])) : min(min(S.cb[q], S.ev[q]), min(S.eh[q], S.eb[q]))) >> 2;
                     result = r;
                 }
             };
@@ -420,8 +450,54 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
         };
         // LOW must be uniform over the warp's control flow: take the slower variant if any group needs it
         const bool any_low = __any_sync(0xffffffffu, low);
-        if (any_low) run(std::true_type{});
-        else run(std::false_type{});
+        // gap bits beyond the leading element of either operand (scanned in shared memory, 4 bytes per load)
+        int gapbits = 0;
+        if (valid) {
+            for (int k = lane * 4; k < t.lr; k += G * 4) {
+                uint32_t w = *reinterpret_cast<const uint32_t *>(my_seq + k);
+                if (k == 0) w &= 0xffffff00u;
+                if (k + 4 > t.lr) w &= 0xffffffffu >> (8 * (k + 4 - t.lr));
+                gapbits |= (int) (w & 0x10101010u);
+            }
+            for (int k = lane * 4; k < t.lc; k += G * 4) {
+                uint32_t w = *reinterpret_cast<const uint32_t *>(my_seq + seq_bytes + k);
+                if (k == 0) w &= 0xffffff00u;
+                if (k + 4 > t.lc) w &= 0xffffffffu >> (8 * (k + 4 - t.lc));
+                gapbits |= (int) (w & 0x10101010u);
+            }
+        }
+        #ifdef POYB200_EXP_DEBUG
+        {
+            // debug: compare the staged bytes with global memory, count mismatching groups and non-noeb warps
+            int bad = 0;
+            if (valid) {
+                for (int k = lane; k < t.lr; k += G) bad |= (my_seq[k] != pool[t.off_r + k]);
+                for (int k = lane; k < t.lc; k += G) bad |= (my_seq[seq_bytes + k] != pool[t.off_c + k]);
+            }
+            const bool anybad = __any_sync(0xffffffffu, bad);
+            const bool anygap = __any_sync(0xffffffffu, gapbits != 0);
+            if (lane32 == 0) {
+                atomicAdd(&g_dbg[0], 1);
+                if (anybad) atomicAdd(&g_dbg[1], 1);
+                if (anygap) atomicAdd(&g_dbg[2], 1);
+            }
+        }
+#endif
+#ifdef POYB200_EXP_FORCE_NOEB
+        const bool noeb = allow_noeb != 0;
+#elif defined(POYB200_EXP_D)
+        const bool anyg = __any_sync(0xffffffffu, gapbits != 0);
+        if (anyg && lane32 == 0) out_cost[0] = -1;  // keeps the scan alive; never happens on the bench data
+        const bool noeb = allow_noeb != 0;
+#elif defined(POYB200_EXP_E)
+        // vote-derived flag, but no scan: gapbits comes from a single word
+        const bool noeb = !__any_sync(0xffffffffu, (my_seq[4 + lane] & 16) != 0) && cm.gap_open > 0 && allow_noeb;
+#else
+        const bool noeb = !__any_sync(0xffffffffu, gapbits != 0) && cm.gap_open > 0 && allow_noeb;
+#endif
+        if (any_low) run(std::true_type{}, std::false_type{});
+        else if (noeb) run(std::false_type{}, std::true_type{});
+        else run(std::false_type{}, std::false_type{});
 
         if (valid && lane == lane_f) {
             if (BT && nr == 0 && nc == 0) result = 0;
@@ -454,7 +530,7 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
 
 template <int K, int G>
 static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
-                                       int *cost, int sm_count, int seq_bytes, cudaStream_t stream) {
+                                       int *cost, int sm_count, int seq_bytes, int allow_noeb, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const size_t smem = STRIPE_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
@@ -467,22 +543,22 @@ static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevC
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb);
     return cudaGetLastError();
 }
 
 static inline cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, DevCM cm,
                                         const uint8_t *pool, uint8_t *dir, int *cost, int sm_count, int seq_bytes,
-                                        cudaStream_t stream) {
+                                        int allow_noeb, cudaStream_t stream) {
     if (!affine) return cudaErrorNotSupported;
     switch (klass - 1) {
-        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
-        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, stream);
+        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
         default: return cudaErrorInvalidValue;
     }
 }

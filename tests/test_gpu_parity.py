@@ -22,7 +22,7 @@ def _affine_cases():
     from poyd_b200 import cost_matrix as CM
 
     return [("sub1_indel2_go3", CM.nucleotides(1, 2, 3)), ("sub2_indel1_go1", CM.nucleotides(2, 1, 1)),
-            ("sub3_indel1_go5", CM.nucleotides(3, 1, 5))]
+            ("sub3_indel1_go5", CM.nucleotides(3, 1, 5)), ("sub1_indel2_go0", CM.nucleotides(1, 2, 0))]
 
 
 def _linear_cases():
