@@ -38,6 +38,9 @@ WORKLOADS = {
     # name: (description, mode, ops per cell)
     "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
                   "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50),
+    "affine500_medianlike": ("configs[1], median-like operands: as affine500 plus 0.5% IUPAC ambiguities and 10% of positions "
+                             "carrying the gap bit (what internal-node medians look like; exercises the block-diagonal "
+                             "state)", 3, 50),
     "linear500": ("cfg 2-lin: DNA pairs 500 bp, linear gaps (subst 1, indel 2), deltaw as Sequence.Align.cost_2 computes it, "
                   "align_2 + ancestor_2 + median_2_with_gaps", 1, 10),
     "protein300": ("configs[2] (3a): protein pairs 300 aa, 22x22 matrix 1/2, deltaw as the product computes it "
@@ -50,9 +53,10 @@ def workload(n_pairs: int, seed: int, name: str = "affine500"):
     """Returns (cm, pool, pairs, deltaw or None)."""
     from poyd_b200 import cost_matrix as CM, sequence as S, synth
 
-    if name == "affine500":
+    if name in ("affine500", "affine500_medianlike"):
         cm = CM.nucleotides(1, 2, 3)
-        pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512)
+        extra = dict(ambiguity=0.005, gap_ambiguity=0.10) if name.endswith("medianlike") else {}
+        pool, pairs = synth.pair_batch(n_pairs, 500, seed=seed, min_len=450, stride=512, **extra)
         return cm, pool, pairs, None
     if name == "linear500":
         cm = CM.default_nucleotides()

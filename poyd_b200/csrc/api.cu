@@ -469,7 +469,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     return POYB200_OK;
 }
 
-extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool upload) {
     if (!ctx || !b) return POYB200_EINVAL;
     if (mode < 0 || mode > 3) return fail(ctx, POYB200_EINVAL, "bad mode");
     cudaSetDevice(ctx->device);
@@ -496,13 +496,15 @@ extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b)
             CK(ctx->d_out[3].reserve(ob));
         }
     }
-    if (n) {
+    if (n && upload) {
         CK(cudaMemcpyAsync(ctx->d_pool.p, b->pool, b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->staged = true;
     return POYB200_OK;
 }
+
+extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b) { return stage_impl(ctx, mode, b, true); }
 
 // Fill + traceback of one chunk on the compute stream.
 static int run_chunk(poyb200_ctx *ctx, size_t ci) {
@@ -624,30 +626,68 @@ extern "C" int poyb200_fetch(poyb200_ctx *ctx) {
     return POYB200_OK;
 }
 
-// One-shot call: results of a chunk leave on the copy-out stream while the next chunks compute.
+// One-shot call, pipelined over chunks on three streams:
+//   s_in    uploads the task array and then the pool in slices;
+//   stream  runs fill + traceback of chunk k as soon as the slices its pairs reference have arrived;
+//   s_out   downloads the results of chunk k while chunk k+1 computes (needs the caller's pair order, i.e. one
+//           kernel class; otherwise one download at the end).
 static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
-    int rc = poyb200_stage(ctx, mode, b);
+    int rc = stage_impl(ctx, mode, b, false);
     if (rc) return rc;
-    if (!ctx->in_order || ctx->chunks.size() < 2) {
-        rc = poyb200_run(ctx);
-        if (rc) return rc;
-        return poyb200_fetch(ctx);
-    }
+    const size_t n = ctx->tasks.size(), nch = ctx->chunks.size();
+    if (n == 0) return POYB200_OK;
     rc = prepare_events(ctx);
     if (rc) return rc;
-    while (ctx->ev_done.size() < ctx->chunks.size()) {
+    constexpr size_t SLICE = (size_t) 32 << 20;
+    const size_t nslices = (b->pool_bytes + SLICE - 1) / SLICE;
+    while (ctx->ev_done.size() < nch + nslices + 1) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->ev_done.push_back(e);
     }
-    for (size_t ci = 0; ci < ctx->chunks.size(); ci++) {
+    cudaEvent_t *ev_chunk = ctx->ev_done.data(), *ev_slice = ctx->ev_done.data() + nch, ev_tasks = ctx->ev_done[nch + nslices];
+    // last pool byte each chunk needs (prefix maximum: slices arrive in order)
+    std::vector<size_t> need(nch, 0);
+    parallel_for(ctx->host_threads, nch, [&](size_t lo, size_t hi, int) {
+        for (size_t ci = lo; ci < hi; ci++) {
+            size_t m = 0;
+            for (size_t k = ctx->chunks[ci].begin; k < ctx->chunks[ci].end; k++) {
+                const Task &t = ctx->tasks[k];
+                m = std::max(m, std::max((size_t) t.off_r + t.lr, (size_t) t.off_c + t.lc));
+            }
+            need[ci] = m;
+        }
+    });
+    for (size_t ci = 1; ci < nch; ci++) need[ci] = std::max(need[ci], need[ci - 1]);
+    CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, ctx->s_in));
+    CK(cudaEventRecord(ev_tasks, ctx->s_in));
+    for (size_t k = 0; k < nslices; k++) {
+        const size_t lo = k * SLICE, len = std::min(SLICE, b->pool_bytes - lo);
+        CK(cudaMemcpyAsync(ctx->d_pool.p + lo, b->pool + lo, len, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ev_slice[k], ctx->s_in));
+    }
+    CK(cudaStreamWaitEvent(ctx->stream, ev_tasks, 0));
+    size_t waited = 0;  // slices the compute stream already waits for
+    for (size_t ci = 0; ci < nch; ci++) {
+        const size_t upto = std::min(nslices, (need[ci] + SLICE - 1) / SLICE);
+        if (upto > waited) {
+            CK(cudaStreamWaitEvent(ctx->stream, ev_slice[upto - 1], 0));
+            waited = upto;
+        }
         rc = run_chunk(ctx, ci);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_done[ci], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[ci], 0));
-        rc = fetch_range(ctx, ctx->chunks[ci].begin, ctx->chunks[ci].end, ctx->s_out);
+        if (ctx->in_order) {
+            CK(cudaEventRecord(ev_chunk[ci], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->s_out, ev_chunk[ci], 0));
+            rc = fetch_range(ctx, ctx->chunks[ci].begin, ctx->chunks[ci].end, ctx->s_out);
+            if (rc) return rc;
+        }
+    }
+    if (!ctx->in_order) {
+        rc = fetch_range(ctx, 0, n, ctx->stream);
         if (rc) return rc;
     }
+    CK(cudaStreamSynchronize(ctx->s_in));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->s_out));
     return POYB200_OK;
