@@ -121,6 +121,42 @@ int poyb200_batch_align_affine_3(poyb200_ctx *ctx, const poyb200_batch *b);  /* 
 int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride,
                            const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len);
 
+/* --- three sequences: algn_CAML_simple_3 / algn_CAML_align_3d / algn_CAML_median_3 (src/algn.c:3458-3475, 3960-3985,
+ * 4225-4235; sequence.ml:727-762) ----------------------------------------------------------------------------------
+ * The reference's cube fill is defective (its neighbour-row pointers lag by one row per plane) and its
+ * median loop never advances (A14); "identical to the reference" therefore means reproducing those results, which is
+ * what these entry points do.  status[t] = 1 marks triples whose traceback the reference would run off the start of a
+ * sequence (it does not check, A13): nothing is returned for them beyond the cost. */
+#define POYB200_WANT3_ALIGNED 1u
+#define POYB200_WANT3_MEDIAN 2u
+
+typedef struct poyb200_cm3 {
+    int32_t lcm, gap;
+    const int32_t *cost;   /* (1 << lcm)^3 entries indexed ((a << lcm) + b) << lcm) + c  (src/cm.c:509-523) */
+    const uint8_t *median; /* same indexing */
+} poyb200_cm3;
+
+typedef struct poyb200_batch3 {
+    const uint8_t *pool;
+    size_t pool_bytes;
+    const int64_t *seq_off;
+    const int32_t *seq_len;
+    int32_t n_seqs;
+    const int32_t *triples; /* 3 * n_triples sequence indices (s1, s2, s3 of algn_nw_3d) */
+    int32_t n_triples;
+    uint32_t want;          /* POYB200_WANT3_* */
+    int32_t *cost;          /* n_triples */
+    uint8_t *aligned_1, *aligned_2, *aligned_3, *median; /* rows of out_stride >= l1 + l2 + l3 bytes, right aligned */
+    int64_t out_stride;
+    int32_t *out_len;       /* n_triples: aligned length (= median length) */
+    int32_t *status;        /* n_triples */
+} poyb200_batch3;
+
+int poyb200_set_cm_3d(poyb200_ctx *ctx, const poyb200_cm3 *cm);
+int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b);
+/* cells of the cube: l1 * l2 * l3 */
+int64_t poyb200_cells_3d(int32_t l1, int32_t l2, int32_t l3);
+
 /* --- split form, used to time the device-resident part on its own ------------------------------------ */
 /* mode: 0 cost_2, 1 align_2, 2 cost_affine_3, 3 align_affine_3 */
 int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b); /* plan + H2D; keeps b for fetch */

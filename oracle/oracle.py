@@ -48,6 +48,10 @@ class _PoCm(C.Structure):
                 ("prepend", _i32p), ("tail", _i32p)]
 
 
+class _PoCm3(C.Structure):
+    _fields_ = [("lcm", C.c_int32), ("gap", C.c_int32), ("cost3", _i32p), ("median3", _u8p)]
+
+
 class _PoBand(C.Structure):
     _fields_ = [("full", C.c_int), ("dlo", C.c_int), ("dhi", C.c_int)]
 
@@ -146,6 +150,68 @@ class Port(_Base):
         self.L.po_batch(C.byref(self.c), mode, _p(pool, _u8p), _p(off, _i64p), _p(length, _i32p), _p(pairs, _i32p),
                         _p(deltaw, _i32p), n, nthreads, _p(cost, _i32p), _p(med, _u8p), _p(medwg, _u8p),
                         _p(ra, _u8p), _p(rb, _u8p), _p(lens, _i32p), C.c_longlong(stride))
+
+
+class Port3:
+    """3-D cube in the reference's executed (defective) form, plain-C port."""
+
+    kind = "port"
+
+    def __init__(self, cm3):
+        if not os.path.exists(PORT_SO):
+            build(ref=False)
+        self.L = C.CDLL(PORT_SO)
+        self._cost = np.ascontiguousarray(cm3.cost, np.int32)
+        self._med = np.ascontiguousarray(cm3.median, np.uint8)
+        self.c = _PoCm3(cm3.lcm, cm3.gap, _p(self._cost, _i32p), _p(self._med, _u8p))
+
+    def align_3(self, s1, s2, s3, want_dir=False):
+        """Returns (cost, status, r1, r2, r3, median[, dir])."""
+        s1, s2, s3 = _u8(s1), _u8(s2), _u8(s3)
+        l1, l2, l3 = len(s1), len(s2), len(s3)
+        d = np.zeros(l1 * l2 * l3, np.uint8)
+        cost = self.L.po_cost_3(C.byref(self.c), _p(s1, _u8p), l1, _p(s2, _u8p), l2, _p(s3, _u8p), l3, _p(d, _u8p))
+        cap = l1 + l2 + l3
+        r = [np.zeros(cap + 1, np.uint8) for _ in range(4)]
+        ml, st = C.c_int(0), C.c_int(0)
+        n = self.L.po_backtrack_3(C.byref(self.c), _p(d, _u8p), _p(s1, _u8p), l1, _p(s2, _u8p), l2, _p(s3, _u8p), l3,
+                                  _p(r[0], _u8p), _p(r[1], _u8p), _p(r[2], _u8p), _p(r[3], _u8p), C.byref(ml), C.byref(st))
+        res = (cost, st.value, r[0][:n].copy(), r[1][:n].copy(), r[2][:n].copy(), r[3][: ml.value].copy())
+        return res + (d,) if want_dir else res
+
+
+class Reference3:
+    """3-D cube through the compiled reference (algn_nw_3d + backtrack_3d + algn_get_median_3d)."""
+
+    kind = "reference"
+
+    def __init__(self, cm3):
+        L = self.L = C.CDLL(REF_SO)
+        L.ref_cm3_create.restype = C.c_void_p
+        L.ref_ws_create.restype = C.c_void_p
+        cost = np.ascontiguousarray(cm3.cost, np.int32)
+        med = np.ascontiguousarray(cm3.median, np.uint8)
+        self.h = C.c_void_p(L.ref_cm3_create(cm3.a_sz_in, cm3.combinations, cm3.cost_model_type, cm3.gap_open,
+                                             cm3.all_elements, _p(cost, _i32p), _p(med, _u8p)))
+        self.ws = C.c_void_p(L.ref_ws_create())
+
+    def align_3(self, s1, s2, s3, want_dir=False):
+        s1, s2, s3 = _u8(s1), _u8(s2), _u8(s3)
+        l1, l2, l3 = len(s1), len(s2), len(s3)
+        cap = l1 + l2 + l3
+        r = [np.zeros(cap + 1, np.uint8) for _ in range(4)]
+        rl, ml, st = C.c_int(0), C.c_int(0), C.c_int(0)
+        d = np.zeros(l1 * l2 * l3, np.uint16) if want_dir else None
+        cost = self.L.ref_align_3(self.h, self.ws, _p(s1, _u8p), l1, _p(s2, _u8p), l2, _p(s3, _u8p), l3, _p(r[0], _u8p),
+                                  _p(r[1], _u8p), _p(r[2], _u8p), C.byref(rl), _p(r[3], _u8p), C.byref(ml), C.byref(st),
+                                  _p(d, _u16p))
+        n = rl.value
+        res = (cost, st.value, r[0][:n].copy(), r[1][:n].copy(), r[2][:n].copy(), r[3][: ml.value].copy())
+        return res + (d,) if want_dir else res
+
+
+def best_checker_3(cm3):
+    return Reference3(cm3) if Reference.available() else Port3(cm3)
 
 
 class Reference(_Base):

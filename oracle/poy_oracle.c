@@ -526,3 +526,138 @@ int po_batch(const po_cm *c, int mode, const uint8_t *pool, const long long *off
     free(th); free(args);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------
+ * 3-D: algn_fill_cube / backtrack_3d / algn_get_median_3d AS THE REFERENCE EXECUTES THEM.
+ *
+ * The cube is l1 planes x l2 rows x l3 cells, filled row by row.  Row (i, j) has linear index r = i*l2 + j.  The
+ * reference sets its three neighbour-row pointers once before the plane loop and advances them l2-1 rows per plane
+ * (src/algn.c:2978-2982, 3023-3025) instead of l2, so for i >= 1 row (i, j >= 1) reads
+ *     upper = 1 + (i-1)(l2-1) + (j-1),   diag = upper - 1,   prev = i(l2-1) + (j-1)
+ * and row (i, 0) reads diag = (i-1)(l2-1) -- not the rows (i-1, j), (i-1, j-1), (i, j-1) a correct recurrence
+ * needs.  All of these are earlier rows, so the result is deterministic; it is simply not an optimal alignment
+ * cost.  Direction codes (src/matrices.h:34-40): P1 1, P2 2, P3 4, S1 8, S2 16, S3 32, SS 64; a later candidate
+ * replaces an earlier one only if strictly cheaper, order P3, P1, P2, S3, S1, S2, SS.
+ */
+typedef struct po_cm3 {
+    int32_t lcm, gap;
+    const int32_t *cost3;   /* (1<<lcm)^3, index ((a << lcm) + b) << lcm) + c   src/cm.c:509-523 */
+    const uint8_t *median3;
+} po_cm3;
+
+static inline int po_cost3(const po_cm3 *c, int a, int b, int d) { return c->cost3[(((a << c->lcm) + b) << c->lcm) + d]; }
+
+/* dir: l1*l2*l3 bytes (one code per cell) or NULL.  Returns mm[-1] of src/algn.c:3054. */
+int po_cost_3(const po_cm3 *c, const uint8_t *s1, int l1, const uint8_t *s2, int l2, const uint8_t *s3, int l3,
+              uint8_t *dir) {
+    const int gap = c->gap;
+    size_t nrows = (size_t) l1 * l2;
+    int *M = (int *) malloc(sizeof(int) * nrows * (size_t) l3);
+    int *gg = (int *) malloc(sizeof(int) * (size_t) l3);
+    for (int k = 0; k < l3; k++) gg[k] = po_cost3(c, gap, gap, s3[k]);
+#define ROW(r) (M + (size_t) (r) * l3)
+#define DIR(r, k, v) do { if (dir) dir[(size_t) (r) * l3 + (k)] = (uint8_t) (v); } while (0)
+    /* plane 0 (:2918-2962) */
+    ROW(0)[0] = 0; DIR(0, 0, 16);
+    for (int k = 1; k < l3; k++) { ROW(0)[k] = ROW(0)[k - 1] + gg[k]; DIR(0, k, 64); }
+    for (int j = 1; j < l2; j++) {
+        int *mm = ROW(j), *prev = ROW(j - 1), b = s2[j];
+        int g0 = po_cost3(c, gap, b, s3[0]);
+        mm[0] = prev[0] + g0; DIR(j, 0, 1);
+        for (int k = 1; k < l3; k++) {
+            int v = prev[k] + g0, d = 1, t = prev[k - 1] + po_cost3(c, gap, b, s3[k]);
+            if (t < v) { v = t; d = 8; }
+            t = mm[k - 1] + gg[k];
+            if (t < v) { v = t; d = 64; }
+            mm[k] = v; DIR(j, k, d);
+        }
+    }
+    for (int i = 1; i < l1; i++) {
+        int a = s1[i];
+        int a0 = po_cost3(c, a, gap, s3[0]);
+        /* first row of the plane (:2990-3013): the "diag" pointer stands for the row above */
+        {
+            size_t r = (size_t) i * l2;
+            int *mm = ROW(r), *D = ROW((size_t) (i - 1) * (l2 - 1));
+            mm[0] = D[0] + a0; DIR(r, 0, 4);
+            for (int k = 1; k < l3; k++) {
+                int v = D[k] + a0, d = 4, t = D[k - 1] + po_cost3(c, a, gap, s3[k]);
+                if (t < v) { v = t; d = 32; }
+                t = gg[k] + mm[k - 1];
+                if (t < v) { v = t; d = 64; }
+                mm[k] = v; DIR(r, k, d);
+            }
+        }
+        for (int j = 1; j < l2; j++) {
+            size_t r = (size_t) i * l2 + j;
+            int b = s2[j];
+            int *mm = ROW(r);
+            const int *U = ROW((size_t) 1 + (size_t) (i - 1) * (l2 - 1) + (j - 1));
+            const int *D = U - l3;
+            const int *P = ROW((size_t) i * (l2 - 1) + (j - 1));
+            int s1gg = a0, gs2g = po_cost3(c, gap, b, s3[0]), s1s2g = po_cost3(c, a, b, s3[0]);
+            for (int k = 0; k < l3; k++) {
+                /* fill_parallel (:2840-2857) */
+                int v = U[k] + s1gg, d = 4, t = P[k] + gs2g;
+                if (t < v) { v = t; d = 1; }
+                t = D[k] + s1s2g;
+                if (t < v) { v = t; d = 2; }
+                if (k >= 1) {
+                    /* fill_moved (:2812-2836) */
+                    t = U[k - 1] + po_cost3(c, a, gap, s3[k]);
+                    if (t < v) { v = t; d = 32; }
+                    t = P[k - 1] + po_cost3(c, gap, b, s3[k]);
+                    if (t < v) { v = t; d = 8; }
+                    t = D[k - 1] + po_cost3(c, a, b, s3[k]);
+                    if (t < v) { v = t; d = 16; }
+                    /* the in-row pass (:3039-3046) */
+                    t = mm[k - 1] + gg[k];
+                    if (t < v) { v = t; d = 64; }
+                }
+                mm[k] = v; DIR(r, k, d);
+            }
+        }
+    }
+    int res = ROW(nrows - 1)[l3 - 1];
+#undef ROW
+#undef DIR
+    free(M); free(gg);
+    return res;
+}
+
+/* backtrack_3d (:3829-3905) + algn_get_median_3d (:4160-4173).  Outputs need l1+l2+l3 (+1 for med) bytes, left aligned
+ * on return.  *status = 1 (and nothing is produced) when the reference's walk would index a sequence below 0, which
+ * the reference does not check. */
+int po_backtrack_3(const po_cm3 *c, const uint8_t *dir, const uint8_t *s1, int l1, const uint8_t *s2, int l2,
+                   const uint8_t *s3, int l3, uint8_t *r1, uint8_t *r2, uint8_t *r3, uint8_t *med, int *medlen,
+                   int *status) {
+    int cap = l1 + l2 + l3, n = 0, i1 = l1 - 1, i2 = l2 - 1, i3 = l3 - 1;
+    long long p = (long long) l1 * l2 * l3 - 1, plane = (long long) l2 * l3, line = l3;
+    uint8_t gap = (uint8_t) c->gap;
+    *status = 0;
+    while (p > 0) {
+        int v = dir[p], u1 = 0, u2 = 0, u3 = 0;
+        if (v & 16) { u1 = u2 = u3 = 1; p -= plane + line + 1; }
+        else if (v & 32) { u1 = u3 = 1; p -= plane + 1; }
+        else if (v & 8) { u2 = u3 = 1; p -= line + 1; }
+        else if (v & 4) { u1 = 1; p -= plane; }
+        else if (v & 64) { u3 = 1; p -= 1; }
+        else if (v & 1) { u2 = 1; p -= line; }
+        else { u1 = u2 = 1; p -= plane + line; }
+        if ((u1 && i1 < 0) || (u2 && i2 < 0) || (u3 && i3 < 0) || n >= cap) { *status = 1; *medlen = 0; return 0; }
+        n++;
+        r1[cap - n] = u1 ? s1[i1--] : gap;
+        r2[cap - n] = u2 ? s2[i2--] : gap;
+        r3[cap - n] = u3 ? s3[i3--] : gap;
+    }
+    /* the median loop never moves its pointers: n copies of the median of the LAST column */
+    if (n > 0) {
+        int m = c->median3[(((r1[cap - 1] << c->lcm) + r2[cap - 1]) << c->lcm) + r3[cap - 1]];
+        memset(med, m, n);
+    }
+    *medlen = n;
+    memmove(r1, r1 + cap - n, n);
+    memmove(r2, r2 + cap - n, n);
+    memmove(r3, r3 + cap - n, n);
+    return n;
+}

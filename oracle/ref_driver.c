@@ -335,3 +335,69 @@ int ref_batch(void *cmh, int mode, const unsigned char *pool, const long long *o
     free(th); free(args);
     return 0;
 }
+
+/* ---- 3-D: algn_CAML_simple_3 / backtrack_3d / median_3 (src/algn.c:3458-3475, 3960-3985, 4225-4235) ------------
+ * The reference's cube fill is defective; this driver runs it as it is. */
+extern cm_3dt cm_set_val_3d(int a_sz, int combinations, int do_aff, int gap_open, int all_elements, cm_3dt res);
+extern int algn_nw_3d(const seqt s1, const seqt s2, const seqt s3, const cm_3dt c, matricest m, int w);
+extern void backtrack_3d(const seqt s1, const seqt s2, seqt s3, seqt r1, seqt r2, seqt r3, matricest m, const cm_3dt c);
+extern void algn_get_median_3d(seqt s1, seqt s2, seqt s3, cm_3dt m, seqt sm);
+
+typedef struct ref_cm3 { struct cm_3d c; } ref_cm3;
+
+/* cost3 / median3: (1 << lcm)^3 entries indexed ((a << lcm) + b) << lcm) + c (src/cm.c:509-523). */
+void *ref_cm3_create(int a_sz_in, int combinations, int cost_model, int gap_open, int all_elements, const int *cost3,
+                     const unsigned char *median3) {
+    ref_cm3 *r = (ref_cm3 *) calloc(1, sizeof(ref_cm3));
+    cm_set_val_3d(a_sz_in, combinations, cost_model, gap_open, all_elements, &r->c);
+    size_t n = (size_t) 1 << (3 * r->c.lcm);
+    memcpy(r->c.cost, cost3, n * sizeof(int));
+    memcpy(r->c.median, median3, n);
+    return r;
+}
+void ref_cm3_free(void *h) { ref_cm3 *r = (ref_cm3 *) h; free(r->c.cost); free(r->c.median); free(r); }
+
+/* Returns the cost.  If r1 != NULL also runs backtrack_3d, but only after checking on the direction cube that the
+ * reference's walk never indexes a sequence below 0 (it does not check, src/algn.c:3871-3903); *status = 1 and no
+ * walk otherwise.  r1..r3 need l1+l2+l3 bytes, med l1+l2+l3+1. */
+int ref_align_3(void *cmh, void *wsh, const unsigned char *s1, int l1, const unsigned char *s2, int l2,
+                const unsigned char *s3, int l3, unsigned char *r1, unsigned char *r2, unsigned char *r3, int *rlen,
+                unsigned char *med, int *medlen, int *status, unsigned short *dir_out) {
+    ref_cm3 *c = (ref_cm3 *) cmh; ref_ws *w = (ref_ws *) wsh;
+    seqt a = mk_seq_from(s1, l1, l1), b = mk_seq_from(s2, l2, l2), d = mk_seq_from(s3, l3, l3);
+    int res = algn_nw_3d(a, b, d, &c->c, &w->m, 0);
+    if (dir_out) memcpy(dir_out, w->m.cube_d, sizeof(unsigned short) * (size_t) l1 * l2 * l3);
+    if (status) *status = 0;
+    if (r1) {
+        /* dry run of the walk (same order of tests as backtrack_3d) */
+        long long p = (long long) l1 * l2 * l3 - 1, plane = (long long) l2 * l3, line = l3;
+        int i1 = l1 - 1, i2 = l2 - 1, i3 = l3 - 1, ok = 1, n = 0;
+        const unsigned short *dm = w->m.cube_d;
+        while (p > 0) {
+            int v = dm[p], u1 = 0, u2 = 0, u3 = 0;
+            if (v & 16) { u1 = u2 = u3 = 1; p -= plane + line + 1; }
+            else if (v & 32) { u1 = u3 = 1; p -= plane + 1; }
+            else if (v & 8) { u2 = u3 = 1; p -= line + 1; }
+            else if (v & 4) { u1 = 1; p -= plane; }
+            else if (v & 64) { u3 = 1; p -= 1; }
+            else if (v & 1) { u2 = 1; p -= line; }
+            else if (v & 2) { u1 = u2 = 1; p -= plane + line; }
+            else { ok = 0; break; }
+            if ((u1 && i1 < 0) || (u2 && i2 < 0) || (u3 && i3 < 0)) { ok = 0; break; }
+            i1 -= u1; i2 -= u2; i3 -= u3;
+            if (++n > l1 + l2 + l3) { ok = 0; break; }
+        }
+        if (!ok) { if (status) *status = 1; *rlen = 0; *medlen = 0; }
+        else {
+            int cap = l1 + l2 + l3;
+            seqt x = mk_seq(cap), y = mk_seq(cap), z = mk_seq(cap), sm = mk_seq(cap + 1);
+            backtrack_3d(a, b, d, x, y, z, &w->m, &c->c);
+            *rlen = seq_out(x, r1); seq_out(y, r2); seq_out(z, r3);
+            algn_get_median_3d(x, y, z, &c->c, sm);
+            *medlen = seq_out(sm, med);
+            free(x); free(y); free(z); free(sm);
+        }
+    }
+    free(a); free(b); free(d);
+    return res;
+}

@@ -27,12 +27,24 @@ class Batch(C.Structure):
                 ("out_stride", C.c_int64), ("out_len", C.c_void_p)]
 
 
+class CM3(C.Structure):
+    _fields_ = [("lcm", C.c_int32), ("gap", C.c_int32), ("cost", i32p), ("median", u8p)]
+
+
+class Batch3(C.Structure):
+    _fields_ = [("pool", C.c_void_p), ("pool_bytes", C.c_size_t), ("seq_off", C.c_void_p), ("seq_len", C.c_void_p),
+                ("n_seqs", C.c_int32), ("triples", C.c_void_p), ("n_triples", C.c_int32), ("want", C.c_uint32),
+                ("cost", C.c_void_p), ("aligned_1", C.c_void_p), ("aligned_2", C.c_void_p), ("aligned_3", C.c_void_p),
+                ("median", C.c_void_p), ("out_stride", C.c_int64), ("out_len", C.c_void_p), ("status", C.c_void_p)]
+
+
 EXPORTS = [
     "poyb200_create", "poyb200_destroy", "poyb200_last_error", "poyb200_version", "poyb200_set_cm",
     "poyb200_host_alloc", "poyb200_host_free", "poyb200_batch_cost_2", "poyb200_batch_align_2",
     "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3", "poyb200_batch_median_2", "poyb200_stage",
     "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
-    "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak",
+    "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak", "poyb200_set_cm_3d",
+    "poyb200_batch_align_3", "poyb200_cells_3d",
 ]
 
 _lib = None
@@ -75,5 +87,9 @@ def lib() -> C.CDLL:
     L.poyb200_stream.argtypes = [C.c_void_p]
     L.poyb200_stream.restype = C.c_void_p
     L.poyb200_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.poyb200_set_cm_3d.argtypes = [C.c_void_p, C.POINTER(CM3)]
+    L.poyb200_batch_align_3.argtypes = [C.c_void_p, C.POINTER(Batch3)]
+    L.poyb200_cells_3d.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.poyb200_cells_3d.restype = C.c_int64
     _lib = L
     return L

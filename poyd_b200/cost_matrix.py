@@ -310,3 +310,63 @@ def nucleotides(trans: int = 1, gaps: int = 2, gap_opening: Optional[int] = None
         m = m.clone()
         m.set_affine(("Affine", gap_opening))
     return m
+
+
+# ---- Cost_matrix.Three_D (src/cost_matrix.ml:703-891) ------------------------------------------------------------
+@dataclasses.dataclass
+class CostMatrix3D:
+    """Flat image of ``struct cm_3d`` (src/cm.h:222-241): cost / median indexed ((a << lcm) + b) << lcm) + c."""
+
+    a_sz_in: int
+    a_sz: int
+    lcm: int
+    gap: int
+    cost_model_type: int
+    combinations: int
+    gap_open: int
+    all_elements: int
+    cost: np.ndarray  # int32 [dim, dim, dim]
+    median: np.ndarray  # uint8 [dim, dim, dim]
+
+
+def of_two_dim(m: CostMatrix) -> CostMatrix3D:
+    """Cost_matrix.Three_D.of_two_dim (cost_matrix.ml:853-862) = cm_CAML_clone_to_3d (src/cm.c:1435) followed by
+    of_two_dim_comb (:803-851) or of_two_dim_no_comb (:785-801)."""
+    dim = 1 << m.lcm
+    nm = CostMatrix3D(a_sz_in=m.lcm if m.combinations else m.a_sz, a_sz=m.a_sz, lcm=m.lcm, gap=m.gap,
+                      cost_model_type=m.cost_model_type, combinations=m.combinations, gap_open=m.gap_open,
+                      all_elements=m.all_elements, cost=np.zeros((dim, dim, dim), np.int32),
+                      median=np.zeros((dim, dim, dim), np.uint8))
+    c2 = m.cost.astype(np.int64)
+    if m.combinations:
+        alph, gap, lcm = m.a_sz, m.gap, m.lcm
+        rng = np.arange(1, alph + 1)
+        best = np.full((alph, alph, alph), _MAX_INT, np.int64)
+        med = np.zeros((alph, alph, alph), np.int64)
+        for l in range(lcm):
+            inter = 1 << l
+            ci = c2[inter, 1:alph + 1]
+            cost = ci[:, None, None] + ci[None, :, None] + ci[None, None, :]
+            if not m.is_metric and inter == gap:
+                sh = ((rng & inter) != 0).astype(np.int64)
+                ok = (sh[:, None, None] + sh[None, :, None] + sh[None, None, :]) >= 2
+                cost = np.where(ok, cost, _MAX_INT)
+            lt, eq = cost < best, cost == best
+            med = np.where(lt, inter, np.where(eq, med | inter, med))
+            best = np.where(lt, cost, best)
+        # "We pick only one median among all options": the lowest set bit (pick_bit, :808-817)
+        low = med & (-med)
+        nm.cost[1:alph + 1, 1:alph + 1, 1:alph + 1] = best
+        nm.median[1:alph + 1, 1:alph + 1, 1:alph + 1] = low
+    else:
+        alph = m.a_sz - 1
+        # of_two_dim_no_comb starts from a zeroed matrix and only lowers costs (`cost < old_cost`), so with
+        # non-negative 2-D costs nothing is ever written: reproduce exactly that (a reference quirk)
+        for l in range(1, alph + 1):
+            cl = c2[l, 1:alph + 1]
+            cost = cl[:, None, None] + cl[None, :, None] + cl[None, None, :]
+            old = nm.cost[1:alph + 1, 1:alph + 1, 1:alph + 1].astype(np.int64)
+            lt = cost < old
+            nm.cost[1:alph + 1, 1:alph + 1, 1:alph + 1] = np.where(lt, cost, old)
+            nm.median[1:alph + 1, 1:alph + 1, 1:alph + 1] = np.where(lt, l, nm.median[1:alph + 1, 1:alph + 1, 1:alph + 1])
+    return nm

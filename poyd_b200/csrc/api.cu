@@ -12,6 +12,7 @@
 #include "stripe_kernels.cuh"
 #include "lin_stripe_kernels.cuh"
 #include "trace_kernels.cuh"
+#include "cube_kernels.cuh"
 
 using namespace poyb200;
 
@@ -83,6 +84,12 @@ struct poyb200_ctx {
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_done;
     bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
+    // 3-D
+    bool has_cm3 = false;
+    DevCM3 dcm3{};
+    DevBuf<int> d_cost3, d_ring, d_status;
+    DevBuf<uint8_t> d_median3;
+    DevBuf<Task3> d_tasks3;
     // stats
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -217,6 +224,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
     ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release();
+    ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->chunk_ev) cudaEventDestroy(e);
@@ -767,3 +775,128 @@ extern "C" int poyb200_debug_counters(int *out) {
     return (int) cudaMemcpyFromSymbol(out, g_dbg, sizeof(int) * 4);
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------------------
+// three sequences
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int64_t poyb200_cells_3d(int32_t l1, int32_t l2, int32_t l3) { return (int64_t) l1 * l2 * l3; }
+
+extern "C" int poyb200_set_cm_3d(poyb200_ctx *ctx, const poyb200_cm3 *cm) {
+    if (!ctx || !cm || !cm->cost || !cm->median) return ctx ? fail(ctx, POYB200_EINVAL, "poyb200_set_cm_3d: NULL table") : POYB200_EINVAL;
+    if (cm->lcm < 1 || cm->lcm > 6) return fail(ctx, POYB200_EINVAL, "poyb200_set_cm_3d: lcm out of range");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t) 1 << (3 * cm->lcm);
+    CK(ctx->d_cost3.reserve(n));
+    CK(ctx->d_median3.reserve(n));
+    CK(cudaMemcpyAsync(ctx->d_cost3.p, cm->cost, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_median3.p, cm->median, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dcm3 = DevCM3{cm->lcm, cm->gap, ctx->d_cost3.p, ctx->d_median3.p};
+    ctx->has_cm3 = true;
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) {
+    if (!ctx || !b) return POYB200_EINVAL;
+    if (!ctx->has_cm3) return fail(ctx, POYB200_ENOCM, "no 3-D cost matrix loaded (poyb200_set_cm_3d)");
+    const int n = b->n_triples;
+    if (n < 0 || b->n_seqs < 0) return fail(ctx, POYB200_EINVAL, "negative count");
+    if (n == 0) return POYB200_OK;
+    if (!b->pool || !b->seq_off || !b->seq_len || !b->triples || !b->cost) return fail(ctx, POYB200_EINVAL, "NULL input array");
+    if (b->pool_bytes >= ((size_t) 1 << 32)) return fail(ctx, POYB200_EINVAL, "pool larger than 4 GiB");
+    const bool want_al = (b->want & POYB200_WANT3_ALIGNED) != 0, want_med = (b->want & POYB200_WANT3_MEDIAN) != 0;
+    const bool bt = want_al || want_med;
+    if (want_al && (!b->aligned_1 || !b->aligned_2 || !b->aligned_3)) return fail(ctx, POYB200_EINVAL, "WANT3_ALIGNED without buffers");
+    if (want_med && !b->median) return fail(ctx, POYB200_EINVAL, "WANT3_MEDIAN without buffer");
+    if (bt && (!b->out_len || !b->status)) return fail(ctx, POYB200_EINVAL, "out_len / status is NULL");
+    cudaSetDevice(ctx->device);
+    std::vector<Task3> tasks((size_t) n);
+    size_t max_ring = 1;
+    long long maxcap = 16;
+    for (int s = 0; s < b->n_seqs; s++) {
+        if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN) return fail(ctx, POYB200_ESEQLEN, "sequence empty or longer than 16384");
+        if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes) return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
+    }
+    for (int p = 0; p < n; p++) {
+        Task3 t{};
+        int idx[3];
+        for (int k = 0; k < 3; k++) {
+            idx[k] = b->triples[3 * p + k];
+            if (idx[k] < 0 || idx[k] >= b->n_seqs) return fail(ctx, POYB200_EINVAL, "triple index out of range");
+        }
+        t.off1 = (uint32_t) b->seq_off[idx[0]]; t.off2 = (uint32_t) b->seq_off[idx[1]]; t.off3 = (uint32_t) b->seq_off[idx[2]];
+        t.l1 = b->seq_len[idx[0]]; t.l2 = b->seq_len[idx[1]]; t.l3 = b->seq_len[idx[2]];
+        t.triple = (uint32_t) p;
+        max_ring = std::max(max_ring, (size_t) (t.l1 + t.l2 + 3) * t.l3);
+        maxcap = std::max<long long>(maxcap, (long long) t.l1 + t.l2 + t.l3);
+        tasks[p] = t;
+    }
+    if (bt && b->out_stride < maxcap) return fail(ctx, POYB200_EINVAL, "out_stride smaller than l1 + l2 + l3");
+    const long long dstride = (maxcap + 15) & ~15ll;
+    // chunks by direction-cube bytes
+    struct C3 { size_t begin, end; };
+    std::vector<C3> chunks;
+    size_t begin = 0, off = 0, maxdir = 16;
+    for (size_t k = 0; k < tasks.size(); k++) {
+        size_t bytes = bt ? (((size_t) tasks[k].l1 * tasks[k].l2 * tasks[k].l3 + 63) & ~(size_t) 63) : 0;
+        if (k > begin && off + bytes > ctx->dir_budget) {
+            chunks.push_back(C3{begin, k});
+            maxdir = std::max(maxdir, off);
+            begin = k;
+            off = 0;
+        }
+        tasks[k].dir_off = off;
+        off += bytes;
+    }
+    chunks.push_back(C3{begin, tasks.size()});
+    maxdir = std::max(maxdir, off);
+    // CTAs: as many as keep all rings inside ~96 MB of L2, at least one per SM's worth of work
+    const size_t ring_bytes = max_ring * sizeof(int);
+    int per_sm = (int) std::max<size_t>(1, std::min<size_t>(4, ((size_t) 96 << 20) / (ring_bytes * ctx->sm_count + 1)));
+    const int grid_max = ctx->sm_count * per_sm;
+    CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+    CK(ctx->d_tasks3.reserve((size_t) n));
+    CK(ctx->d_costs.reserve((size_t) n + 1));
+    CK(ctx->d_ring.reserve(max_ring * (size_t) grid_max));
+    if (bt) {
+        CK(ctx->d_dir.reserve(maxdir));
+        CK(ctx->d_outlen.reserve((size_t) n + 4));
+        CK(ctx->d_status.reserve((size_t) n + 4));
+        const size_t ob = (size_t) n * dstride + 16;
+        if (want_al) { CK(ctx->d_out[0].reserve(ob)); CK(ctx->d_out[1].reserve(ob)); CK(ctx->d_out[2].reserve(ob)); }
+        if (want_med) CK(ctx->d_out[3].reserve(ob));
+    }
+    CK(cudaMemcpyAsync(ctx->d_pool.p, b->pool, b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tasks3.p, tasks.data(), (size_t) n * sizeof(Task3), cudaMemcpyHostToDevice, ctx->stream));
+    Out3 out{ctx->d_costs.p, ctx->d_outlen.p, ctx->d_status.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
+             dstride, b->want};
+    for (const C3 &ch : chunks) {
+        const int nt = (int) (ch.end - ch.begin);
+        const int grid = std::min(nt, grid_max);
+        cube_fill_kernel<<<grid, CUBE_THREADS, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
+                                                                 ctx->d_ring.p, max_ring, ctx->d_dir.p, ctx->d_costs.p, bt ? 1 : 0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (bt) {
+            cube_traceback_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
+                                                                              ctx->d_dir.p, out);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaMemcpyAsync(b->cost, ctx->d_costs.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bt) {
+        CK(cudaMemcpyAsync(b->out_len, ctx->d_outlen.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(b->status, ctx->d_status.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        uint8_t *dst[4] = {b->aligned_1, b->aligned_2, b->aligned_3, b->median};
+        const bool need[4] = {want_al, want_al, want_al, want_med};
+        const size_t w = (size_t) std::min<long long>(dstride, b->out_stride);
+        for (int k = 0; k < 4; k++)
+            if (need[k])
+                CK(cudaMemcpy2DAsync(dst[k] + (b->out_stride - w), (size_t) b->out_stride, ctx->d_out[k].p + (dstride - w),
+                                     (size_t) dstride, w, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged = false;
+    return POYB200_OK;
+}

@@ -308,3 +308,61 @@ def cells_linear(l1: int, l2: int, deltaw: int) -> int:
 def cells_affine(la: int, lb: int) -> int:
     """DP cells ``algn_fill_plane_3_aff`` visits (band + left-edge cells + the initialised row)."""
     return int(_lib.lib().poyb200_cells_affine(int(la), int(lb)))
+
+
+@dataclass
+class Aligned3:
+    """Result of :meth:`Align3.align_3`: rows right aligned, ``lens[t]`` elements each; ``status[t] = 1`` marks triples
+    whose traceback the reference would run off the start of a sequence (undefined there; nothing is returned)."""
+
+    cost: np.ndarray
+    lens: Optional[np.ndarray] = None
+    status: Optional[np.ndarray] = None
+    aligned_1: Optional[np.ndarray] = None
+    aligned_2: Optional[np.ndarray] = None
+    aligned_3: Optional[np.ndarray] = None
+    median: Optional[np.ndarray] = None
+
+    def get(self, what: str, t: int) -> np.ndarray:
+        buf = getattr(self, what)
+        n = int(self.lens[t])
+        return buf[t, buf.shape[1] - n:]
+
+
+class Align3(Align):
+    """``Sequence.Align.align_3`` / ``cost_3`` / ``median_3`` (src/sequence.ml:727-762, 871-893, 934-947) over a batch
+    of triples, with the reference's cube semantics as executed."""
+
+    def __init__(self, cm: CostMatrix, cm3, device: int = -1):
+        super().__init__(cm, device)
+        self._t3 = [np.ascontiguousarray(cm3.cost, np.int32), np.ascontiguousarray(cm3.median, np.uint8)]
+        c = _lib.CM3(cm3.lcm, cm3.gap, self._t3[0].ctypes.data_as(_lib.i32p), self._t3[1].ctypes.data_as(_lib.u8p))
+        self._check(self.L.poyb200_set_cm_3d(self.h, C.byref(c)))
+
+    def align_3(self, pool: SeqPool, triples, want: int = 3) -> Aligned3:
+        triples = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
+        n = len(triples)
+        b = _lib.Batch3()
+        b.pool, b.pool_bytes = pool.pool.ctypes.data, pool.pool.nbytes
+        b.seq_off, b.seq_len, b.n_seqs = pool.off.ctypes.data, pool.len.ctypes.data, len(pool)
+        b.triples, b.n_triples, b.want = triples.ctypes.data, n, want
+        res = Aligned3(cost=np.zeros(n, np.int32))
+        b.cost = res.cost.ctypes.data
+        if want:
+            stride = 16
+            if n:
+                stride = int(pool.len[triples].astype(np.int64).sum(axis=1).max())
+            stride = (stride + 15) // 16 * 16
+            res.lens, res.status = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            b.out_len, b.status, b.out_stride = res.lens.ctypes.data, res.status.ctypes.data, stride
+            if want & 1:
+                res.aligned_1, res.aligned_2, res.aligned_3 = (np.zeros((n, stride), np.uint8) for _ in range(3))
+                b.aligned_1, b.aligned_2, b.aligned_3 = (x.ctypes.data for x in (res.aligned_1, res.aligned_2, res.aligned_3))
+            if want & 2:
+                res.median = np.zeros((n, stride), np.uint8)
+                b.median = res.median.ctypes.data
+        self._check(self.L.poyb200_batch_align_3(self.h, C.byref(b)))
+        return res
+
+    def cost_3(self, pool: SeqPool, triples) -> np.ndarray:
+        return self.align_3(pool, triples, want=0).cost

@@ -345,3 +345,83 @@ def test_linear_generic_matches_stripe(S, checker_factory, monkeypatch):
                     assert np.array_equal(g.get("aligned_a", k), r1[: rl.value]), (flag, k)
                     assert np.array_equal(g.get("aligned_b", k), r2[: rl.value]), (flag, k)
     al.close()
+
+
+def test_maximum_lengths_take_the_generic_kernels(S, checker_factory):
+    """Sequences near the reference's 16384-element cap (src/seq.c:370) and pairs wider than any register shape:
+    they must run (generic CUDA kernels) and still match."""
+    from poyd_b200 import cost_matrix as CM
+
+    rng = np.random.default_rng(99)
+
+    def rnd(n, gapamb=0.0):
+        s = rng.choice(np.array([1, 2, 4, 8], np.uint8), size=n)
+        if gapamb:
+            s[rng.random(n) < gapamb] |= 16
+        return np.concatenate([[16], s]).astype(np.uint8)
+
+    a = rnd(6000, 0.02)
+    b = a.copy()
+    b[1:][rng.random(6000) < 0.1] = 4
+    seqs = [a, b, rnd(16383), rnd(2500), rnd(900), rnd(5200, 0.02)]
+    pool = S.SeqPool(seqs)
+    pairs = np.array([[0, 1], [3, 4], [4, 0], [5, 1]], np.int32)
+    aff = CM.nucleotides(1, 2, 3)
+    al = S.Align(aff)
+    o = checker_factory(aff).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=4)
+    assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), o, label="affine long")
+    al.close()
+    lin = CM.default_nucleotides()
+    al = S.Align(lin)
+    pairs = np.array([[0, 1], [3, 4], [2, 3], [1, 5]], np.int32)  # [2, 3]: 16384 x 2501, full matrix (l1 >= 1.5 l2)
+    dw = al.deltaw_for(pool, pairs)
+    o = checker_factory(lin).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=4)
+    assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear long")
+    al.close()
+
+
+def test_three_sequence_cube_as_the_reference_executes_it(S):
+    """configs[3] path (algn_nw_3d + backtrack_3d + algn_get_median_3d).  The reference's cube fill is defective
+    (SURVEY.md A12-A14); parity means the same costs, walks and medians as the compiled reference, triple by triple."""
+    from oracle import oracle
+    from poyd_b200 import cost_matrix as CM
+
+    oracle.build(ref=True)
+    cm = CM.default_nucleotides()
+    cm3 = CM.of_two_dim(cm)
+    chk = oracle.best_checker_3(cm3)
+    rng = np.random.default_rng(8)
+
+    def rnd(n):
+        return np.concatenate([[16], rng.choice(np.array([1, 2, 4, 8], np.uint8), size=n)]).astype(np.uint8)
+
+    seqs, triples = [], []
+    shapes = [(0, 0, 0), (1, 0, 2), (5, 5, 5), (12, 30, 7), (40, 40, 40), (33, 20, 70), (60, 61, 59), (1, 50, 1),
+              (90, 80, 100), (100, 100, 100), (20, 20, 600), (150, 20, 20)]
+    for (n1, n2, n3) in shapes * 2:
+        a = rnd(n1)
+        b = a.copy() if (n2 == n1 and rng.random() < 0.7) else rnd(n2)
+        if len(b) > 1:
+            b[1:][rng.random(len(b) - 1) < 0.1] = 2
+        c = a.copy() if (n3 == n1 and rng.random() < 0.7) else rnd(n3)
+        if len(c) > 1:
+            c[1:][rng.random(len(c) - 1) < 0.1] = 8
+        k = len(seqs)
+        seqs += [a, b, c]
+        triples.append((k, k + 1, k + 2))
+    pool = S.SeqPool(seqs)
+    triples = np.array(triples, np.int32)
+    al = S.Align3(cm, cm3)
+    g = al.align_3(pool, triples, want=3)
+    assert np.array_equal(al.cost_3(pool, triples), g.cost)
+    for t, (i1, i2, i3) in enumerate(triples):
+        cost, status, r1, r2, r3, med = chk.align_3(pool.seq(i1), pool.seq(i2), pool.seq(i3))
+        assert g.cost[t] == cost, (t, g.cost[t], cost)
+        assert g.status[t] == status, t
+        if status == 0:
+            assert g.lens[t] == len(r1), t
+            assert np.array_equal(g.get("aligned_1", t), r1), t
+            assert np.array_equal(g.get("aligned_2", t), r2), t
+            assert np.array_equal(g.get("aligned_3", t), r3), t
+            assert np.array_equal(g.get("median", t), med), t
+    al.close()
