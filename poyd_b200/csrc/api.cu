@@ -812,6 +812,7 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
     cudaSetDevice(ctx->device);
     std::vector<Task3> tasks((size_t) n);
     size_t max_ring = 1;
+    int max_l3 = 1;
     long long maxcap = 16;
     for (int s = 0; s < b->n_seqs; s++) {
         if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN) return fail(ctx, POYB200_ESEQLEN, "sequence empty or longer than 16384");
@@ -828,6 +829,7 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
         t.l1 = b->seq_len[idx[0]]; t.l2 = b->seq_len[idx[1]]; t.l3 = b->seq_len[idx[2]];
         t.triple = (uint32_t) p;
         max_ring = std::max(max_ring, (size_t) (t.l1 + t.l2 + 3) * t.l3);
+        max_l3 = std::max(max_l3, t.l3);
         maxcap = std::max<long long>(maxcap, (long long) t.l1 + t.l2 + t.l3);
         tasks[p] = t;
     }
@@ -873,7 +875,8 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
     for (const C3 &ch : chunks) {
         const int nt = (int) (ch.end - ch.begin);
         const int grid = std::min(nt, grid_max);
-        cube_fill_kernel<<<grid, CUBE_THREADS, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
+        const int cube_threads = std::min(CUBE_THREADS, std::max(64, (max_l3 + 31) & ~31));
+        cube_fill_kernel<<<grid, cube_threads, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
                                                                  ctx->d_ring.p, max_ring, ctx->d_dir.p, ctx->d_costs.p, bt ? 1 : 0);
         ctx->launches++;
         CK(cudaGetLastError());

@@ -47,8 +47,9 @@ constexpr int T_P3 = 0, T_P1 = 1, T_P2 = 2, T_S3 = 3, T_S1 = 4, T_S2 = 5, T_SS =
 constexpr int CUBE_INF = 0x3fffffff;
 
 // Exclusive prefix-min over the block, in thread order; `carry` (in/out, block-uniform) is the minimum of everything
-// that came before this call's elements.  Two __syncthreads.
-__device__ __forceinline__ int block_excl_prefix_min(int v, int &carry, int *s_warp) {
+// that came before this call's elements.  One __syncthreads: the warp totals go through a double-buffered array
+// (s_warp[2][32], `parity` flips per call) and are combined with redux.sync.
+__device__ __forceinline__ int block_excl_prefix_min(int v, int &carry, int (*s_warp)[32], int &parity) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     int inc = v;
 #pragma unroll
@@ -58,24 +59,24 @@ __device__ __forceinline__ int block_excl_prefix_min(int v, int &carry, int *s_w
     }
     int exc = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) exc = CUBE_INF;
-    if (lane == 31) s_warp[warp] = inc;
+    int *buf = s_warp[parity];
+    parity ^= 1;
+    if (lane == 31) buf[warp] = inc;
     __syncthreads();
-    int before = carry, total = carry;
-    for (int w = 0; w < nwarp; w++) {
-        const int t = s_warp[w];
-        if (w < warp) before = min(before, t);
-        total = min(total, t);
-    }
-    __syncthreads();
-    carry = total;
-    return min(exc, before);
+    const int mine = (lane < nwarp) ? buf[lane] : CUBE_INF;
+    const int before = __reduce_min_sync(0xffffffffu, (lane < warp) ? mine : CUBE_INF);
+    const int total = __reduce_min_sync(0xffffffffu, mine);
+    const int res = min(exc, min(before, carry));
+    carry = min(carry, total);
+    return res;
 }
 
 __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__restrict__ tasks, int ntasks, DevCM3 cm,
                                                                  const uint8_t *__restrict__ pool, int *ring_all,
                                                                  size_t ring_ints, uint8_t *__restrict__ dir,
                                                                  int *__restrict__ out_cost, int want_dir) {
-    __shared__ int s_warp[CUBE_THREADS / 32];
+    __shared__ int s_warp[2][32];
+    int scan_parity = 0;
     int *ring = ring_all + (size_t) blockIdx.x * ring_ints;
     const int lcm = cm.lcm, gap = cm.gap;
     for (int ti = blockIdx.x; ti < ntasks; ti += gridDim.x) {
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__
         uint8_t *dcube = dir + t.dir_off;
         const int s3_0 = s3[0];
         auto cost3 = [&](int a, int b, int c) { return 8 * __ldg(cm.cost + ((((a << lcm) + b) << lcm) + c)); };
-        auto rowp = [&](long long r) { return ring + (size_t) (r % RW) * l3; };
         int *prefG = ring + (size_t) RW * l3;  // 8 * sum_{1 <= t <= k} cost3[gap][gap][s3[t]], once per triple
         __syncthreads();
         {
@@ -100,12 +100,12 @@ __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__
                     const int n = __shfl_up_sync(0xffffffffu, pg, o);
                     if (lane >= o) pg += n;
                 }
-                if (lane == 31) s_warp[warp] = pg;
+                if (lane == 31) s_warp[0][warp] = pg;
                 __syncthreads();
                 int before = 0, total = 0;
                 for (int w = 0; w < (int) (blockDim.x >> 5); w++) {
-                    if (w < warp) before += s_warp[w];
-                    total += s_warp[w];
+                    if (w < warp) before += s_warp[0][w];
+                    total += s_warp[0][w];
                 }
                 __syncthreads();
                 if (k < l3) __stcg(prefG + k, pg + before + run);
@@ -113,25 +113,137 @@ __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__
             }
         }
         __syncthreads();
-        for (long long r = 0; r < (long long) l1 * l2; r++) {
-            const int i = (int) (r / l2), j = (int) (r % l2);
-            int *mm = rowp(r);
+        if (l3 <= (int) blockDim.x) {
+            // ---- one cell per thread, software-pipelined ------------------------------------------------------
+            // From plane 2 on a row only reads rows written at least 3 rows earlier, so (a) the loads of row r+1 are
+            // issued at the start of row r and overlap its whole computation, and (b) the only barrier of a row is the
+            // one inside the prefix scan -- it also publishes the previous rows' stores.
+            const int k = threadIdx.x;
+            const bool live = k < l3;
+            const int c3 = live ? s3[k] : s3_0;
+            const int pg = live ? __ldcg(prefG + k) : 0;
+            const int nrows = l1 * l2;
+            auto slot_of = [&](long long x) { return (int) (x % RW); };
+            auto inc = [&](int sl) { return (sl + 1 == RW) ? 0 : sl + 1; };
+            // in[0..5] = U[k], P[k], D[k], U[k-1], P[k-1], D[k-1] (unused ones stay 0)
+            auto issue = [&](int kind, int su, int sd, int sp, int (&in)[6]) {
+                in[0] = in[1] = in[2] = in[3] = in[4] = in[5] = 0;
+                if (!live) return;
+                const int *U = ring + (size_t) su * l3, *D = ring + (size_t) sd * l3, *P = ring + (size_t) sp * l3;
+                if (kind == 1) { in[1] = __ldcg(P + k); if (k >= 1) in[4] = __ldcg(P + k - 1); }
+                else if (kind == 2) { in[2] = __ldcg(D + k); if (k >= 1) in[5] = __ldcg(D + k - 1); }
+                else if (kind == 3) {
+                    in[0] = __ldcg(U + k); in[1] = __ldcg(P + k); in[2] = __ldcg(D + k);
+                    if (k >= 1) { in[3] = __ldcg(U + k - 1); in[4] = __ldcg(P + k - 1); in[5] = __ldcg(D + k - 1); }
+                }
+            };
+            int i = 0, j = 0, slot_r = 0, slot_u = 0, slot_d = 0, slot_p = 0;
+            int pre[6];
+            bool have = false;
+            int c_a_g_k = 0, c_a_g_0 = 0;  // per plane: cost3(a, gap, s3[k]), cost3(a, gap, s3[0])
+            for (int r = 0; r < nrows; r++) {
+                int *mm = ring + (size_t) slot_r * l3;
+                const int a = s1[i], b = s2[j];
+                int kind;
+                if (i == 0) {
+                    kind = (j == 0) ? 0 : 1;
+                    slot_p = (slot_r == 0) ? RW - 1 : slot_r - 1;
+                } else if (j == 0) {
+                    kind = 2;
+                    const long long u = 1 + (long long) (i - 1) * (l2 - 1);
+                    slot_u = slot_of(u);
+                    slot_d = slot_of(u - 1);
+                    slot_p = slot_of((long long) i * (l2 - 1));
+                    c_a_g_k = cost3(a, gap, c3);
+                    c_a_g_0 = cost3(a, gap, s3_0);
+                } else {
+                    kind = 3;
+                }
+                int in[6];
+                if (have) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) in[q] = pre[q];
+                } else {
+                    issue(kind, slot_u, slot_d, slot_p, in);
+                }
+                // prefetch the next row's inputs (both rows in planes >= 2)
+                have = false;
+                if (i >= 2 && r + 1 < nrows) {
+                    if (j + 1 < l2) {
+                        const bool adv = (kind == 3);
+                        issue(3, adv ? inc(slot_u) : slot_u, adv ? inc(slot_d) : slot_d, adv ? inc(slot_p) : slot_p, pre);
+                    } else {
+                        issue(2, 0, slot_of((long long) i * (l2 - 1)), 0, pre);
+                    }
+                    have = true;
+                }
+                int base = CUBE_INF;
+                if (live) {
+                    if (kind == 0) {
+                        base = (k == 0) ? (0 | T_S2) : CUBE_INF;
+                    } else if (kind == 1) {
+                        base = in[1] + cost3(gap, b, s3_0) + T_P1;
+                        if (k >= 1) base = min(base, in[4] + cost3(gap, b, c3) + T_S1);
+                    } else if (kind == 2) {
+                        base = in[2] + c_a_g_0 + T_P3;
+                        if (k >= 1) base = min(base, in[5] + c_a_g_k + T_S3);
+                    } else {
+                        base = in[0] + c_a_g_0 + T_P3;
+                        base = min(base, in[1] + cost3(gap, b, s3_0) + T_P1);
+                        base = min(base, in[2] + cost3(a, b, s3_0) + T_P2);
+                        if (k >= 1) {
+                            base = min(base, in[3] + c_a_g_k + T_S3);
+                            base = min(base, in[4] + cost3(gap, b, c3) + T_S1);
+                            base = min(base, in[5] + cost3(a, b, c3) + T_S2);
+                        }
+                    }
+                }
+                int carry = CUBE_INF;
+                const int v = live ? ((base & ~7) - pg) : CUBE_INF;
+                const int e = block_excl_prefix_min(v, carry, s_warp, scan_parity);
+                if (live) {
+                    int fin = base & ~7, tag = base & 7;
+                    if (e < v) { fin = e + pg; tag = T_SS; }
+                    __stcg(mm + k, fin);
+                    if (want_dir) __stcs(dcube + (size_t) r * l3 + k, CUBE_CODE[tag]);
+                    if (r == nrows - 1 && k == l3 - 1) out_cost[t.triple] = fin >> 3;
+                }
+                if (i < 2) __syncthreads();  // planes 0 and 1 read rows written one or two rows earlier
+                if (kind == 3) { slot_u = inc(slot_u); slot_d = inc(slot_d); slot_p = inc(slot_p); }
+                slot_r = inc(slot_r);
+                if (++j == l2) { j = 0; i++; }
+            }
+            __syncthreads();
+            continue;
+        }
+        // Row bookkeeping without 64-bit divisions: (i, j) and the ring slots of the current row and of its three
+        // neighbour rows advance by one per row; slot(x) = x mod RW is kept incrementally.
+        const int nrows = l1 * l2;  // <= 2^28
+        auto slot_of = [&](long long x) { return (int) (x % RW); };
+        int i = 0, j = 0, slot_r = 0;
+        int slot_u = 0, slot_d = 0, slot_p = 0;  // valid from plane 1 on
+        for (int r = 0; r < nrows; r++) {
+            int *mm = ring + (size_t) slot_r * l3;
             // neighbour rows and per-row constants (a = s1[i], b = s2[j])
             const int a = s1[i], b = s2[j];
             const int *U = nullptr, *D = nullptr, *P = nullptr;
             int kind;
             if (i == 0) {
                 kind = (j == 0) ? 0 : 1;
-                if (j > 0) P = rowp(r - 1);
+                if (j > 0) P = ring + (size_t) (slot_r == 0 ? RW - 1 : slot_r - 1) * l3;
             } else if (j == 0) {
                 kind = 2;
-                D = rowp((long long) (i - 1) * (l2 - 1));
+                // start of plane i: upper = 1 + (i-1)(l2-1), diag = upper - 1, prev = i(l2-1)  (for its row j = 1)
+                const long long u = 1 + (long long) (i - 1) * (l2 - 1);
+                slot_u = slot_of(u);
+                slot_d = slot_of(u - 1);
+                slot_p = slot_of((long long) i * (l2 - 1));
+                D = ring + (size_t) slot_d * l3;
             } else {
                 kind = 3;
-                const long long u = 1 + (long long) (i - 1) * (l2 - 1) + (j - 1);
-                U = rowp(u);
-                D = rowp(u - 1);
-                P = rowp((long long) i * (l2 - 1) + (j - 1));
+                U = ring + (size_t) slot_u * l3;
+                D = ring + (size_t) slot_d * l3;
+                P = ring + (size_t) slot_p * l3;
             }
             const int c_a_g_0 = cost3(a, gap, s3_0), c_g_b_0 = cost3(gap, b, s3_0), c_a_b_0 = cost3(a, b, s3_0);
             int carry = CUBE_INF;   // min over earlier cells of (clean value - prefix of gap-gap costs)
@@ -163,7 +275,7 @@ __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__
                 }
                 // in-row pass: final[k] = min(base[k], final[k-1] + gg[k])  (:3039-3046), as a prefix-min
                 const int v = live ? ((base & ~7) - pg) : CUBE_INF;
-                const int e = block_excl_prefix_min(v, carry, s_warp);
+                const int e = block_excl_prefix_min(v, carry, s_warp, scan_parity);
                 if (live) {
                     int fin = base & ~7, tag = base & 7;
                     if (e < v) {
@@ -172,10 +284,17 @@ __global__ void __launch_bounds__(CUBE_THREADS) cube_fill_kernel(const Task3 *__
                     }
                     __stcg(mm + k, fin);
                     if (want_dir) __stcs(dcube + (size_t) r * l3 + k, CUBE_CODE[tag]);
-                    if (r == (long long) l1 * l2 - 1 && k == l3 - 1) out_cost[t.triple] = fin >> 3;
+                    if (r == nrows - 1 && k == l3 - 1) out_cost[t.triple] = fin >> 3;
                 }
             }
             __syncthreads();  // the row is complete and visible before any later row reads it
+            if (kind == 3) {
+                slot_u = (slot_u + 1 == RW) ? 0 : slot_u + 1;
+                slot_d = (slot_d + 1 == RW) ? 0 : slot_d + 1;
+                slot_p = (slot_p + 1 == RW) ? 0 : slot_p + 1;
+            }
+            slot_r = (slot_r + 1 == RW) ? 0 : slot_r + 1;
+            if (++j == l2) { j = 0; i++; }
         }
     }
 }

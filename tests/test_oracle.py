@@ -155,3 +155,30 @@ def test_deltaw_rule_and_protein_quirk():
     assert (cnt > 0.7 * pool.len).all()
     pool, pairs = synth.pair_batch(8, 500, seed=3)
     assert (pool.count(16) == 1).all()  # DNA: only the leading gap
+
+
+def test_port_vs_compiled_reference_cube(O):
+    """3-D: the port reproduces the reference's executed (defective) cube fill, its walk and its constant median."""
+    _need_ref(O)
+    from poyd_b200 import cost_matrix as CM
+
+    cm3 = CM.of_two_dim(CM.default_nucleotides())
+    assert cm3.cost[1, 2, 4] == 2 and cm3.cost[1, 1, 1] == 0 and cm3.cost[1, 1, 16] == 2 and cm3.median[1, 1, 16] == 1
+    P, R = O.Port3(cm3), O.Reference3(cm3)
+    rng = np.random.default_rng(4)
+
+    def rnd(n):
+        return np.concatenate([[16], rng.choice(np.array([1, 2, 4, 8], np.uint8), size=n)]).astype(np.uint8)
+
+    # the two probes of SURVEY.md Appendix B: the cube is NOT an optimal 3-way alignment
+    x = rnd(10)
+    assert R.align_3(x, x, x)[0] > 0
+    for _ in range(120):
+        a = rnd(int(rng.integers(0, 45)))
+        b = a.copy() if rng.random() < 0.5 else rnd(int(rng.integers(0, 45)))
+        c = rnd(int(rng.integers(0, 45)))
+        rp, rr = P.align_3(a, b, c, want_dir=True), R.align_3(a, b, c, want_dir=True)
+        assert rp[0] == rr[0] and rp[1] == rr[1]
+        assert np.array_equal(rp[6], rr[6])
+        for u, v in zip(rp[2:6], rr[2:6]):
+            assert np.array_equal(u, v)
