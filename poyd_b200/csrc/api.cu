@@ -68,7 +68,8 @@ struct poyb200_ctx {
     std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
     DevBuf<uint8_t> d_pool, d_dir, d_out[4];
     DevBuf<Task> d_tasks;
-    DevBuf<int> d_costs, d_outlen, d_lin_state;
+    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters;
+    size_t counter_next = 0;  // work counters handed to launches of the current call (zeroed once per call)
     DevBuf<int4> d_aff_state;
     long long dstride = 0;
     size_t dir_budget = 0;
@@ -223,7 +224,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
-    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release();
+    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -294,18 +295,28 @@ static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, 
     t.BL = round16((uint32_t) (W + 2) / 2 + 1);
 }
 
+// Work counters: one zeroed int per persistent launch of a call (reset in bulk by reset_counters).
+constexpr size_t MAX_COUNTERS = 1 << 16;
+static int *next_counter(poyb200_ctx *ctx) { return ctx->d_counters.p + (ctx->counter_next++ % MAX_COUNTERS); }
+static int reset_counters(poyb200_ctx *ctx) {
+    CK(ctx->d_counters.reserve(MAX_COUNTERS));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, MAX_COUNTERS * sizeof(int), ctx->stream));
+    ctx->counter_next = 0;
+    return POYB200_OK;
+}
+
 static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n) {
     if (n <= 0) return POYB200_OK;
     if (klass >= KLASS_LIN_BASE) {
         cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
-                                          ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, ctx->stream);
+                                          ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
     }
     if (klass != KLASS_GENERIC) {
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, ctx->stream);
+                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -541,10 +552,10 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
         if (affine)
             aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                  ctx->d_dir.p, out);
+                                                                  ctx->d_dir.p, out, next_counter(ctx));
         else
             lin_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                  ctx->d_dir.p, out);
+                                                                  ctx->d_dir.p, out, next_counter(ctx));
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -567,6 +578,8 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
     if (!ctx->staged) return fail(ctx, POYB200_EINVAL, "poyb200_run without poyb200_stage");
     cudaSetDevice(ctx->device);
     int rc = prepare_events(ctx);
+    if (rc) return rc;
+    rc = reset_counters(ctx);
     if (rc) return rc;
     for (size_t ci = 0; ci < ctx->chunks.size(); ci++) {
         rc = run_chunk(ctx, ci);
@@ -645,6 +658,8 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     const size_t n = ctx->tasks.size(), nch = ctx->chunks.size();
     if (n == 0) return POYB200_OK;
     rc = prepare_events(ctx);
+    if (rc) return rc;
+    rc = reset_counters(ctx);
     if (rc) return rc;
     constexpr size_t SLICE = (size_t) 32 << 20;
     const size_t nslices = (b->pool_bytes + SLICE - 1) / SLICE;

@@ -130,7 +130,7 @@ template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                           const uint8_t *__restrict__ pool,
                                                                           uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                          int seq_bytes, int custom_tail) {
+                                                                          int seq_bytes, int custom_tail, int *work_counter) {
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -158,7 +158,14 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, 3) lin_stripe_kernel(const 
     const int warp_global = blockIdx.x * STRIPE_WARPS + warp_in_block;
     const int total_warps = gridDim.x * STRIPE_WARPS;
 
-    for (int batch = warp_global; batch * GPW < ntasks; batch += total_warps) {
+    // batches of GPW pairs are handed out dynamically (one atomic per warp and batch): no wave-quantisation tail
+    (void) warp_global;
+    (void) total_warps;
+    for (;;) {
+        int batch = 0;
+        if (lane32 == 0) batch = atomicAdd(work_counter, 1);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch * GPW >= ntasks) break;
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
         Task t;
@@ -280,7 +287,7 @@ static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
 
 template <int K, int G>
 static cudaError_t lin_stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
-                                           int *cost, int sm_count, int seq_bytes, int custom_tail, cudaStream_t stream) {
+                                           int *cost, int sm_count, int seq_bytes, int custom_tail, int *work_counter, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const size_t smem = lin_table_bytes(cm.lcm) + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
@@ -293,15 +300,15 @@ static cudaError_t lin_stripe_launch_shape(bool bt, const Task *d_tasks, int n, 
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, custom_tail);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, custom_tail, work_counter);
     return cudaGetLastError();
 }
 
 static inline cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool,
                                             uint8_t *dir, int *cost, int sm_count, int seq_bytes, int custom_tail,
-                                            cudaStream_t stream) {
+                                            int *work_counter, cudaStream_t stream) {
 #define LIN_CASE(IDX, KK, GG) \
-    case IDX: return lin_stripe_launch_shape<KK, GG>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, custom_tail, stream)
+    case IDX: return lin_stripe_launch_shape<KK, GG>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, custom_tail, work_counter, stream)
     switch (klass - KLASS_LIN_BASE) {
         LIN_CASE(0, 8, 8);
         LIN_CASE(1, 10, 8);

@@ -340,7 +340,7 @@ template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                        const uint8_t *__restrict__ pool,
                                                                        uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                       int seq_bytes, int allow_noeb) {
+                                                                       int seq_bytes, int allow_noeb, int *work_counter) {
     constexpr int GPW = 32 / G;  // groups (pairs) per warp
     constexpr int Q = 2 * K;
     constexpr int BL = (K <= 4) ? 4 : 8;
@@ -368,7 +368,14 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
     const int warp_global = blockIdx.x * STRIPE_WARPS + warp_in_block;
     const int total_warps = gridDim.x * STRIPE_WARPS;
 
-    for (int batch = warp_global; batch * GPW < ntasks; batch += total_warps) {
+    // batches of GPW pairs are handed out dynamically (one atomic per warp and batch): no wave-quantisation tail
+    (void) warp_global;
+    (void) total_warps;
+    for (;;) {
+        int batch = 0;
+        if (lane32 == 0) batch = atomicAdd(work_counter, 1);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch * GPW >= ntasks) break;
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
         Task t;
@@ -530,7 +537,7 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
 
 template <int K, int G>
 static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
-                                       int *cost, int sm_count, int seq_bytes, int allow_noeb, cudaStream_t stream) {
+                                       int *cost, int sm_count, int seq_bytes, int allow_noeb, int *work_counter, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const size_t smem = STRIPE_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
@@ -543,22 +550,22 @@ static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevC
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb, work_counter);
     return cudaGetLastError();
 }
 
 static inline cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, DevCM cm,
                                         const uint8_t *pool, uint8_t *dir, int *cost, int sm_count, int seq_bytes,
-                                        int allow_noeb, cudaStream_t stream) {
+                                        int allow_noeb, int *work_counter, cudaStream_t stream) {
     if (!affine) return cudaErrorNotSupported;
     switch (klass - 1) {
-        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
-        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, stream);
+        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
         default: return cudaErrorInvalidValue;
     }
 }

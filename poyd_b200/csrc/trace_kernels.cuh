@@ -31,8 +31,15 @@ struct RevWriter {
 // backtrace_affine (src/algn.c:1983-2097).  dcap = device row stride (multiple of 16).
 __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
-                                                            const uint8_t *__restrict__ dir, OutPtrs out) {
-  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
+                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter) {
+  // walkers take pairs from a shared counter, a warp's worth at a time: no wave-quantisation tail
+  for (;;) {
+    int base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= ntasks) break;
+    const int ti = base + (threadIdx.x & 31);
+    if (ti < ntasks) {
     const Task t = tasks[ti];
     const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;
@@ -116,6 +123,8 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     if (w_al) { ri.flush(); rj.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
+    }
+    __syncwarp();
   }
 }
 
@@ -124,8 +133,15 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
 // algn_get_median_2d_with_gaps (:4024-4035) -- what SeqCS.DOS.median asks for (src/seqCS.ml:757-766).
 __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
-                                                            const uint8_t *__restrict__ dir, OutPtrs out) {
-  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
+                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter) {
+  // walkers take pairs from a shared counter, a warp's worth at a time: no wave-quantisation tail
+  for (;;) {
+    int base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= ntasks) break;
+    const int ti = base + (threadIdx.x & 31);
+    if (ti < ntasks) {
     const Task t = tasks[ti];
     const uint8_t *s1 = pool + t.off_r, *s2 = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;
@@ -168,6 +184,8 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     if (w_al) { r1.flush(); r2.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
+    }
+    __syncwarp();
   }
 }
 
