@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "GCUPS (band cells/s, batched pairwise affine median DP: align_affine_3 fill + traceback + median)"
+METRIC = "GCUPS (band cells/s, batched pairwise median DP: fill + traceback + median)"
 UNIT = "GCUPS"
 OPS_PER_CELL = 50  # integer ops per affine_3 cell with traceback, counted from src/algn.c
 

@@ -1,5 +1,6 @@
 // Host side of the C ABI (include/poyb200.h): planning, device memory, launches.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -41,6 +42,36 @@ struct DevBuf {
     }
 };
 
+// Grow-only array in pinned host memory (so that its upload is a true asynchronous DMA).
+template <typename T>
+struct PinnedVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool resize(size_t m) {
+        if (m > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t want = m + m / 8 + 64;
+            if (cudaHostAlloc((void **) &p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+            cap = want;
+        }
+        n = m;
+        return true;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+    size_t size() const { return n; }
+    T *data() { return p; }
+    T *begin() { return p; }
+    T *end() { return p + n; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct Chunk {
     size_t begin, end;  // task range
     size_t dir_bytes;
@@ -63,7 +94,7 @@ struct poyb200_ctx {
     bool staged = false;
     int mode = 0;
     poyb200_batch hb{};
-    std::vector<Task> tasks;
+    PinnedVec<Task> tasks, tasks_tmp;
     std::vector<Chunk> chunks;
     std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
     DevBuf<uint8_t> d_pool, d_dir, d_out[4];
@@ -81,7 +112,11 @@ struct poyb200_ctx {
     int host_threads = 8;
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
     bool in_order = true;           // tasks[k].pair == k
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr;
+    DevBuf<uint8_t> d_dir2;        // second direction buffer: traceback of chunk k overlaps the fill of chunk k+1
+    uint8_t *cur_dir = nullptr;
+    bool overlap_tb = true;        // POYB200_OVERLAP_TB=0: fill and traceback strictly serial on one stream
+    std::vector<cudaEvent_t> ev_fill, ev_tb;
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_done;
     bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
@@ -201,6 +236,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_tb, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
     ctx->host_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     size_t free_b = 0, total_b = 0;
@@ -211,6 +247,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
     if (const char *s = getenv("POYB200_NOEB")) ctx->allow_noeb = atoi(s);
+    if (const char *s = getenv("POYB200_OVERLAP_TB")) ctx->overlap_tb = atoi(s) != 0;
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
     if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
     if (const char *s = getenv("POYB200_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(s));
@@ -225,6 +262,8 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
     ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release();
+    ctx->tasks.release();
+    ctx->tasks_tmp.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -233,6 +272,10 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
+    for (auto &e : ctx->ev_fill) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_tb) cudaEventDestroy(e);
+    ctx->d_dir2.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -308,14 +351,14 @@ static int reset_counters(poyb200_ctx *ctx) {
 static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n) {
     if (n <= 0) return POYB200_OK;
     if (klass >= KLASS_LIN_BASE) {
-        cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
+        cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
                                           ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
     }
     if (klass != KLASS_GENERIC) {
-        cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_dir.p, ctx->d_costs.p,
+        cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
                                       ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
@@ -328,18 +371,18 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         CK(ctx->d_aff_state.reserve(nwarps * ctx->state_stride));
         if (bt)
             aff_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
-                                                                      ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+                                                                      ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
         else
             aff_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
-                                                                       ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+                                                                       ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
     } else {
         CK(ctx->d_lin_state.reserve(nwarps * ctx->state_stride));
         if (bt)
             lin_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
-                                                                      ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+                                                                      ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
         else
             lin_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
-                                                                       ctx->state_stride, ctx->d_dir.p, ctx->d_costs.p);
+                                                                       ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -351,8 +394,9 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
 // ---------------------------------------------------------------------------------------------------------
 // Runs fn(lo, hi, slot) over [0, n) on up to `ctx->host_threads` threads.
 template <typename F>
-static void parallel_for(int nthreads, size_t n, F fn) {
-    if (nthreads <= 1 || n < 65536) {
+static void parallel_for(int nthreads, size_t n, F fn, size_t grain = 32768) {
+    if ((size_t) nthreads > n / grain) nthreads = (int) (n / grain);  // at least `grain` items per thread
+    if (nthreads <= 1) {
         fn((size_t) 0, n, 0);
         return;
     }
@@ -396,11 +440,15 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         if (pt.err == POYB200_ESEQLEN) return fail(ctx, POYB200_ESEQLEN, "sequence empty (no leading gap) or longer than 16384");
         if (pt.err) return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
     }
-    ctx->tasks.resize((size_t) b->n_pairs);
+    if (!ctx->tasks.resize((size_t) b->n_pairs)) return fail(ctx, POYB200_ENOMEM, "pinned allocation of the task array failed");
     const DevCM dcm = ctx->dcm;
     const bool allow_stripe = ctx->allow_stripe;
     parallel_for(NT, (size_t) b->n_pairs, [&](size_t lo, size_t hi, int slot) {
-        Part &pt = parts[slot];
+        Part pt;  // thread-local: the parts[] entries share cache lines
+        struct Commit {
+            Part &src, &dst;
+            ~Commit() { dst = src; }
+        } commit{pt, parts[slot]};
         for (size_t p = lo; p < hi; p++) {
             const int a = b->pairs[2 * p], c = b->pairs[2 * p + 1];
             if (a < 0 || a >= b->n_seqs || c < 0 || c >= b->n_seqs) {
@@ -463,28 +511,78 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     ctx->stripe_seq_bytes = (max_stripe_len + 15) & ~15;
     // Group by kernel class (stable: keeps the caller's order inside a class).  A batch of one class -- the usual
     // case -- stays in the caller's order, which lets results leave chunk by chunk while later chunks compute.
-    ctx->in_order = (b->n_pairs == 0) || (k_or == k_and);
-    if (!ctx->in_order)
-        std::stable_sort(ctx->tasks.begin(), ctx->tasks.end(), [](const Task &x, const Task &y) { return x.klass < y.klass; });
-    // cut into chunks: direction bands within the budget, and at most chunk_pairs pairs (pipelining granularity)
+    // Chunks are contiguous ranges of the caller's pair list (so the results of a chunk are contiguous rows and can leave
+    // while later chunks compute); inside a chunk the tasks are grouped by kernel class.
+    ctx->in_order = true;
+    const bool one_class = (b->n_pairs == 0) || (k_or == k_and);
+    const size_t ntasks = ctx->tasks.size();
+    auto band_bytes = [&](const Task &t) { return bt ? (((size_t) dir_bytes(t) + 63) & ~(size_t) 63) : (size_t) 0; };
+    // 1. cut by count; if some chunk's direction bands exceed the budget (long sequences) cut serially by bytes instead
     ctx->chunks.clear();
-    size_t begin = 0, off = 0;
-    for (size_t k = 0; k < ctx->tasks.size(); k++) {
-        Task &t = ctx->tasks[k];
-        size_t bytes = 0;
-        if (bt) {
-            bytes = (size_t) dir_bytes(t);
-            bytes = (bytes + 63) & ~(size_t) 63;
+    const size_t CP = ctx->chunk_pairs, nch0 = (ntasks + CP - 1) / CP;
+    ctx->chunks.resize(nch0);
+    bool over = false;
+    parallel_for(NT, nch0, [&](size_t lo, size_t hi, int) {
+        for (size_t c = lo; c < hi; c++) {
+            const size_t kb = c * CP, ke = std::min(ntasks, kb + CP);
+            size_t tot = 0;
+            for (size_t k = kb; k < ke; k++) tot += band_bytes(ctx->tasks[k]);
+            ctx->chunks[c] = Chunk{kb, ke, tot};
+            if (tot > ctx->dir_budget) over = true;  // benign race: only ever set to true
         }
-        if (k > begin && (off + bytes > ctx->dir_budget || k - begin >= ctx->chunk_pairs)) {
-            ctx->chunks.push_back(Chunk{begin, k, off});
-            begin = k;
-            off = 0;
+    }, 1);
+    if (over) {
+        ctx->chunks.clear();
+        size_t begin = 0, off = 0;
+        for (size_t k = 0; k < ntasks; k++) {
+            const size_t bytes = band_bytes(ctx->tasks[k]);
+            if (k > begin && (off + bytes > ctx->dir_budget || k - begin >= CP)) {
+                ctx->chunks.push_back(Chunk{begin, k, off});
+                begin = k;
+                off = 0;
+            }
+            off += bytes;
         }
-        t.dir_off = off;
-        off += bytes;
+        if (ntasks > begin) ctx->chunks.push_back(Chunk{begin, ntasks, off});
     }
-    if (ctx->tasks.size() > begin) ctx->chunks.push_back(Chunk{begin, ctx->tasks.size(), off});
+    // Taper: the results of the last chunk cannot overlap any compute, so cut it into quarters.
+    if (bt && ctx->chunks.size() >= 2) {
+        const Chunk last = ctx->chunks.back();
+        const size_t len = last.end - last.begin;
+        if (len >= 4096) {
+            ctx->chunks.pop_back();
+            for (int q = 0; q < 4; q++) ctx->chunks.push_back(Chunk{last.begin + len * q / 4, last.begin + len * (q + 1) / 4, 0});
+        }
+    }
+    // 2. per chunk, in parallel: stable grouping by class (counting sort into the second array) and band layout
+    if (!one_class && !ctx->tasks_tmp.resize(ntasks)) return fail(ctx, POYB200_ENOMEM, "pinned allocation of the task array failed");
+    parallel_for(NT, ctx->chunks.size(), [&](size_t lo, size_t hi, int) {
+        constexpr int NK = 64;
+        for (size_t c = lo; c < hi; c++) {
+            Chunk &ch = ctx->chunks[c];
+            Task *src = ctx->tasks.data();
+            if (!one_class) {
+                size_t hist[NK] = {0};
+                for (size_t k = ch.begin; k < ch.end; k++) hist[src[k].klass & (NK - 1)]++;
+                size_t run = ch.begin;
+                for (int q = 0; q < NK; q++) {
+                    const size_t v = hist[q];
+                    hist[q] = run;
+                    run += v;
+                }
+                Task *dst = ctx->tasks_tmp.data();
+                for (size_t k = ch.begin; k < ch.end; k++) dst[hist[src[k].klass & (NK - 1)]++] = src[k];
+                src = dst;
+            }
+            size_t off = 0;
+            for (size_t k = ch.begin; k < ch.end; k++) {
+                src[k].dir_off = off;
+                off += band_bytes(src[k]);
+            }
+            ch.dir_bytes = off;
+        }
+    }, 1);
+    if (!one_class) std::swap(ctx->tasks, ctx->tasks_tmp);
     return POYB200_OK;
 }
 
@@ -506,6 +604,7 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     for (auto &c : ctx->chunks) maxdir = std::max(maxdir, c.dir_bytes);
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
+        if (ctx->overlap_tb && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
         CK(ctx->d_outlen.reserve(4 * n + 4));
         const size_t ob = n * (size_t) ctx->dstride + 16;
         if (b->want & POYB200_WANT_MEDIAN) CK(ctx->d_out[0].reserve(ob));
@@ -525,15 +624,20 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
 
 extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b) { return stage_impl(ctx, mode, b, true); }
 
-// Fill + traceback of one chunk on the compute stream.
+// Fill of chunk ci on the compute stream, its traceback on the traceback stream.  With two direction buffers the
+// (latency-bound, 128..512 walkers per SM) traceback of chunk ci runs underneath the (ALU-bound) fill of chunk ci+1.
 static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     const int mode = ctx->mode;
     const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
     const Chunk &ch = ctx->chunks[ci];
+    const bool two = bt && ctx->overlap_tb && ctx->chunks.size() >= 2;
+    cudaStream_t s_tb = two ? ctx->s_tb : ctx->stream;
+    ctx->cur_dir = (two && (ci & 1)) ? ctx->d_dir2.p : ctx->d_dir.p;
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want};
-    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci], ctx->stream));
+    if (two && ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - 2], 0));  // the buffer is free again
+    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk
     size_t k = ch.begin;
     while (k < ch.end) {
@@ -544,32 +648,52 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         if (rc) return rc;
         k = e;
     }
-    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 1], ctx->stream));
+    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 1], ctx->stream));
     if (bt) {
+        if (two) {
+            CK(cudaEventRecord(ctx->ev_fill[ci], ctx->stream));
+            CK(cudaStreamWaitEvent(s_tb, ctx->ev_fill[ci], 0));
+        }
+        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 2], s_tb));
         const int nt = (int) (ch.end - ch.begin);
         // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
         // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
         const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
         if (affine)
-            aff_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                  ctx->d_dir.p, out, next_counter(ctx));
+            aff_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                                                           next_counter(ctx));
         else
-            lin_traceback_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p,
-                                                                  ctx->d_dir.p, out, next_counter(ctx));
+            lin_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                                                           next_counter(ctx));
         ctx->launches++;
         CK(cudaGetLastError());
+        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));
     }
-    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[3 * ci + 2], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_tb[ci], s_tb));  // chunk ci is complete
     return POYB200_OK;
 }
 
 static int prepare_events(poyb200_ctx *ctx) {
-    while (ctx->timing && ctx->chunk_ev.size() < 3 * ctx->chunks.size()) {
+    while (ctx->timing && ctx->chunk_ev.size() < 4 * ctx->chunks.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->chunk_ev.push_back(e);
     }
+    while (ctx->ev_fill.size() < ctx->chunks.size()) {
+        cudaEvent_t e, f;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&f, cudaEventDisableTiming));
+        ctx->ev_fill.push_back(e);
+        ctx->ev_tb.push_back(f);
+    }
     ctx->timed_chunks = ctx->timing ? ctx->chunks.size() : 0;
+    return POYB200_OK;
+}
+
+// Makes the compute stream wait for the tracebacks still running on the traceback stream.
+static int join_streams(poyb200_ctx *ctx) {
+    const size_t nch = ctx->chunks.size();
+    for (size_t ci = (nch >= 2 ? nch - 2 : 0); ci < nch; ci++) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci], 0));
     return POYB200_OK;
 }
 
@@ -585,7 +709,7 @@ extern "C" int poyb200_run(poyb200_ctx *ctx) {
         rc = run_chunk(ctx, ci);
         if (rc) return rc;
     }
-    return POYB200_OK;
+    return join_streams(ctx);
 }
 
 extern "C" int poyb200_sync(poyb200_ctx *ctx) {
@@ -601,9 +725,13 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
     ms[0] = ms[1] = 0.f;
     for (size_t c = 0; c < ctx->timed_chunks; c++) {
         float a = 0.f, b = 0.f;
-        CK(cudaEventSynchronize(ctx->chunk_ev[3 * c + 2]));
-        CK(cudaEventElapsedTime(&a, ctx->chunk_ev[3 * c], ctx->chunk_ev[3 * c + 1]));
-        CK(cudaEventElapsedTime(&b, ctx->chunk_ev[3 * c + 1], ctx->chunk_ev[3 * c + 2]));
+        const bool bt = (ctx->mode == MODE_ALIGN_2 || ctx->mode == MODE_ALIGN_AFF);
+        CK(cudaEventSynchronize(ctx->chunk_ev[4 * c + 1]));
+        CK(cudaEventElapsedTime(&a, ctx->chunk_ev[4 * c], ctx->chunk_ev[4 * c + 1]));
+        if (bt) {
+            CK(cudaEventSynchronize(ctx->chunk_ev[4 * c + 3]));
+            CK(cudaEventElapsedTime(&b, ctx->chunk_ev[4 * c + 2], ctx->chunk_ev[4 * c + 3]));
+        }
         ms[0] += a;
         ms[1] += b;
     }
@@ -611,23 +739,32 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
 }
 
 // D2H of the results of pairs [lo, hi) on stream st (rows of one pair range are contiguous on both sides).
-static int fetch_range(poyb200_ctx *ctx, size_t lo, size_t hi, cudaStream_t st) {
+// lens_known: out_len of the range is already on the host; then only the columns that hold data are copied (rows are
+// right aligned, typical alignments are about half as long as the worst case the rows are sized for).
+static int fetch_range(poyb200_ctx *ctx, size_t lo, size_t hi, cudaStream_t st, bool lens_known = false) {
     const poyb200_batch &b = ctx->hb;
     const bool bt = (ctx->mode == MODE_ALIGN_2 || ctx->mode == MODE_ALIGN_AFF);
     const size_t n = hi - lo;
     if (n == 0) return POYB200_OK;
     if (b.cost) CK(cudaMemcpyAsync(b.cost + lo, ctx->d_costs.p + lo, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (bt && b.want) {
-        CK(cudaMemcpyAsync(b.out_len + 4 * lo, ctx->d_outlen.p + 4 * lo, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (!lens_known)
+            CK(cudaMemcpyAsync(b.out_len + 4 * lo, ctx->d_outlen.p + 4 * lo, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
         uint8_t *dst[4] = {b.median, b.medianwg, b.aligned_a, b.aligned_b};
         const uint32_t need[4] = {POYB200_WANT_MEDIAN, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
         // right-aligned device rows -> right-aligned caller rows
-        const size_t w = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
+        const size_t wfull = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
+        int wmax[4] = {0, 0, 0, 0};
+        if (lens_known)
+            for (size_t p = lo; p < hi; p++)
+                for (int k = 0; k < 4; k++) wmax[k] = std::max(wmax[k], b.out_len[4 * p + k]);
         for (int k = 0; k < 4; k++) {
             if (!(b.want & need[k])) continue;
             uint8_t *d = dst[k] + lo * (size_t) b.out_stride;
             const uint8_t *src = ctx->d_out[k].p + lo * (size_t) ctx->dstride;
-            if (ctx->dstride == b.out_stride)
+            const size_t w = lens_known ? std::min(wfull, ((size_t) wmax[k] + 31) & ~(size_t) 31) : wfull;
+            if (w == 0) continue;
+            if (ctx->dstride == b.out_stride && w == wfull)
                 CK(cudaMemcpyAsync(d, src, n * (size_t) ctx->dstride, cudaMemcpyDeviceToHost, st));
             else
                 CK(cudaMemcpy2DAsync(d + (b.out_stride - w), (size_t) b.out_stride, src + (ctx->dstride - w),
@@ -652,9 +789,17 @@ extern "C" int poyb200_fetch(poyb200_ctx *ctx) {
 //   stream  runs fill + traceback of chunk k as soon as the slices its pairs reference have arrived;
 //   s_out   downloads the results of chunk k while chunk k+1 computes (needs the caller's pair order, i.e. one
 //           kernel class; otherwise one download at the end).
+static double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
 static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+    static const bool trace = getenv("POYB200_TRACE") != nullptr;
+    const double t0 = now_ms();
     int rc = stage_impl(ctx, mode, b, false);
     if (rc) return rc;
+    const double t1 = now_ms();
     const size_t n = ctx->tasks.size(), nch = ctx->chunks.size();
     if (n == 0) return POYB200_OK;
     rc = prepare_events(ctx);
@@ -668,7 +813,7 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->ev_done.push_back(e);
     }
-    cudaEvent_t *ev_chunk = ctx->ev_done.data(), *ev_slice = ctx->ev_done.data() + nch, ev_tasks = ctx->ev_done[nch + nslices];
+    cudaEvent_t *ev_slice = ctx->ev_done.data() + nch, ev_tasks = ctx->ev_done[nch + nslices];
     // last pool byte each chunk needs (prefix maximum: slices arrive in order)
     std::vector<size_t> need(nch, 0);
     parallel_for(ctx->host_threads, nch, [&](size_t lo, size_t hi, int) {
@@ -680,7 +825,7 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             }
             need[ci] = m;
         }
-    });
+    }, 1);
     for (size_t ci = 1; ci < nch; ci++) need[ci] = std::max(need[ci], need[ci - 1]);
     CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, ctx->s_in));
     CK(cudaEventRecord(ev_tasks, ctx->s_in));
@@ -699,10 +844,24 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         }
         rc = run_chunk(ctx, ci);
         if (rc) return rc;
-        if (ctx->in_order) {
-            CK(cudaEventRecord(ev_chunk[ci], ctx->stream));
-            CK(cudaStreamWaitEvent(ctx->s_out, ev_chunk[ci], 0));
-            rc = fetch_range(ctx, ctx->chunks[ci].begin, ctx->chunks[ci].end, ctx->s_out);
+    }
+    rc = join_streams(ctx);
+    if (rc) return rc;
+    if (ctx->in_order) {
+        // All compute is enqueued; now follow it chunk by chunk: fetch the lengths of a finished chunk on their own
+        // stream, then copy only the columns in use while later chunks compute.
+        const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF) && b->want;
+        for (size_t ci = 0; ci < nch; ci++) {
+            const Chunk &ch = ctx->chunks[ci];
+            if (bt) {
+                CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_tb[ci], 0));  // s_in is idle once the pool is up
+                CK(cudaMemcpyAsync(b->out_len + 4 * ch.begin, ctx->d_outlen.p + 4 * ch.begin, 4 * (ch.end - ch.begin) * sizeof(int),
+                                   cudaMemcpyDeviceToHost, ctx->s_in));
+                CK(cudaStreamSynchronize(ctx->s_in));
+            } else {
+                CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_tb[ci], 0));
+            }
+            rc = fetch_range(ctx, ch.begin, ch.end, ctx->s_out, bt);
             if (rc) return rc;
         }
     }
@@ -710,9 +869,16 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         rc = fetch_range(ctx, 0, n, ctx->stream);
         if (rc) return rc;
     }
+    const double t2 = now_ms();
     CK(cudaStreamSynchronize(ctx->s_in));
+    const double t3 = now_ms();
     CK(cudaStreamSynchronize(ctx->stream));
+    const double t4 = now_ms();
     CK(cudaStreamSynchronize(ctx->s_out));
+    const double t5 = now_ms();
+    if (trace)
+        fprintf(stderr, "[poyb200] plan+reserve %.1f ms, enqueue %.1f ms, wait h2d %.1f, wait compute %.1f, wait d2h %.1f, total %.1f ms\n",
+                t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
     return POYB200_OK;
 }
 

@@ -43,7 +43,7 @@ constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared mem
 
 constexpr int STRIPE_WARPS = 4;
 #ifndef STRIPE_MIN_BLOCKS
-#define STRIPE_MIN_BLOCKS 3
+#define STRIPE_MIN_BLOCKS 2
 #endif
 constexpr int STRIPE_LUT_BYTES = 16 * 17 * 8;  // == 16 * LUT_ROW_BYTES
 constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * 8;
