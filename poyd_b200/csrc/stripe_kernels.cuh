@@ -128,14 +128,14 @@ struct AffWinRow {
     int gopge4p1;  // 4 * (si_gap_opening + si_gap_extension) + 1   (CB tag 1 -> EV tag 2)
     int gop4;      // 4 * si_gap_opening
     int lut;       // byte offset of the row (si & 15) in the cost LUT
-    int gm;        // -1 when si carries the gap bit
+    int gf;        // 1 when si carries the gap bit, else 0 (a multiplier: the selects run on the FMA pipe as IMADs)
 };
 struct AffWinCol {
     int hx4;       // 4 * sj_horizontal_extension[j]
     int gopg4m1;   // 4 * (gap_open_prec[j] + gap_row[j]) - 1       (CB tag 1 -> EH tag 0)
     int gop4;      // 4 * gap_open_prec[j]
     int lut;       // byte offset of the column (sj & 15) inside a LUT row
-    int gm;
+    int gf;
 };
 
 // One interior cell on tagged, x4 values, for DNA matrices (lcm = 5, gap = 16 = TMPGAP, codes < 32), where "has
@@ -161,39 +161,40 @@ __device__ __forceinline__ int aff_cell_dna(int ehl, int cbl, int evu, int cbu, 
     ev = min(x, y);
     if (BT) byte |= (x < y) ? 0 : AB_ENDV;
     if (NOEB) {
-        const int a2 = ehd + d.x + (r.gop4 & c.gm);
-        const int a1 = evd + d.x + (c.gop4 & r.gm);
+        // "x & mask" written as a multiply-add: the INT32 ALU pipe is the bottleneck, the FMA pipe has room
+        const int a2 = (r.gop4 * c.gf + ehd) + d.x;
+        const int a1 = (c.gop4 * r.gf + evd) + d.x;
         const int a0 = cbd + d.x + 2;
         const int ck = min(a0, min(a1, a2));
         cb = (ck & ~3) | TAG_CB;
         eb = ebd;
         if (BT) {
             const int fk = min(eh, min(ev, cb));
-            byte |= (ck & 3) | ((fk & 3) << 2) | AB_ENDB;
+            byte += (fk & 3) * 4 + (ck & 3) + AB_ENDB;
         }
         return byte;
     }
     // FILL_EXTEND_BLOCK_DIAGONAL :1861-1882 / _NOBT :1837-1854
-    const int bothm = r.gm & c.gm;     // -1 when both carry the gap bit
-    const int dg = HIGH4 & ~bothm;     // 0 or 4*HIGH_NUM
+    const int bothf = r.gf * c.gf;              // 1 when both carry the gap bit
+    const int dg = HIGH4 - HIGH4 * bothf;       // 0 or 4*HIGH_NUM
     if (BT) {
         const int c2 = cbd + 2;        // CB tag 1 -> EB tag 3
         eb = min(ebd, c2) + dg;        // extend and open share the addend (:1871-1872)
         byte |= (ebd < c2) ? 0 : AB_ENDB;
     } else {
-        const int odg = dg | (go8 & bothm);  // both ? 2*go : HIGH_NUM (:1846; its flag2 can never hold with flag)
+        const int odg = dg + go8 * bothf;  // both ? 2*go : HIGH_NUM (:1846; its flag2 can never hold with flag)
         eb = min(ebd + dg, cbd + odg + 2);
     }
     // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977, candidates tagged H 0, D 1, V 2, A 3
-    const int a2 = ehd + d.x + (r.gop4 & c.gm);
+    const int a2 = (r.gop4 * c.gf + ehd) + d.x;
     const int a3 = ebd + d.y + max(r.gop4, c.gop4);
-    const int a1 = evd + d.x + (c.gop4 & r.gm);
+    const int a1 = (c.gop4 * r.gf + evd) + d.x;
     const int a0 = cbd + d.x + 2;
     const int ck = min(min(a0, a1), min(a2, a3));
     cb = (ck & ~3) | TAG_CB;
     if (BT) {
         const int fk = min(min(eh, ev), min(eb, cb));  // ASSIGN_MINIMUM :2251-2280
-        byte |= (ck & 3) | ((fk & 3) << 2);
+        byte += (fk & 3) * 4 + (ck & 3);
     }
     return byte;
 }
@@ -223,7 +224,7 @@ struct AffStripe {
         r.vx4 = (i > 1 && (pi & 16) && !(ci & 16)) ? r.gop4 + ge4 : ge4;  // :2483-2485
         r.gopge4p1 = r.gop4 + ge4 + 1;
         r.lut = (ci & 15) * LUT_ROW_BYTES;
-        r.gm = -((ci >> 4) & 1);
+        r.gf = (ci >> 4) & 1;
         return r;
     }
     __device__ __forceinline__ AffWinCol make_col(int j) {
@@ -236,7 +237,7 @@ struct AffStripe {
         c.hx4 = ((pj & 16) && !(cj & 16) && j != 1) ? c.gop4 + g4 : g4;  // :2454-2458
         c.gopg4m1 = c.gop4 + g4 - 1;
         c.lut = (cj & 15) * 8;
-        c.gm = -((cj >> 4) & 1);
+        c.gf = (cj >> 4) & 1;
         return c;
     }
 
