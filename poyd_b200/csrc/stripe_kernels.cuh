@@ -85,7 +85,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 template <int G>
 __device__ __forceinline__ void stage_pair(uint8_t *dst_r, uint8_t *dst_c, const uint8_t *gr, const uint8_t *gc, int lr, int lc,
                                            int lane, bool valid, uint64_t *bar, uint32_t &phase, int pad_code) {
+#ifdef POYB200_EXP_NO_TMA
+    const bool bulk = false;  // diagnostic build: plain-load staging only
+#else
     const bool bulk = valid && ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0);
+#endif
+#ifdef POYB200_EXP_FENCE_ALL
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+#endif
     if (bulk) {
         if (lane == 0) {
             const uint32_t br = (uint32_t) (lr + 15) & ~15u, bc = (uint32_t) (lc + 15) & ~15u;
