@@ -425,3 +425,41 @@ def test_three_sequence_cube_as_the_reference_executes_it(S):
             assert np.array_equal(g.get("aligned_3", t), r3), t
             assert np.array_equal(g.get("median", t), med), t
     al.close()
+
+
+def test_one_million_pairs_bit_exact(S, checker_factory):
+    """BASELINE.json target: bit-exact costs and medians against algn.c on >= 1 M synthetic pairs (configs[1] shape:
+    500 bp DNA, affine).  Compared in slices against the compiled reference on all host threads; half of the slices carry
+    gap-ambiguous codes (median-like operands, full block-diagonal cell), half do not (NOEB fast path)."""
+    import os
+
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3)
+    chk = checker_factory(cm)
+    threads = len(os.sched_getaffinity(0))
+    al = S.Align(cm)
+    total, slice_pairs = 0, 125_000
+    for k in range(8):
+        extra = dict(ambiguity=0.005, gap_ambiguity=0.10) if k % 2 else {}
+        pool, pairs = synth.pair_batch(slice_pairs, 500, seed=1000 + k, min_len=450, stride=512, **extra)
+        g = al.align_affine_3(pool, pairs, S.WANT_MEDIAN)
+        o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=threads)
+        assert np.array_equal(g.cost, o["cost"]), f"slice {k}: cost mismatch"
+        assert np.array_equal(g.lens[:, 0], o["lens"][:, 0]), f"slice {k}: median length mismatch"
+        # medians: compare as right-aligned blocks in one vectorised pass
+        L = o["lens"][:, 0]
+        w = int(L.max())
+        gm = g.median[:, g.median.shape[1] - w:]
+        om = np.zeros((slice_pairs, w), np.uint8)
+        cols = np.arange(w)[None, :]
+        src = cols - (w - L[:, None])
+        valid = src >= 0
+        om[valid] = o["median"][np.nonzero(valid)[0], src[valid]]
+        assert np.array_equal(np.where(valid, gm, 0), om), f"slice {k}: median mismatch"
+        cg = al.cost_2(pool, pairs)
+        oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=threads)["cost"]
+        assert np.array_equal(cg, oc), f"slice {k}: cost-only mismatch"
+        total += slice_pairs
+    assert total >= 1_000_000
+    al.close()
