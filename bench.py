@@ -34,6 +34,8 @@ UNIT = "GCUPS"
 OPS_PER_CELL = 50  # integer ops per affine_3 cell with traceback, counted from src/algn.c
 
 
+NCU_DRAM_BYTES_PER_PAIR = {"affine500": 6.863494e9 / 100000}
+
 WORKLOADS = {
     # name: (description, mode, ops per cell)
     "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
@@ -333,8 +335,15 @@ def main():
     # (the band is re-read by the traceback kernel, not by this one)
     alg_bytes = float(pool.len[pairs[:, 0]].astype(np.int64).sum() + pool.len[pairs[:, 1]].astype(np.int64).sum()) + float(cells)
     fill_s = f_ms * 1e-3
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_fill_final.csv:
+    # dram__bytes_read.sum + dram__bytes_write.sum = 6.863 GB for one launch over 100 000 pairs of this workload),
+    # scaled to the pairs one launch of this run covers; null for workloads without a capture.
+    traffic = NCU_DRAM_BYTES_PER_PAIR.get(args.workload)
+    if traffic is not None:
+        traffic = traffic * n / fill_launches
     roof = {"bound": "hbm", "achieved": alg_bytes / fill_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+            "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r01_fill_final.csv)",
+            "algorithmic_bytes_per_launch": alg_bytes / fill_launches, "peak_source": hbm_src,
             "kernel": "aff_stripe_kernel<5,8,true>" if wl_mode == 3 else "lin_stripe_kernel<K,G,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
             "note": "integer min-plus recurrence: ALU-bound, see roofline_int32"}
     gops = cells * ops_per_cell / fill_s * 1e-9
