@@ -11,6 +11,7 @@
 #include "generic_kernels.cuh"
 #include "peak.cuh"
 #include "stripe_kernels.cuh"
+#include "aff_fast_kernels.cuh"
 #include "lin_stripe_kernels.cuh"
 #include "trace_kernels.cuh"
 #include "cube_kernels.cuh"
@@ -99,7 +100,7 @@ struct poyb200_ctx {
     std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
     DevBuf<uint8_t> d_pool, d_dir, d_out[4];
     DevBuf<Task> d_tasks;
-    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters;
+    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters, d_slow_list;
     size_t counter_next = 0;  // work counters handed to launches of the current call (zeroed once per call)
     DevBuf<int4> d_aff_state;
     long long dstride = 0;
@@ -108,6 +109,7 @@ struct poyb200_ctx {
     int stripe_seq_bytes = 16;
     int trace_threads_per_sm = 512;
     int allow_noeb = 1;   // POYB200_NOEB=0 disables the no-gap-bit fast path of the affine stripe kernels
+    int allow_fast = 1;   // POYB200_FAST=0: no aff_fast_kernel, every batch goes to aff_stripe_kernel
     int custom_tail = 0;  // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int host_threads = 8;
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
@@ -247,6 +249,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
     if (const char *s = getenv("POYB200_NOEB")) ctx->allow_noeb = atoi(s);
+    if (const char *s = getenv("POYB200_FAST")) ctx->allow_fast = atoi(s);
     if (const char *s = getenv("POYB200_OVERLAP_TB")) ctx->overlap_tb = atoi(s) != 0;
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
     if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
@@ -261,7 +264,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
-    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release();
+    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release(); ctx->d_slow_list.release();
     ctx->tasks.release();
     ctx->tasks_tmp.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
@@ -358,8 +361,20 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         return POYB200_OK;
     }
     if (klass != KLASS_GENERIC) {
+        // pairs without gap bits take aff_fast_kernel; the batches it declines are listed for aff_stripe_kernel
+        const int *list = nullptr, *count = nullptr;
+        if (affine && ctx->allow_fast && ctx->allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
+            CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
+            int *cnt = next_counter(ctx);
+            cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
+                                        ctx->stripe_seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt, ctx->stream);
+            ctx->launches++;
+            CK(e);
+            list = ctx->d_slow_list.p;
+            count = cnt;
+        }
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, next_counter(ctx), ctx->stream);
+                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, next_counter(ctx), list, count, ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;

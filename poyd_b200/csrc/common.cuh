@@ -46,6 +46,7 @@ struct Task {
     uint32_t G, twoK, BL;   // direction addressing, see dir_index
     int32_t dbase;          // diagonal held by lane 0, slot 0 (= dlo for the generic kernels)
     uint32_t klass;         // kernel class chosen by the planner
+    int32_t tshift;         // direction addressing counts steps from anti-diagonal `tshift` (0 unless a kernel asks)
 };
 
 // Byte index of cell (i, j) inside a pair's direction band: anti-diagonal major, then lane-group chunk.
@@ -53,22 +54,25 @@ struct Task {
 // Anti-diagonals are tiled by 8: the 8 chunks a lane writes during steps 8k..8k+7 are contiguous (one 64-byte
 // line for BL = 8), so a traceback, which moves one or two anti-diagonals per step and drifts slowly across
 // diagonals, stays inside a line for several steps.
+// Steps are counted from anti-diagonal t.tshift (<= 0 for every cell of the matrix): the affine stripe kernels choose it
+// so that a tile starts where their double-step counter is a multiple of 4, whatever the pair's first diagonal is,
+// which lets an unrolled block of 8 double steps store at compile-time offsets.
 __host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int j) {
-    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j);
+    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j - t.tshift);
     const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
     return ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
 }
 // Direction code of cell (i, j): a byte, or a 2-bit field of a 32-bit chunk (TF_DIR2).
 __device__ __forceinline__ int dir_fetch(const Task &t, const uint8_t *dbase, int i, int j) {
-    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j);
+    const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j - t.tshift);
     const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
     const uint64_t chunk = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL;
     if (t.flags & TF_DIR2) return (__ldg(dbase + chunk + (m >> 2)) >> ((m & 3) * 2)) & 3;
     return __ldg(dbase + chunk + m);
 }
-// Bytes of one pair's direction band (T runs over 0 .. lr + lc - 2).
+// Bytes of one pair's direction band (steps 0 .. lr + lc - 2 - tshift).
 __host__ __device__ __forceinline__ uint64_t dir_bytes(const Task &t) {
-    return (uint64_t) ((t.lr + t.lc - 1 + 7) >> 3) * 8 * t.G * t.BL;
+    return (uint64_t) ((t.lr + t.lc - 1 - t.tshift + 7) >> 3) * 8 * t.G * t.BL;
 }
 
 struct DevCM {

@@ -349,7 +349,11 @@ template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                        const uint8_t *__restrict__ pool,
                                                                        uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                       int seq_bytes, int allow_noeb, int *work_counter) {
+                                                                       int seq_bytes, int allow_noeb, int *work_counter,
+                                                                       const int *__restrict__ batch_list,
+                                                                       const int *__restrict__ batch_count) {
+    // batch_list != nullptr: only the batches aff_fast_kernel declined (aff_fast_kernels.cuh), *batch_count of them
+    if (batch_list != nullptr && *batch_count == 0) return;
     constexpr int GPW = 32 / G;  // groups (pairs) per warp
     constexpr int Q = 2 * K;
     constexpr int BL = (K <= 4) ? 4 : 8;
@@ -384,6 +388,10 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
         int batch = 0;
         if (lane32 == 0) batch = atomicAdd(work_counter, 1);
         batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch_list != nullptr) {
+            if (batch >= *batch_count) break;
+            batch = batch_list[batch];
+        }
         if (batch * GPW >= ntasks) break;
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
@@ -432,7 +440,10 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
 #pragma unroll
             for (int o = G; o < 32; o <<= 1) u_b = max(u_b, __shfl_xor_sync(0xffffffffu, u_b, o));
             // chunk address of (step T, this lane): tiles of 8 steps, see dir_index (common.cuh)
-            auto chunk = [&](int T) { return dbase + (((size_t) (T >> 3) * G + lane) * 8 + (T & 7)) * BL; };
+            auto chunk = [&](int T) {
+                const int S2 = T - t.tshift;
+                return dbase + (((size_t) (S2 >> 3) * G + lane) * 8 + (S2 & 7)) * BL;
+            };
             auto emit = [&](const uint32_t (&de)[2], const uint32_t (&dod)[2]) {
                 if (BT) {
                     const int te = 2 * u + d0;
@@ -524,6 +535,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+#ifndef POYB200_KERNELS_ONLY  // (kernel-only translation units: SASS experiments)
 
 // Chooses a stripe shape for an affine pair; returns false when the pair must take the generic kernel.
 static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
@@ -538,6 +550,8 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
             t.twoK = 2 * K;
             t.BL = (K <= 4) ? 4 : 8;
             t.dbase = t.dhi + 2 - 2 * K * G;
+            // steps are counted from a multiple of 8 double-step halves: see dir_index and aff_fast_kernels.cuh
+            t.tshift = t.dbase + ((2 * ((-t.dbase) >> 1)) & ~7);
             return true;
         }
     }
@@ -546,7 +560,8 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
 
 template <int K, int G>
 static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
-                                       int *cost, int sm_count, int seq_bytes, int allow_noeb, int *work_counter, cudaStream_t stream) {
+                                       int *cost, int sm_count, int seq_bytes, int allow_noeb, int *work_counter,
+                                       const int *batch_list, const int *batch_count, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const size_t smem = STRIPE_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
@@ -559,24 +574,28 @@ static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevC
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb, work_counter);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb, work_counter, batch_list,
+                                                      batch_count);
     return cudaGetLastError();
 }
 
 static inline cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, DevCM cm,
                                         const uint8_t *pool, uint8_t *dir, int *cost, int sm_count, int seq_bytes,
-                                        int allow_noeb, int *work_counter, cudaStream_t stream) {
+                                        int allow_noeb, int *work_counter, const int *batch_list, const int *batch_count,
+                                        cudaStream_t stream) {
     if (!affine) return cudaErrorNotSupported;
     switch (klass - 1) {
-        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
-        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, stream);
+        case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 3: return stripe_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 4: return stripe_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 5: return stripe_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
+        case 6: return stripe_launch_shape<8, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }
+
+#endif  // POYB200_KERNELS_ONLY
 
 }  // namespace poyb200
