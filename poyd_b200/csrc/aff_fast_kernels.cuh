@@ -6,11 +6,11 @@
 //   * the block-diagonal state is gone (see the NOEB note in stripe_kernels.cuh) and with it every per-row / per-column
 //     gap-opening special case: a row needs {4 * cost[si][gap], address of its LUT row}, a column
 //     {4 * prepend[sj], byte offset inside a LUT row}, both fetched from 256-entry shared tables with one 8-byte load;
-//   * the row / column windows do not slide.  They are rings of 8 slots and the sweep is unrolled in blocks of 8
-//     double steps, so every slot index is a compile-time constant and no register is ever copied;
-//   * a block starts where the double-step counter is a multiple of 4, which by the choice of Task::tshift is a
-//     tile boundary of the direction band for every pair of the warp: the 16 stores of a block go to compile-time
-//     offsets from one running pointer;
+//   * the row / column windows do not slide.  They are rings of K + 1 slots and the sweep is unrolled in blocks of
+//     K + 1 double steps, so every slot index is a compile-time constant and no register is ever copied;
+//   * by the choice of Task::tshift the two steps of a double step are neighbours inside a tile of the direction band
+//     and the tile phase depends on the double-step counter only: one 16-byte store per double step, at an offset
+//     that is the same for the whole warp;
 //   * the middle of the sweep (every lane inside the matrix, every pair of the warp still running) runs blocks without
 //     any position test; the first and last few blocks run the same code with the tests switched on (EDGE).
 //
@@ -20,9 +20,17 @@
 
 namespace poyb200 {
 
-constexpr int FAST_P = 8;                                   // ring slots = double steps per block
-constexpr int FAST_LUT_ROW = 17 * 4;                        // 16 ints + 1 pad
-constexpr int FAST_TABLE_BYTES = 2 * 256 * 8 + 16 * FAST_LUT_ROW + STRIPE_WARPS * 4 * 8;
+constexpr int FAST_LUT_ROW = 20 * 4;                        // 16 ints + 4 pad
+// LUT slot of a 4-bit code: A, C, G, T (1, 2, 4, 8) take slots 0..3, so with rows 20 words apart the 16 combinations
+// of unambiguous bases sit in 16 different banks; the other codes follow.
+__host__ __device__ constexpr int fast_lut_slot(int code) {
+    // slots {4, 0, 1, 5, 2, 6, 7, 8, 3, 9, 10, 11, 12, 13, 14, 15} for codes 0..15, one nibble each
+    return (int) ((0xfedcba9387625104ull >> (4 * (code & 15))) & 15);
+}
+// tabR, tabC, LUT of the ring blocks; LUT, prepend and gap tables of the boundary phase; one mbarrier per group
+constexpr int FAST_SCR_INTS = 16;  // >= 2 K
+constexpr int FAST_TABLE_BYTES =
+    2 * 256 * 8 + 16 * FAST_LUT_ROW + STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * 8 + STRIPE_WARPS * 4 * FAST_SCR_INTS * 4;
 // The unchecked blocks read codes past an operand's end (rows up to Q G / 2 + D - 2 past it, columns up to G K + D - 1):
 // every staged operand gets that much private slack, so the stray reads never touch another warp's buffers.
 __host__ __device__ constexpr int fast_operand_pad(int K, int G) { return (K * G + 8 + 15) & ~15; }
@@ -40,6 +48,18 @@ __device__ __forceinline__ int2 lds_v2(uint32_t a) {
     asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+// a * one + b with `one` an opaque register holding 1: an add the assembler must issue on the FMA pipe (the INT32 ALU
+// pipe is the busier one in the unchecked block)
+__device__ __forceinline__ int fma_add(int a, int one, int b) {
+#ifdef FAST_X_NOFMA
+    (void) one;
+    return a + b;
+#else
+    int v;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(one), "r"(b));
+    return v;
+#endif
+}
 // staged operands change from pair to pair: volatile, so the load is neither hoisted nor merged across pairs
 __device__ __forceinline__ int lds_u8_seq(uint32_t a) {
     int v;
@@ -49,97 +69,97 @@ __device__ __forceinline__ int lds_u8_seq(uint32_t a) {
 
 template <int K, int G, bool BT>
 struct AffFast {
-    static constexpr int Q = 2 * K, P = FAST_P, BL = (K <= 4) ? 4 : 8;
-    static constexpr int D = (K <= 6) ? 2 : 1;  // windows are loaded D double steps ahead
-    static_assert(K + 1 + D <= P + 1 && K + D <= P, "ring too small");
+    // P = ring slots = double steps per unrolled block.  K + 1 columns are live in a step and the next row / column
+    // is fetched one step ahead into the slot that just died, so K + 1 slots do.  Instruction-cache footprint decides the
+    // speed of this kernel: a block is 6 double steps x 10 cells x ~26 instructions x 16 B = 25 KB for K = 5, and
+    // nothing else may be large -- a first version whose boundary phases were unrolled the same way (88 KB per block)
+    // ran at half the speed with 57 % "no instruction" stalls (profiles/).
+    static constexpr int Q = 2 * K, P = K + 1, BL = (K <= 4) ? 4 : 8;
 
     int cb[Q], ev[Q], eh[Q];
     int Rv[P], Cv[P];       // 4 * cost[si][gap], 4 * prepend[sj]
     uint32_t Rl[P], Cl[P];  // shared address of the LUT row, byte offset of the column
     uint32_t si, sj, tabR, tabC;  // shared addresses
-    int nr, nc, go4, lane, keep;
+    int nr, nc, lane, keep;
+    int one;       // 1, opaque (fma_add)
+    int c_h, c_v;  // go4 (CB tag 0 -> EH tag 0), go4 + 2 (-> EV tag 2): registers, so the adds stay two-input
     // per pair
-    int d0, sbase, u_first, u_last, lane_f, q_f, result;
-    uint8_t *dbase;
+    int u_last, lane_f;
+    int *scr;  // shared, Q ints per group
 
-    template <bool EDGE>
+    // Rows / columns past the end of an operand (a pair that finished while others of the warp still run, or the last
+    // lanes of a stripe that overhangs the matrix) read the last code again: such cells are never used.
     __device__ __forceinline__ void load_row(int slot, int i) {
-        if (EDGE) i = min(max(i, 0), nr);
-        const int2 e = lds_v2(tabR + 8 * lds_u8_seq(si + i));
+        const int2 e = lds_v2(tabR + 8 * lds_u8_seq(si + min(i, nr)));
         Rv[slot] = e.x;
         Rl[slot] = (uint32_t) e.y;
     }
-    template <bool EDGE>
     __device__ __forceinline__ void load_col(int slot, int j) {
-        if (EDGE) j = min(max(j, 0), nc);
-        const int2 e = lds_v2(tabC + 8 * lds_u8_seq(sj + j));
+        const int2 e = lds_v2(tabC + 8 * lds_u8_seq(sj + min(j, nc)));
         Cv[slot] = e.x;
         Cl[slot] = (uint32_t) e.y;
     }
-    // Windows as block entry expects them: rows i0-K+1 .. i0+D-1 in slots (r & 7), columns j0 .. j0+K+D-1 in slots n & 7.
+    // Windows as block entry expects them: rows i0-K+1 .. i0 in slots r mod P, columns j0 .. j0+K in slots n mod P
+    // (all rows and columns >= 1 here).
     __device__ __forceinline__ void init_windows(int i0, int j0) {
 #pragma unroll
-        for (int r = -K + 1; r <= D - 1; r++) load_row<true>(r & (P - 1), i0 + r);
+        for (int r = -K + 1; r <= 0; r++) load_row((r + P) % P, i0 + r);
 #pragma unroll
-        for (int n = 0; n <= K + D - 1; n++) load_col<true>(n & (P - 1), j0 + n);
+        for (int n = 0; n <= K; n++) load_col(n % P, j0 + n);
     }
 
-    template <bool EDGE>
-    __device__ __forceinline__ int cell(int i, int j, int ehl, int cbl, int evu, int cbu, int q, int rs, int cs) {
-        const int c_h = go4 - 1, c_v = go4 + 1;  // CB tag 1 -> EH tag 0 / EV tag 2
+    // The close-block state is kept with tag 0 here (cb[] = 4 * CB): its consumers add their tag with the constant they
+    // add anyway, and the choice bits of the close-block minimum come out as a subtraction.
+    __device__ __forceinline__ int cell(int ehl, int cbl, int evu, int cbu, int q, int rs, int cs) {
         const int t = cbl + c_h, t2 = cbu + c_v;
-        int neh = min(ehl, t) + Cv[cs];           // FILL_EXTEND_HORIZONTAL :1765-1787
-        int nev = min(evu, t2) + Rv[rs];          // FILL_EXTEND_VERTICAL :1813-1830
+        const int neh = min(ehl, t) + Cv[cs];     // FILL_EXTEND_HORIZONTAL :1765-1787
+        const int nev = min(evu, t2) + Rv[rs];    // FILL_EXTEND_VERTICAL :1813-1830
         const int d = lds_s32(Rl[rs] + Cl[cs]);   // 4 * cost[si & 15][sj & 15]
-        const int ck = min(min(cb[q] + 2, ev[q]), eh[q]) + d;  // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977 (tags A 3, V 2, H 0)
-        int ncb = (ck & keep) | TAG_CB;
+        const int ck = min(min(cb[q] + 3, ev[q]), eh[q]) + d;  // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977 (tags A 3, V 2, H 0)
+        const int ncb = ck & keep;
         int byte = 0;
         if (BT) {
-            byte = (ehl < t) ? AB_ENDB : (AB_ENDB | AB_ENDH);
-            byte += (evu < t2) ? 0 : AB_ENDV;
-            const int fk = min(min(neh, nev), ncb);  // ASSIGN_MINIMUM :2251-2280
-            byte += (fk & 3) * 4 + (ck & 3);
-        }
-        if (EDGE) {
-            if (i == 0) {
-                if (j == 0) {  // :2194-2198
-                    ncb = TAG_CB; neh = go4 + TAG_EH; nev = go4 + TAG_EV;
-                } else {       // :2212-2217
-                    const int rr = ehl + Cv[cs];
-                    neh = rr; ncb = rr + TAG_CB; nev = HIGH4 + TAG_EV;
-                }
-            } else if (j == 0) {  // the left-edge cells of rows 1..39 (:2486-2494)
-                ncb = HIGH4 + TAG_CB; neh = HIGH4 + TAG_EH;
-                nev = evu + Rv[rs];
-            }
-        }
-        if (EDGE) {
-            // the final cell: the cost of the alignment (:2540-2547).  Unchecked blocks end before any pair's last step.
-            if (i == nr && j == nc) result = min(ncb, min(nev, neh)) >> 2;
+            const int fk = min(min(neh, nev), fma_add(ncb, one, one));  // ASSIGN_MINIMUM :2251-2280 (one = TAG_CB)
+            const int flags = fma_add((ehl < t) ? AB_ENDB : (AB_ENDB | AB_ENDH), one, (evu < t2) ? 0 : AB_ENDV);
+            byte = ((fk * 4 + (ck - ncb)) & 15) | flags;
         }
         cb[q] = ncb; ev[q] = nev; eh[q] = neh;
         return byte;
     }
 
-    // One block of P double steps starting at double step u (u % 4 == 0 when !EDGE), lane origin (i0, j0).
-    // !EDGE: dptr = address of this lane's chunk for the block's first step.
-    template <bool EDGE>
+    // K direction bytes -> two words, by multiply-adds (FMA pipe)
+    __device__ __forceinline__ void pack(const int (&by)[K], uint32_t (&w)[2]) {
+        constexpr int N0 = K < 4 ? K : 4;
+        int a = by[N0 - 1];
+#pragma unroll
+        for (int m = N0 - 2; m >= 0; m--) a = a * 256 + by[m];
+        w[0] = (uint32_t) a;
+        if (K > 4) {
+            int b = by[K - 1];
+#pragma unroll
+            for (int m = K - 2; m >= 4; m--) b = b * 256 + by[m];
+            w[1] = (uint32_t) b;
+        }
+    }
+
+    // One block of P double steps starting at double step u (every lane at rows and columns >= 1), lane origin
+    // (i0, j0).  dptr = the address this lane's chunk of local step 0 has once the pair's tile origin is folded in.
     __device__ __forceinline__ void block(int u, int i0, int j0, uint8_t *dptr) {
 #pragma unroll
         for (int p = 0; p < P; p++) {
             uint32_t de[2] = {0, 0}, dod[2] = {0, 0};
+            int by[K];
             // ---- even step: q = 2m, cell (i0 + p - m, j0 + p + m)
             int in_eh = __shfl_up_sync(0xffffffffu, eh[Q - 1], 1, G);
             int in_cb = __shfl_up_sync(0xffffffffu, cb[Q - 1], 1, G);
-            if (lane == 0) { in_eh = HIGH4 + TAG_EH; in_cb = HIGH4 + TAG_CB; }  // the left-edge cells (:2487, :2494)
+            if (lane == 0) { in_eh = HIGH4 + TAG_EH; in_cb = HIGH4; }  // the left-edge cells (:2487, :2494)
 #pragma unroll
             for (int m = 0; m < K; m++) {
                 const int q = 2 * m;
                 const int ehl = (m == 0) ? in_eh : eh[q - 1], cbl = (m == 0) ? in_cb : cb[q - 1];
-                const int byte = cell<EDGE>(i0 + p - m, j0 + p + m, ehl, cbl, ev[q + 1], cb[q + 1], q, (p - m) & (P - 1),
-                                            (p + m) & (P - 1));
-                if (BT) de[m >> 2] |= (uint32_t) byte << (8 * (m & 3));
+                by[m] = cell(ehl, cbl, ev[q + 1], cb[q + 1], q, (p - m + P) % P, (p + m) % P);
             }
+            if (BT) pack(by, de);
             // ---- odd step: q = 2m + 1, cell (i0 + p - m, j0 + p + m + 1)
             const int in_ev = __shfl_down_sync(0xffffffffu, ev[0], 1, G);
             const int in_cbu = __shfl_down_sync(0xffffffffu, cb[0], 1, G);
@@ -147,34 +167,39 @@ struct AffFast {
             for (int m = 0; m < K; m++) {
                 const int q = 2 * m + 1;
                 const int evu = (m == K - 1) ? in_ev : ev[q + 1], cbu = (m == K - 1) ? in_cbu : cb[q + 1];
-                const int byte = cell<EDGE>(i0 + p - m, j0 + p + m + 1, eh[q - 1], cb[q - 1], evu, cbu, q, (p - m) & (P - 1),
-                                            (p + m + 1) & (P - 1));
+                by[m] = cell(eh[q - 1], cb[q - 1], evu, cbu, q, (p - m + P) % P, (p + m + 1) % P);
                 if (m == K - 1) {
                     if (lane == G - 1) {  // diagonal dhi + 1: poisoned (:2531-2535)
-                        cb[q] = HIGH4 + TAG_CB; ev[q] = HIGH4 + TAG_EV; eh[q] = HIGH4 + TAG_EH;
+                        cb[q] = HIGH4; ev[q] = HIGH4 + TAG_EV; eh[q] = HIGH4 + TAG_EH;
                     }
                 }
-                if (BT) dod[m >> 2] |= (uint32_t) byte << (8 * (m & 3));
             }
-            // ---- direction bytes
-            if (!EDGE) {
-                if (BT) {
-                    constexpr int TILE = G * 8 * BL;
-                    store_dir<BL>(dptr + ((2 * p) >> 3) * TILE + ((2 * p) & 7) * BL, de);
-                    store_dir<BL>(dptr + ((2 * p + 1) >> 3) * TILE + ((2 * p + 1) & 7) * BL, dod);
+            if (BT) pack(by, dod);
+            // ---- direction bytes.  Steps 2(u+p) and 2(u+p)+1 are neighbours inside a tile (Task::tshift): one store for
+            // both, at an offset that depends on u only.  A pair that has finished stores nothing; the odd half of a
+            // pair's last double step may lie past its last anti-diagonal, still inside the band's last tile.
+            const int uu = u + p;
+            if (BT) {
+                constexpr int TILE = G * 8 * BL;
+                const int s2 = 2 * uu;
+                uint8_t *dst = dptr + (ptrdiff_t) (s2 >> 3) * TILE + (s2 & 7) * BL;
+                if (uu <= u_last) {
+                    if (BL == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(de[0], dod[0]);
+                    else *reinterpret_cast<uint4 *>(dst) = make_uint4(de[0], de[1], dod[0], dod[1]);
                 }
-            } else {
-                const int uu = u + p;
-                if (BT && uu >= u_first && uu <= u_last) {
-                    const int te = 2 * uu + d0, s = 2 * uu - sbase;  // s = te - tshift
-                    if (te >= 0) store_dir<BL>(dbase + (((size_t) (s >> 3) * G + lane) * 8 + (s & 7)) * BL, de);
-                    if (te + 1 <= nr + nc) store_dir<BL>(dbase + (((size_t) ((s + 1) >> 3) * G + lane) * 8 + ((s + 1) & 7)) * BL, dod);
-                }
-                (void) uu;
             }
-            // ---- windows: row i0 + p + D and column j0 + p + K + D enter
-            load_row<EDGE>((p + D) & (P - 1), i0 + p + D);
-            load_col<EDGE>((p + K + D) & (P - 1), j0 + p + K + D);
+            // ---- the final cell (nr, nc) belongs to double step u_last: the cost of the alignment (:2540-2547).
+            // The lane that owns its diagonal parks the minima of all its slots in shared memory and picks the slot
+            // after the sweep (selecting the slot here, by index, would push the state arrays to local memory).
+            if (__any_sync(0xffffffffu, uu == u_last)) {
+                if (uu == u_last && lane == lane_f) {
+#pragma unroll
+                    for (int q = 0; q < Q; q++) scr[q] = min(min(cb[q], eh[q]), ev[q]);
+                }
+            }
+            // ---- windows: row i0 + p + 1 and column j0 + p + K + 1 enter
+            load_row((p + 1) % P, i0 + p + 1);
+            load_col((p + K + 1) % P, j0 + p + K + 1);
         }
     }
 };
@@ -183,23 +208,36 @@ struct AffFast {
 template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     aff_fast_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm, const uint8_t *__restrict__ pool, uint8_t *__restrict__ dir,
-                    int *__restrict__ out_cost, int seq_bytes, int *work_counter, int *slow_list, int *slow_count, int keep_mask) {
+                    int *__restrict__ out_cost, int seq_bytes, int *work_counter, int *slow_list, int *slow_count, int keep_mask, int one) {
+    // keep_mask = ~3 and one = 1 arrive as arguments so that they live in registers (see AffFast::cell, fma_add)
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
     using S_t = AffFast<K, G, BT>;
-    constexpr int BL = S_t::BL;
+    constexpr int BL = S_t::BL, P = S_t::P;
     extern __shared__ __align__(16) uint8_t smem[];
     int2 *s_tabR = reinterpret_cast<int2 *>(smem);
     int2 *s_tabC = s_tabR + 256;
     int *s_lut = reinterpret_cast<int *>(s_tabC + 256);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + 2 * 256 * 8 + 16 * FAST_LUT_ROW);
-    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_bar + STRIPE_WARPS * 4);
+    // tables of the boundary phase (AffStripe, stripe_kernels.cuh)
+    uint8_t *s_lut2 = smem + 2 * 256 * 8 + 16 * FAST_LUT_ROW;
+    int *s_prep = reinterpret_cast<int *>(s_lut2 + STRIPE_LUT_BYTES);
+    int *s_get = s_prep + 32;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_get + 32);
+    int *s_scr = reinterpret_cast<int *>(s_bar + STRIPE_WARPS * 4);  // FAST_SCR_INTS per group
+    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_scr + STRIPE_WARPS * 4 * FAST_SCR_INTS);
     if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
     uint32_t bar_phase = 0;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-        s_lut[(k >> 4) * 17 + (k & 15)] = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
-        s_tabR[k] = make_int2(4 * __ldg(cm.cost + ((k & 31) << cm.lcm) + cm.gap), (int) (smem_u32(s_lut) + (k & 15) * FAST_LUT_ROW));
-        s_tabC[k] = make_int2(4 * __ldg(cm.prepend + (k & 31)), (k & 15) * 4);
+        const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
+        s_lut[fast_lut_slot(k >> 4) * (FAST_LUT_ROW / 4) + fast_lut_slot(k)] = c4;
+        *reinterpret_cast<int2 *>(s_lut2 + (k >> 4) * LUT_ROW_BYTES + (k & 15) * 8) = make_int2(c4, c4 - 2);
+        s_tabR[k] = make_int2(4 * __ldg(cm.cost + ((k & 31) << cm.lcm) + cm.gap),
+                              (int) (smem_u32(s_lut) + fast_lut_slot(k) * FAST_LUT_ROW));
+        s_tabC[k] = make_int2(4 * __ldg(cm.prepend + (k & 31)), fast_lut_slot(k) * 4);
+    }
+    for (int k = threadIdx.x; k < 32; k += blockDim.x) {
+        s_prep[k] = 4 * __ldg(cm.prepend + k);
+        s_get[k] = 4 * __ldg(cm.cost + (k << cm.lcm) + cm.gap);
     }
     __syncthreads();
 
@@ -207,6 +245,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     const int grp = lane32 / G, lane = lane32 % G;
     const int op_stride = seq_bytes + fast_operand_pad(K, G);
     uint8_t *my_seq = s_seq + (size_t) ((warp_in_block * GPW + grp) * 2) * op_stride;
+    int *my_scr = s_scr + (warp_in_block * GPW + grp) * FAST_SCR_INTS;
 
     for (;;) {
         int batch = 0;
@@ -251,44 +290,70 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
             continue;
         }
 
-        S_t S;
-        S.si = smem_u32(my_seq); S.sj = smem_u32(my_seq + op_stride);
-        S.tabR = smem_u32(s_tabR); S.tabC = smem_u32(s_tabC);
-        S.nr = nr; S.nc = nc; S.go4 = 4 * cm.gap_open; S.lane = lane; S.keep = keep_mask;
-        S.d0 = d0;
-        S.u_first = (-d0) >> 1;  // first double step: t = 2u + d0 in {-1, 0}
-        S.u_last = valid ? ((nr + nc - d0) >> 1) : (S.u_first - 1);
-        S.sbase = (2 * S.u_first) & ~7;
-        S.dbase = dir + t.dir_off;
+        const int u_first = (-d0) >> 1;  // first double step: t = 2u + d0 in {-1, 0}
+        const int u_last = valid ? ((nr + nc - d0) >> 1) : (u_first - 1);
+        const int sbase = (2 * u_first) & ~7;  // d0 + sbase == t.tshift
+        uint8_t *dbase = dir + t.dir_off;
         const int dd_f = (nc - nr) - d0;
-        S.lane_f = dd_f / Q; S.q_f = dd_f % Q;
-        S.result = 0;
-        int u_end = S.u_last, u_safe = S.u_last, u_begin = S.u_first;
+        const int lane_f = dd_f / Q;
+        int u_end = u_last, u_begin = u_first;
         int u_b = max(G * K, 1 - d0);  // from here on every lane has i >= 1 and j >= 1
 #pragma unroll
         for (int o = G; o < 32; o <<= 1) {
             u_end = max(u_end, __shfl_xor_sync(0xffffffffu, u_end, o));
-            u_safe = min(u_safe, __shfl_xor_sync(0xffffffffu, u_safe, o));
             u_begin = min(u_begin, __shfl_xor_sync(0xffffffffu, u_begin, o));
             u_b = max(u_b, __shfl_xor_sync(0xffffffffu, u_b, o));
         }
-#pragma unroll
-        for (int q = 0; q < Q; q++) { S.cb[q] = HIGH4 + TAG_CB; S.ev[q] = HIGH4 + TAG_EV; S.eh[q] = HIGH4 + TAG_EH; }
-        int u = u_begin & ~3;
+        S_t S;
+        int u = u_begin;
         int i0 = u - lane * K, j0 = u + d0 + lane * K;
-        S.init_windows(i0, j0);
-        for (; u < u_b && u <= u_end; u += FAST_P, i0 += FAST_P, j0 += FAST_P) S.template block<true>(u, i0, j0, nullptr);
-        if (u + FAST_P <= u_safe) {
-            const int s0 = 2 * u - S.sbase;
-            uint8_t *dptr = S.dbase + ((size_t) (s0 >> 3) * G + lane) * 8 * BL;
-            for (; u + FAST_P <= u_safe; u += FAST_P, i0 += FAST_P, j0 += FAST_P, dptr += 2 * G * 8 * BL)
-                S.template block<false>(u, i0, j0, dptr);
+        {
+            // ---- boundary phase: row 0, column 0 and the cells before them, with the stripe kernel's own sweep
+            AffStripe<K, G, BT, false, true> A;
+            A.si = my_seq; A.sj = my_seq + op_stride;
+            A.lut = s_lut2; A.prep = s_prep; A.get = s_get;
+            A.nr = nr; A.nc = nc; A.go4 = 4 * cm.gap_open; A.lane = lane; A.qlow = 0;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                A.cb[q] = HIGH4 + TAG_CB; A.ev[q] = HIGH4 + TAG_EV; A.eh[q] = HIGH4 + TAG_EH; A.eb[q] = HIGH4 + TAG_EB;
+            }
+            A.init_windows(i0, j0);
+            for (; u < u_b && u <= u_end; u++) {
+                uint32_t de[2], dod[2];
+                A.template double_step<true>(i0, j0, de, dod);
+                if (BT) {
+                    const int te = 2 * u + d0, s2 = 2 * u - sbase;  // s2 = te - tshift
+                    if (u >= u_first && u <= u_last) {
+                        if (te >= 0) store_dir<BL>(dbase + (((size_t) (s2 >> 3) * G + lane) * 8 + (s2 & 7)) * BL, de);
+                        if (te + 1 <= nr + nc) store_dir<BL>(dbase + (((size_t) ((s2 + 1) >> 3) * G + lane) * 8 + ((s2 + 1) & 7)) * BL, dod);
+                    }
+                }
+                if (u == u_last && lane == lane_f) {
+#pragma unroll
+                    for (int q = 0; q < Q; q++) my_scr[q] = min(min(A.cb[q], A.eh[q]), A.ev[q]);
+                }
+                i0++; j0++;
+                A.slide_windows(i0, j0);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++) { S.cb[q] = A.cb[q] - TAG_CB; S.ev[q] = A.ev[q]; S.eh[q] = A.eh[q]; }
         }
-        for (; u <= u_end; u += FAST_P, i0 += FAST_P, j0 += FAST_P) S.template block<true>(u, i0, j0, nullptr);
+        if (u <= u_end) {
+            S.si = smem_u32(my_seq); S.sj = smem_u32(my_seq + op_stride);
+            S.tabR = smem_u32(s_tabR); S.tabC = smem_u32(s_tabC);
+            S.nr = nr; S.nc = nc; S.lane = lane; S.keep = keep_mask; S.one = one;
+            S.c_h = 4 * cm.gap_open; S.c_v = 4 * cm.gap_open + TAG_EV;
+            S.u_last = u_last; S.lane_f = lane_f; S.scr = my_scr;
+            S.init_windows(i0, j0);
+            // local step of (double step u, even half) is 2u - sbase: fold the per-pair part into the pointer
+            uint8_t *dptr = dbase + (ptrdiff_t) lane * 8 * BL - (ptrdiff_t) (sbase >> 3) * (G * 8 * BL);
+            for (; u <= u_end; u += P, i0 += P, j0 += P) S.block(u, i0, j0, dptr);
+        }
 
-        if (valid && lane == S.lane_f) {
-            if (BT && nr == 0 && nc == 0) S.result = 0;
-            out_cost[t.pair] = S.result;
+        if (valid && lane == lane_f) {
+            int result = my_scr[dd_f % Q] >> 2;  // parked by this very lane
+            if (BT && nr == 0 && nc == 0) result = 0;
+            out_cost[t.pair] = result;
         }
         __syncwarp();
     }
@@ -311,7 +376,7 @@ static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM 
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, work_counter, slow_list, slow_count, ~3);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, work_counter, slow_list, slow_count, ~3, 1);
     return cudaGetLastError();
 }
 
