@@ -34,7 +34,7 @@ UNIT = "GCUPS"
 OPS_PER_CELL = 50  # integer ops per affine_3 cell with traceback, counted from src/algn.c
 
 
-NCU_DRAM_BYTES_PER_PAIR = {"affine500": 6.863494e9 / 100000}
+NCU_DRAM_BYTES_PER_PAIR = {"affine500": 6.617161e9 / 100000}
 
 WORKLOADS = {
     # name: (description, mode, ops per cell)
@@ -335,21 +335,25 @@ def main():
     # (the band is re-read by the traceback kernel, not by this one)
     alg_bytes = float(pool.len[pairs[:, 0]].astype(np.int64).sum() + pool.len[pairs[:, 1]].astype(np.int64).sum()) + float(cells)
     fill_s = f_ms * 1e-3
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_fill_final.csv:
-    # dram__bytes_read.sum + dram__bytes_write.sum = 6.863 GB for one launch over 100 000 pairs of this workload),
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_fill_fast.csv:
+    # dram__bytes_read.sum + dram__bytes_write.sum = 6.617 GB for one launch over 100 000 pairs of this workload),
     # scaled to the pairs one launch of this run covers; null for workloads without a capture.
     traffic = NCU_DRAM_BYTES_PER_PAIR.get(args.workload)
     if traffic is not None:
         traffic = traffic * n / fill_launches
     roof = {"bound": "hbm", "achieved": alg_bytes / fill_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r01_fill_final.csv)",
+            "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r01_fill_fast.csv)",
             "algorithmic_bytes_per_launch": alg_bytes / fill_launches, "peak_source": hbm_src,
-            "kernel": "aff_stripe_kernel<5,8,true>" if wl_mode == 3 else "lin_stripe_kernel<K,G,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
+            "kernel": ("aff_fast_kernel<5,8,true>" if args.workload == "affine500" else "aff_stripe_kernel<K,G,true>") if wl_mode == 3 else "lin_stripe_kernel<K,G,true>", "kernel_ms_per_step": f_ms, "launches_per_step": fill_launches,
             "note": "integer min-plus recurrence: ALU-bound, see roofline_int32"}
     gops = cells * ops_per_cell / fill_s * 1e-9
     roof_int = {"bound": "int32_alu", "achieved": gops, "peak": add_g, "unit": "Gop/s", "frac": gops / add_g,
                 "ops_per_cell": ops_per_cell, "peak_source": "measured live: dependent-free add.s32 chains (poyb200_int32_peak)",
-                "peak_minmax_gops": mm_g, "peak_minplus_mix_gops": mix_g, "kernel_gcups": cells / fill_s * 1e-9}
+                "peak_minmax_gops": mm_g, "peak_minplus_mix_gops": mix_g, "kernel_gcups": cells / fill_s * 1e-9,
+                "note": "ops_per_cell is the REFERENCE's operation count per cell (SURVEY.md 8d), i.e. algorithmic work; the kernel "
+                        "executes fewer (ncu: 30.1 warp instructions per 32 cells incl. loads/stores on affine500, "
+                        "profiles/r01_fill_fast.csv), so frac can exceed 1; the executed-instruction view is ALU pipe 74 % / "
+                        "issue 81 % active"}
     base = None
     if not args.skip_cpu:
         sample = args.cpu_sample or max(2000, 1500 * threads)
