@@ -169,6 +169,30 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Multi-rank runs: pin this process (and so its pinned host buffers, first touch) to the CPUs of the NUMA node its GPU
+    hangs off, so the 8 ranks' host copies do not all cross one socket.  No-op where sysfs has no answer."""
+    try:
+        import subprocess
+
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        node = int(open("/sys/bus/pci/devices/" + bdf[4:] + "/numa_node").read())
+        if node < 0:
+            return "numa_node unknown (-1): not bound"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: none of its CPUs available, not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +235,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: no binding"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -318,6 +343,28 @@ def main():
     e2e_value = total_cells_all / e2e_max * 1e-9
     checksum = int(cost_t.numpy().astype(np.int64).sum())
 
+    # ---- end-to-end leg 2: the payload SeqCS.DOS.median keeps (cost, median, three gap bitsets; src/seqCS.ml:769-776)
+    # instead of the four sequences -- same kernels, same traceback, smaller result
+    bstride = ((stride + 7) // 8 + 3) // 4 * 4
+    bits_t = [torch.empty((n, bstride), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+    batch.want = S.WANT_MEDIAN | S.WANT_BITSETS
+    batch.medianwg = batch.aligned_a = batch.aligned_b = None
+    batch.bits_a, batch.bits_b, batch.bits_wg = (t.data_ptr() for t in bits_t)
+    batch.bits_stride = bstride
+    d2h_dos = int(n * stride + 3 * n * bstride + n * 4 + n * 16)
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_call()
+    torch.cuda.synchronize()
+    dos_s = (time.perf_counter() - t0) / args.steps
+    barrier()
+    dos_max = max_over_ranks(dos_s)
+    dos_value = total_cells_all / dos_max * 1e-9
+    assert int(cost_t.numpy().astype(np.int64).sum()) == checksum
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,7 +402,7 @@ def main():
                         "profiles/r01_fill_fast.csv), so frac can exceed 1; the executed-instruction view is ALU pipe 74 % / "
                         "issue 81 % active"}
     base = None
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:  # the CPU baseline is an N=1 leg (rank 0, all host threads)
         sample = args.cpu_sample or max(2000, 1500 * threads)
         base, _ = cpu_arm(cm, pool, pairs, sample, threads, deltaw=dw, mode=wl_mode)
     line = {
@@ -367,6 +414,12 @@ def main():
                    "l2": "inputs (pool + direction bands, > 1 GB) exceed the 126 MB L2 between iterations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_max * 1e3, "outputs": "cost, median, medianwg, aligned a, aligned b (pinned host buffers)"},
+        "e2e_dos_median": {"value": dos_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dos,
+                           "ms_per_step": dos_max * 1e3,
+                           "outputs": "what SeqCS.DOS.median keeps (src/seqCS.ml:769-776): cost, median, gap bitsets of "
+                                      "aligned a / aligned b / medianwg (POYB200_WANT_BITSETS); same kernels, the aligned "
+                                      "sequences stay on the device"},
+        "numa": numa_note,
         "gpu_launches": int(launches),
         "phase_ms": {"fill": f_ms, "traceback": t_ms},
         "roofline": roof, "roofline_int32": roof_int, "clocks": clocks, "cost_checksum": checksum,

@@ -60,6 +60,8 @@ extern "C" {
 #define POYB200_WANT_MEDIAN 1u    /* ancestor_2 (linear) / `median` of align_affine_3 */
 #define POYB200_WANT_MEDIANWG 2u  /* median_2_with_gaps (linear) / `medianwg` */
 #define POYB200_WANT_ALIGNED 4u   /* the two aligned (edited) sequences */
+#define POYB200_WANT_BITSETS 8u   /* the three gap bitsets SeqCS.DOS.median keeps instead of the aligned sequences:
+                                     seq_to_bitset gap tmpa / tmpb / seqmwg (src/seqCS.ml:649-655, 769-771) */
 
 /* Flat image of the reference's `struct cm` (src/cm.h:32-46).  cost/median/worst have (1<<lcm)*(1<<lcm)
  * entries indexed (a << lcm) + b (src/cm.c:501-504); prepend_cost/tail_cost have 1<<lcm entries. */
@@ -89,7 +91,15 @@ typedef struct poyb200_batch {
     int32_t *cost;
     uint8_t *median, *medianwg, *aligned_a, *aligned_b;
     int64_t out_stride;
-    int32_t *out_len; /* 4 * n_pairs */
+    int32_t *out_len; /* 4 * n_pairs: lengths of median, medianwg, aligned a, aligned b */
+    /* POYB200_WANT_BITSETS: rows of bits_stride bytes (a multiple of 4, >= out_stride / 8).  Each row holds one bit
+     * per column of the alignment, 1 where the element differs from the gap code (BitSet.is_set of seq_to_bitset),
+     * as a RIGHT-aligned bit string, most significant bit of a byte first: column c of an alignment of n columns
+     * (n = out_len[4 p + 2]) is bit 8 * bits_stride - n + c, i.e. numpy.unpackbits(row)[-n:] is the bitset in column
+     * order.  Bits in front of the string are unspecified.  With cost + median + these three rows a caller holds
+     * everything DOS.median stores (the aligned sequences follow from bitset + operand, bitset_to_seq, :623-647). */
+    uint8_t *bits_a, *bits_b, *bits_wg;
+    int64_t bits_stride;
 } poyb200_batch;
 
 typedef struct poyb200_ctx poyb200_ctx;

@@ -24,7 +24,8 @@ class Batch(C.Structure):
                 ("n_seqs", C.c_int32), ("pairs", C.c_void_p), ("n_pairs", C.c_int32), ("deltaw", C.c_void_p),
                 ("swaped", C.c_void_p), ("want", C.c_uint32), ("cost", C.c_void_p), ("median", C.c_void_p),
                 ("medianwg", C.c_void_p), ("aligned_a", C.c_void_p), ("aligned_b", C.c_void_p),
-                ("out_stride", C.c_int64), ("out_len", C.c_void_p)]
+                ("out_stride", C.c_int64), ("out_len", C.c_void_p), ("bits_a", C.c_void_p), ("bits_b", C.c_void_p),
+                ("bits_wg", C.c_void_p), ("bits_stride", C.c_int64)]
 
 
 class CM3(C.Structure):

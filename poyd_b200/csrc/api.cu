@@ -98,12 +98,12 @@ struct poyb200_ctx {
     PinnedVec<Task> tasks, tasks_tmp;
     std::vector<Chunk> chunks;
     std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
-    DevBuf<uint8_t> d_pool, d_dir, d_out[4];
+    DevBuf<uint8_t> d_pool, d_dir, d_out[4], d_bits[3];
     DevBuf<Task> d_tasks;
     DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters, d_slow_list;
     size_t counter_next = 0;  // work counters handed to launches of the current call (zeroed once per call)
     DevBuf<int4> d_aff_state;
-    long long dstride = 0;
+    long long dstride = 0, bstride = 0;
     size_t dir_budget = 0;
     int state_stride = 0;
     int stripe_seq_bytes = 16;
@@ -518,10 +518,17 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         if ((b->want & POYB200_WANT_MEDIANWG) && !b->medianwg) return fail(ctx, POYB200_EINVAL, "WANT_MEDIANWG without buffer");
         if ((b->want & POYB200_WANT_ALIGNED) && (!b->aligned_a || !b->aligned_b))
             return fail(ctx, POYB200_EINVAL, "WANT_ALIGNED without buffers");
-        if (b->want && b->out_stride < maxcap) return fail(ctx, POYB200_EINVAL, "out_stride smaller than len a + len b + 2");
+        if ((b->want & ~POYB200_WANT_BITSETS) && b->out_stride < maxcap)
+            return fail(ctx, POYB200_EINVAL, "out_stride smaller than len a + len b + 2");
+        if (b->want & POYB200_WANT_BITSETS) {
+            if (!b->bits_a || !b->bits_b || !b->bits_wg) return fail(ctx, POYB200_EINVAL, "WANT_BITSETS without buffers");
+            if ((b->bits_stride & 3) || b->bits_stride * 8 < maxcap)
+                return fail(ctx, POYB200_EINVAL, "bits_stride must be a multiple of 4 and hold len a + len b + 2 bits");
+        }
         if (b->want && !b->out_len) return fail(ctx, POYB200_EINVAL, "out_len is NULL");
     }
     ctx->dstride = (maxcap + 15) & ~15ll;
+    ctx->bstride = (ctx->dstride / 8 + 3) & ~3ll;
     ctx->state_stride = maxW + 2;
     ctx->stripe_seq_bytes = (max_stripe_len + 15) & ~15;
     // Group by kernel class (stable: keeps the caller's order inside a class).  A batch of one class -- the usual
@@ -628,6 +635,8 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
             CK(ctx->d_out[2].reserve(ob));
             CK(ctx->d_out[3].reserve(ob));
         }
+        if (b->want & POYB200_WANT_BITSETS)
+            for (int k = 0; k < 3; k++) CK(ctx->d_bits[k].reserve(n * (size_t) ctx->bstride + 16));
     }
     if (n && upload) {
         CK(cudaMemcpyAsync(ctx->d_pool.p, b->pool, b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -650,7 +659,7 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     cudaStream_t s_tb = two ? ctx->s_tb : ctx->stream;
     ctx->cur_dir = (two && (ci & 1)) ? ctx->d_dir2.p : ctx->d_dir.p;
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
-                ctx->d_outlen.p, ctx->dstride, ctx->hb.want};
+                ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride};
     if (two && ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - 2], 0));  // the buffer is free again
     if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk
@@ -784,6 +793,18 @@ static int fetch_range(poyb200_ctx *ctx, size_t lo, size_t hi, cudaStream_t st, 
             else
                 CK(cudaMemcpy2DAsync(d + (b.out_stride - w), (size_t) b.out_stride, src + (ctx->dstride - w),
                                      (size_t) ctx->dstride, w, n, cudaMemcpyDeviceToHost, st));
+        }
+        if (b.want & POYB200_WANT_BITSETS) {
+            // right-aligned bit rows: the trailing bytes that hold the longest alignment of the range
+            uint8_t *bdst[3] = {b.bits_a, b.bits_b, b.bits_wg};
+            const size_t bfull = (size_t) std::min<long long>(ctx->bstride, b.bits_stride);
+            const size_t bw = lens_known ? std::min(bfull, ((size_t) (wmax[2] + 7) / 8 + 31) & ~(size_t) 31) : bfull;
+            for (int k = 0; k < 3 && bw; k++) {
+                uint8_t *d = bdst[k] + lo * (size_t) b.bits_stride;
+                const uint8_t *src = ctx->d_bits[k].p + lo * (size_t) ctx->bstride;
+                CK(cudaMemcpy2DAsync(d + (b.bits_stride - bw), (size_t) b.bits_stride, src + (ctx->bstride - bw),
+                                     (size_t) ctx->bstride, bw, n, cudaMemcpyDeviceToHost, st));
+            }
         }
     }
     return POYB200_OK;

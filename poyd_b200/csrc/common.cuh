@@ -88,6 +88,8 @@ struct OutPtrs {
     int *out_len;
     long long stride;
     uint32_t want;
+    uint8_t *bits_a, *bits_b, *bits_wg;  // POYB200_WANT_BITSETS rows
+    long long bstride;                   // bytes per bitset row (multiple of 4)
 };
 
 __device__ __forceinline__ int cm_cost(const DevCM &c, int a, int b) { return __ldg(c.cost + (a << c.lcm) + b); }

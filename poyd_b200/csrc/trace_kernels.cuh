@@ -28,6 +28,26 @@ struct RevWriter {
     }
 };
 
+// One flag per alignment column, written right-to-left like RevWriter: a right-aligned bit string, most significant bit
+// of a byte first (numpy.unpackbits order), gathered into 32-bit words.  capbits is a multiple of 32.
+struct RevBitWriter {
+    uint32_t *base;
+    int pos;
+    uint32_t acc;
+    __device__ __forceinline__ void init(uint8_t *row, int capbits) { base = reinterpret_cast<uint32_t *>(row); pos = capbits; acc = 0; }
+    __device__ __forceinline__ void put(bool bit) {
+        pos--;
+        acc |= (uint32_t) bit << ((((pos >> 3) & 3) << 3) + 7 - (pos & 7));
+        if ((pos & 31) == 0) {
+            __stcs(base + (pos >> 5), acc);
+            acc = 0;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (pos & 31) __stcs(base + (pos >> 5), acc);
+    }
+};
+
 // backtrace_affine (src/algn.c:1983-2097).  dcap = device row stride (multiple of 16).
 __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
@@ -45,8 +65,16 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     const uint8_t *dbase = dir + t.dir_off;
     const int dcap = (int) out.stride;
     const size_t row = (size_t) t.pair * out.stride;
-    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4;
+    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
     RevWriter med, wg, ri, rj;
+    RevBitWriter bi, bj, bw;
+    {
+        const size_t brow = w_bits ? (size_t) t.pair * out.bstride : 0;
+        const bool rows_b_ = (t.flags & TF_ROWS_ARE_B) != 0;
+        bi.init((rows_b_ ? out.bits_b : out.bits_a) + brow, (int) out.bstride * 8);
+        bj.init((rows_b_ ? out.bits_a : out.bits_b) + brow, (int) out.bstride * 8);
+        bw.init(out.bits_wg + brow, (int) out.bstride * 8);
+    }
     med.init(out.median + (w_med ? row : 0), dcap);
     wg.init(out.medianwg + (w_wg ? row : 0), dcap);
     // resi belongs to the row sequence; rows may be the caller's operand b (algn.c:2606-2616)
@@ -59,8 +87,8 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     enum { M_TODO, M_VERT, M_HORI, M_DIAG, M_ALGN };
     int mode = M_TODO;
 #define PUT_MED(v) do { nmed++; med_first = (v); if (w_med) med.put(v); } while (0)
-#define PUT_WG(v) do { nwg++; if (w_wg) wg.put(v); } while (0)
-#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } } while (0)
+#define PUT_WG(v) do { nwg++; if (w_wg) wg.put(v); if (w_bits) bw.put((v) != TMPGAP); } while (0)
+#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } if (w_bits) { bi.put((a) != TMPGAP); bj.put((b) != TMPGAP); } } while (0)
     while (i != 0 && j != 0) {
         const int d = j - i;
         int b;
@@ -121,6 +149,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     if (w_med) med.flush();
     if (w_wg) wg.flush();
     if (w_al) { ri.flush(); rj.flush(); }
+    if (w_bits) { bi.flush(); bj.flush(); bw.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
     }
@@ -147,10 +176,17 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     const uint8_t *dbase = dir + t.dir_off;
     const int dcap = (int) out.stride, gap = cm.gap;
     const size_t row = (size_t) t.pair * out.stride;
-    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4;
+    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
     const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
     const bool swaped = (t.flags & TF_SWAPED) != 0;
     RevWriter med, wg, r1, r2;
+    RevBitWriter b1, b2, bw;
+    {
+        const size_t brow = w_bits ? (size_t) t.pair * out.bstride : 0;
+        b1.init((rows_b ? out.bits_b : out.bits_a) + brow, (int) out.bstride * 8);
+        b2.init((rows_b ? out.bits_a : out.bits_b) + brow, (int) out.bstride * 8);
+        bw.init(out.bits_wg + brow, (int) out.bstride * 8);
+    }
     med.init(out.median + (w_med ? row : 0), dcap);
     wg.init(out.medianwg + (w_wg ? row : 0), dcap);
     r1.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
@@ -176,12 +212,14 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
         const int ea = rows_b ? y : x, eb = rows_b ? x : y;  // caller's operand order
         const int mm = cm_median(cm, ea, eb);
         if (w_wg) wg.put(mm);
+        if (w_bits) { b1.put(x != gap); b2.put(y != gap); bw.put(mm != gap); }
         if (mm != gap) { nmed++; if (w_med) med.put(mm); }
     }
     nmed++;
     if (w_med) { med.put(gap); med.flush(); }
     if (w_wg) wg.flush();
     if (w_al) { r1.flush(); r2.flush(); }
+    if (w_bits) { b1.flush(); b2.flush(); bw.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
     ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
     }

@@ -27,7 +27,7 @@ import numpy as np
 from . import _lib
 from .cost_matrix import CostMatrix
 
-WANT_MEDIAN, WANT_MEDIANWG, WANT_ALIGNED = 1, 2, 4
+WANT_MEDIAN, WANT_MEDIANWG, WANT_ALIGNED, WANT_BITSETS = 1, 2, 4, 8
 MODE_COST_2, MODE_ALIGN_2, MODE_COST_AFFINE_3, MODE_ALIGN_AFFINE_3 = 0, 1, 2, 3
 
 
@@ -90,6 +90,9 @@ class Aligned:
     medianwg: Optional[np.ndarray] = None
     aligned_a: Optional[np.ndarray] = None
     aligned_b: Optional[np.ndarray] = None
+    bits_a: Optional[np.ndarray] = None   # WANT_BITSETS: right-aligned bit rows (numpy.unpackbits order)
+    bits_b: Optional[np.ndarray] = None
+    bits_wg: Optional[np.ndarray] = None
 
     _COL = {"median": 0, "medianwg": 1, "aligned_a": 2, "aligned_b": 3}
 
@@ -97,6 +100,12 @@ class Aligned:
         buf = getattr(self, what)
         n = int(self.lens[p, self._COL[what]])
         return buf[p, buf.shape[1] - n:]
+
+    def bitset(self, what: str, p: int) -> np.ndarray:
+        """``seq_to_bitset gap`` of the aligned operand a / b or of medianwg (src/seqCS.ml:649-655) as 0/1 flags in
+        column order: 1 where the element is not the gap."""
+        n = int(self.lens[p, 2])
+        return np.unpackbits(getattr(self, "bits_" + what)[p])[-n:] if n else np.zeros(0, np.uint8)
 
 
 def deltaw_calc(s1len: np.ndarray, s2len: np.ndarray, deltaw: Optional[np.ndarray]) -> np.ndarray:
@@ -179,6 +188,12 @@ class Align:
         res = Aligned(cost=np.zeros(n, np.int32))
         b.cost = res.cost.ctypes.data
         b.want = want
+        if (want & WANT_BITSETS) and outputs:
+            cap = int((pool.len[pairs[:, 0]].astype(np.int64) + pool.len[pairs[:, 1]]).max()) + 2 if n else 16
+            bstride = ((cap + 7) // 8 + 3) // 4 * 4
+            res.bits_a, res.bits_b, res.bits_wg = (np.zeros((n, bstride), np.uint8) for _ in range(3))
+            b.bits_a, b.bits_b, b.bits_wg = res.bits_a.ctypes.data, res.bits_b.ctypes.data, res.bits_wg.ctypes.data
+            b.bits_stride = bstride
         if want and outputs:
             stride = 16
             if n:

@@ -121,3 +121,21 @@ def ragged_batch(n_pairs: int, max_len: int = 300, seed: int = 7, alphabet: str 
     pool = SeqPool(seqs)
     pairs = np.arange(2 * n_pairs, dtype=np.int32).reshape(-1, 2)
     return pool, pairs
+
+
+def taxa_on_random_tree(n_taxa: int, length: int = 1500, seed: int = 5, subst: float = 0.03, indel: float = 0.005):
+    """Leaf sequences of a random binary tree (configs[4] of BASELINE.json: "500-taxon x 1.5 kb unaligned DNA"): a
+    uniform root sequence evolves down a random-join topology, every branch applying `subst` substitutions and `indel`
+    single-base indels.  Returns {taxon code 1..n: [sequence with its leading gap]} (one locus per taxon)."""
+    rng = np.random.default_rng(seed)
+    bases = np.array([1, 2, 4, 8], np.uint8)
+    # random topology by successive splits: a list of current tips, each a sequence; pick one, replace by two children
+    tips = [bases[rng.integers(0, 4, size=length)]]
+    while len(tips) < n_taxa:
+        k = int(rng.integers(0, len(tips)))
+        parent = tips.pop(k)
+        for _ in range(2):
+            flat, lens = _mutate_rows(rng, parent[None, :], bases, subst, indel)
+            tips.append(flat[:int(lens[0])])
+    perm = rng.permutation(n_taxa)
+    return {i + 1: [np.concatenate([[DNA_GAP], tips[int(p)]]).astype(np.uint8)] for i, p in enumerate(perm)}

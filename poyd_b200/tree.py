@@ -326,86 +326,131 @@ class Evaluator:
             out[k] = len(store) - 1
         return out  # type: ignore[return-value]
 
-    def evaluate(self, topo: Topology, leaves: Dict[int, List[np.ndarray]]) -> TreeCost:
-        n_loci = len(next(iter(leaves.values())))
-        store: List[np.ndarray] = []
-        nb0 = getattr(self.e, "calls", 0)
-        # directional nodes D[(u, v)] = u looking away from v: (store index per locus, total cost, min_child_code)
-        D: Dict[Tuple[int, int], Tuple[List[int], int, int]] = {}
-        leaf_entry: Dict[int, Tuple[List[int], int, int]] = {}
-        for code, seqs in leaves.items():
+    # -- persistent state: every sequence ever produced, and the medians keyed by WHAT they are medians of.  A
+    # directional node depends only on the rooted subtree behind it, so subtrees are interned (hash-consed) and their
+    # medians survive from one tree to the next -- a Wagner step or an SPR move recomputes only what it changed.
+    def _reset(self) -> None:
+        self.store: List[np.ndarray] = []
+        self._sig: Dict[Tuple[int, int], int] = {}          # (sig x, sig y) ordered -> sig id of the median node
+        self._node: Dict[int, Tuple[List[int], int, int]] = {}  # sig id -> (store index per locus, total cost, min_child_code)
+        self._edge: Dict[Tuple[int, int], Tuple[List[int], int]] = {}
+        self._leafsig: Dict[int, int] = {}
+        self.n_medians = 0
+        self._next_sig = 0
+
+    def _new_sig(self) -> int:
+        self._next_sig += 1
+        return self._next_sig - 1
+
+    def _leaf(self, code: int, seqs: List[np.ndarray]) -> int:
+        sig = self._leafsig.get(code)
+        if sig is None:
             idx = []
-            for s in seqs:
-                store.append(np.ascontiguousarray(s, np.uint8))
-                idx.append(len(store) - 1)
-            leaf_entry[code] = (idx, 0, code)
+            for q in seqs:
+                self.store.append(np.ascontiguousarray(q, np.uint8))
+                idx.append(len(self.store) - 1)
+            sig = self._leafsig[code] = self._new_sig()
+            self._node[sig] = (idx, 0, code)
+        return sig
 
-        def nbrs(v):
-            return topo.nodes[v]
-
-        # dependency level of every directed pair
-        level: Dict[Tuple[int, int], int] = {}
-        order: List[Tuple[int, int]] = []
+    def directional(self, topo: Topology, leaves: Dict[int, List[np.ndarray]]) -> Dict[Tuple[int, int], int]:
+        """Signature of every directional node ``(u, v)`` = u looking away from v (``AllDirNode.not_with v``), all
+        missing medians computed level by level, one batch per level."""
+        n_loci = len(next(iter(leaves.values())))
+        store = self.store
+        sig: Dict[Tuple[int, int], int] = {}
+        pending: Dict[Tuple[int, int], int] = {}   # directed pair -> level, for the ones whose median is not cached
         for u in topo.nodes:
-            for v in nbrs(u):
+            for v in topo.nodes[u]:
                 stack = [(u, v)]
                 while stack:
                     a, b = stack[-1]
-                    if (a, b) in level:
+                    if (a, b) in sig:
                         stack.pop()
                         continue
                     if topo.is_leaf(a):
-                        level[(a, b)] = 0
+                        sig[(a, b)] = self._leaf(a, leaves[a])
                         stack.pop()
                         continue
                     x, y = topo.other_two_nbrs(b, a)
-                    need = [(x, a), (y, a)]
-                    miss = [k for k in need if k not in level]
+                    miss = [k for k in ((x, a), (y, a)) if k not in sig]
                     if miss:
                         stack.extend(miss)
-                    else:
-                        level[(a, b)] = 1 + max(level[need[0]], level[need[1]])
-                        order.append((a, b))
-                        stack.pop()
-        for (a, b), lv in level.items():
-            if lv == 0:
-                D[(a, b)] = leaf_entry[a]
-        n_medians = 0
-        for lv in range(1, max(level.values()) + 1 if level else 1):
-            keys = [k for k in order if level[k] == lv]
-            jobs, spec = [], []
-            for (a, b) in keys:
-                x, y = topo.other_two_nbrs(b, a)
-                dx, dy = D[(x, a)], D[(y, a)]
-                if not dx[2] < dy[2]:  # Node.cs_median: the operand with the smaller min_child_code first
-                    dx, dy = dy, dx
-                spec.append((dx, dy))
-                for l in range(n_loci):
-                    jobs.append((dx[0][l], dy[0][l]))
-            res = self._medians(store, jobs)
-            n_medians += len(jobs)
-            for k, (key, (dx, dy)) in enumerate(zip(keys, spec)):
-                r = res[k * n_loci:(k + 1) * n_loci]
-                D[key] = ([i for i, _ in r], dx[1] + dy[1] + sum(c for _, c in r), min(dx[2], dy[2]))
-        # edge medians (refresh_all_edges) and their root costs
-        edges = topo.pre_order_edges()
-        jobs, spec = [], []
-        for (a, b) in edges:
-            da, db = D[(a, b)], D[(b, a)]
-            if not da[2] < db[2]:
-                da, db = db, da
-            spec.append((da, db))
-            for l in range(n_loci):
-                jobs.append((da[0][l], db[0][l]))
-        res = self._medians(store, jobs)
-        n_medians += len(jobs)
+                        continue
+                    sx, sy = sig[(x, a)], sig[(y, a)]
+                    # Node.cs_median: the operand with the smaller min_child_code first (src/node.ml:343-348)
+                    if not self._minc(sx, pending) < self._minc(sy, pending):
+                        sx, sy = sy, sx
+                    s_ = self._sig.get((sx, sy))
+                    if s_ is None:
+                        s_ = self._sig[(sx, sy)] = self._new_sig()
+                        self._fresh[s_] = (sx, sy, 1 + max(self._fresh.get(sx, (0, 0, 0))[2], self._fresh.get(sy, (0, 0, 0))[2]))
+                    sig[(a, b)] = s_
+                    stack.pop()
+        # compute the fresh signatures, level by level
+        if self._fresh:
+            top = max(l for _, _, l in self._fresh.values())
+            for lv in range(1, top + 1):
+                keys = [k for k, (_, _, l) in self._fresh.items() if l == lv]
+                jobs = []
+                for k in keys:
+                    sx, sy, _ = self._fresh[k]
+                    for l in range(n_loci):
+                        jobs.append((self._node[sx][0][l], self._node[sy][0][l]))
+                res = self._medians(store, jobs)
+                self.n_medians += len(jobs)
+                for i, k in enumerate(keys):
+                    sx, sy, _ = self._fresh[k]
+                    r = res[i * n_loci:(i + 1) * n_loci]
+                    nx, ny = self._node[sx], self._node[sy]
+                    self._node[k] = ([j for j, _ in r], nx[1] + ny[1] + sum(c for _, c in r), min(nx[2], ny[2]))
+            self._fresh.clear()
+        return sig
+
+    def _minc(self, s_: int, pending) -> int:
+        if s_ in self._node:
+            return self._node[s_][2]
+        sx, sy, _ = self._fresh[s_]
+        return min(self._minc(sx, pending), self._minc(sy, pending))
+
+    def edge_medians(self, topo: Topology, sig: Dict[Tuple[int, int], int], edges: List[Tuple[int, int]],
+                     n_loci: int) -> Dict[Tuple[int, int], Tuple[List[int], int]]:
+        """``refresh_all_edges`` (src/allDirChar.ml:672-700): the median across every edge and its root cost."""
         E: Dict[Tuple[int, int], Tuple[List[int], int]] = {}
-        for k, (e, (da, db)) in enumerate(zip(edges, spec)):
-            r = res[k * n_loci:(k + 1) * n_loci]
-            E[e] = ([i for i, _ in r], da[1] + db[1] + sum(c for _, c in r))
+        jobs, todo = [], []
+        for (a, b) in edges:
+            sa, sb = sig[(a, b)], sig[(b, a)]
+            if not self._node[sa][2] < self._node[sb][2]:
+                sa, sb = sb, sa
+            hit = self._edge.get((sa, sb))
+            if hit is not None:
+                E[(a, b)] = hit
+                continue
+            todo.append(((a, b), sa, sb))
+            for l in range(n_loci):
+                jobs.append((self._node[sa][0][l], self._node[sb][0][l]))
+        res = self._medians(self.store, jobs)
+        self.n_medians += len(jobs)
+        for i, (e, sa, sb) in enumerate(todo):
+            r = res[i * n_loci:(i + 1) * n_loci]
+            E[e] = self._edge[(sa, sb)] = ([j for j, _ in r], self._node[sa][1] + self._node[sb][1] + sum(c for _, c in r))
+        return E
+
+    def evaluate(self, topo: Topology, leaves: Dict[int, List[np.ndarray]], keep: bool = False) -> TreeCost:
+        """Downpass + uppass of one tree.  ``keep=True`` keeps the median cache for the next tree over the same leaves."""
+        if not keep or not hasattr(self, "store"):
+            self._reset()
+        self._fresh: Dict[int, Tuple[int, int, int]] = {}
+        n_loci = len(next(iter(leaves.values())))
+        store = self.store
+        nb0, nm0 = getattr(self.e, "calls", 0), self.n_medians
+        sig = self.directional(topo, leaves)
+        D = {k: self._node[v] for k, v in sig.items()}
+        edges = topo.pre_order_edges()
+        E = self.edge_medians(topo, sig, edges, n_loci)
         # general_pick_best_root with blindly_trust_downpass
         h = topo.handle
-        root = (h, nbrs(h)[0])  # create_root: the handle and its parent
+        root = (h, topo.nodes[h][0])  # create_root: the handle and its parent
         best = E[root][1]
         for e in sorted(edges, key=lambda e: (-e[0], -e[1])):
             c = E[e][1]
@@ -434,19 +479,60 @@ class Evaluator:
                     nxt.append((cur, y, sg))
             frontier = nxt
         # check_cost: distances between single assignments along the edges, oriented away from the handle
-        jobs, zero = [], 0
+        jobs = []
         for (p, v) in edges:
             for l in range(n_loci):
                 s1, s2 = store[singles[p][l]], store[singles[v][l]]
-                if _is_empty(s1, self.gap) or _is_empty(s2, self.gap):
-                    zero += 1  # missing_distance = 0
-                else:
+                if not (_is_empty(s1, self.gap) or _is_empty(s2, self.gap)):  # else missing_distance = 0
                     jobs.append((singles[p][l], singles[v][l]))
         adjusted = int(self.e.distance(store, np.array(jobs, np.int32)).astype(np.int64).sum()) if jobs else 0
         return TreeCost(adjusted=adjusted, unadjusted=int(best), root=root,
                         singles={v: [store[i] for i in ix] for v, ix in singles.items()},
                         root_costs={e: c for e, (_, c) in E.items()}, batches=getattr(self.e, "calls", 0) - nb0,
-                        medians=n_medians, stats={"edges": len(edges), "loci": n_loci, "sequences": len(store)})
+                        medians=self.n_medians - nm0, stats={"edges": len(edges), "loci": n_loci, "sequences": len(store)})
+
+    # -- Wagner build with a batched candidate-edge sweep (Ptree.make_wagner_tree, src/ptree.ml:948-1060) --------------
+    def wagner(self, leaves: Dict[int, List[np.ndarray]], order: Optional[List[int]] = None):
+        """Adds the taxa one at a time.  For each, ``AllDirChar.cost_fn`` (src/allDirChar.ml:1279-1317) --
+        ``Node.distance clade (median across the edge)``, i.e. ``DOS.distance`` -- is evaluated on EVERY edge of the
+        current tree in one batch (the Wagner manager really visits all edges, src/queues.ml:367-407), the taxon joins
+        the edge of smallest cost, and only the medians the join invalidated are recomputed.  Deterministic variant:
+        taxa in the given order, ties to the first edge in pre-order (the reference randomises both).
+        Returns (topology, per-step records)."""
+        self._reset()
+        self._fresh = {}
+        order = list(order) if order is not None else sorted(leaves)
+        n_loci = len(next(iter(leaves.values())))
+        t1, t2 = order[0], order[1]
+        nodes: Dict[int, Tuple[int, ...]] = {t1: (t2,), t2: (t1,)}
+        topo = Topology(nodes, t1, len(leaves))
+        next_id = max(leaves) + 1
+        steps = []
+        for c in order[2:]:
+            sig = self.directional(topo, leaves)
+            edges = topo.pre_order_edges()
+            E = self.edge_medians(topo, sig, edges, n_loci)
+            cl = self._node[self._leaf(c, leaves[c])][0]
+            jobs, owner = [], []
+            for k, e in enumerate(edges):
+                for l in range(n_loci):
+                    m = E[e][0][l]
+                    if not (_is_empty(self.store[cl[l]], self.gap) or _is_empty(self.store[m], self.gap)):
+                        jobs.append((cl[l], m))
+                        owner.append(k)
+            delta = np.zeros(len(edges), np.int64)
+            if jobs:
+                np.add.at(delta, np.array(owner), self.e.distance(self.store, np.array(jobs, np.int32)).astype(np.int64))
+            k = int(np.argmin(delta))  # first minimum
+            a, b = edges[k]
+            v = next_id
+            next_id += 1
+            nodes[v] = (a, b, c)
+            nodes[a] = tuple(v if x == b else x for x in nodes[a])
+            nodes[b] = tuple(v if x == a else x for x in nodes[b])
+            nodes[c] = (v,)
+            steps.append({"taxon": c, "edge": (a, b), "delta": int(delta[k]), "edges": len(edges)})
+        return topo, steps
 
     def _nonempty_parent(self, store, parent: int, mine: int) -> int:
         # DOS.to_single (src/seqCS.ml:734-739): an empty parent is replaced by the vertex's own sequence

@@ -463,3 +463,37 @@ def test_one_million_pairs_bit_exact(S, checker_factory):
         total += slice_pairs
     assert total >= 1_000_000
     al.close()
+
+
+@pytest.mark.parametrize("affine", [True, False])
+def test_dos_median_payload_bitsets(S, checker_factory, affine):
+    """POYB200_WANT_BITSETS: cost + median + the three gap bitsets SeqCS.DOS.median keeps (src/seqCS.ml:769-771) --
+    without transferring the aligned sequences -- against seq_to_bitset of the checker's aligned sequences, for
+    ragged lengths (so operands swap roles) and for operands that carry gap bits."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    cm = CM.nucleotides(1, 2, 3) if affine else CM.default_nucleotides()
+    chk = checker_factory(cm)
+    for pool, pairs in (synth.ragged_batch(1500, max_len=260, seed=41),
+                        synth.pair_batch(700, 500, seed=42, min_len=430, gap_ambiguity=0.08)):
+        al = S.Align(cm)
+        if affine:
+            g = al.align_affine_3(pool, pairs, want=S.WANT_MEDIAN | S.WANT_BITSETS)
+            o = chk.batch(3, pool.pool, pool.off, pool.len, pairs)
+        else:
+            dw = al.deltaw_for(pool, pairs)
+            g = al.align_2(pool, pairs, want=S.WANT_MEDIAN | S.WANT_BITSETS)
+            o = chk.batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw)
+        assert g.aligned_a is None and g.medianwg is None
+        assert np.array_equal(g.cost, o["cost"]) and np.array_equal(g.lens, o["lens"])
+        for p in range(len(pairs)):
+            n, nm = int(o["lens"][p, 2]), int(o["lens"][p, 0])
+            assert np.array_equal(g.get("median", p), o["median"][p, :nm])
+            assert np.array_equal(g.bitset("a", p), (o["ra"][p, :n] != cm.gap).astype(np.uint8)), p
+            assert np.array_equal(g.bitset("b", p), (o["rb"][p, :n] != cm.gap).astype(np.uint8)), p
+            assert np.array_equal(g.bitset("wg", p), (o["medianwg"][p, :n] != cm.gap).astype(np.uint8)), p
+        # the full payload in one call gives the same bitsets
+        g2 = al.align_affine_3(pool, pairs, want=15) if affine else al.align_2(pool, pairs, want=15)
+        for p in range(0, len(pairs), 7):
+            assert np.array_equal(g2.bitset("a", p), g.bitset("a", p)) and np.array_equal(g2.bitset("wg", p), g.bitset("wg", p))
+        al.close()

@@ -75,3 +75,62 @@ def test_reference_tree_costs_gpu(tmp_path, k):
         assert eng.al.launch_count() > 0
     finally:
         eng.close()
+
+
+def _newick(topo):
+    def down(p, v):
+        if topo.is_leaf(v):
+            return str(v)
+        x, y = topo.other_two_nbrs(p, v)
+        return "(" + " ".join(sorted([down(v, x), down(v, y)])) + ")"
+    h = topo.handle
+    return "(" + str(h) + " " + down(h, topo.nodes[h][0]) + ")" if topo.is_leaf(h) else None
+
+
+@pytest.mark.parametrize("affine", [False, True])
+def test_wagner_sweep_and_cache_cpu_checker(affine, checker_factory):
+    from oracle_engine import OracleEngine
+    from poyd_b200 import synth
+
+    cm = CM.nucleotides(2, 1, 1) if affine else CM.default_nucleotides()
+    leaves = synth.taxa_on_random_tree(12, 120, seed=3, subst=0.06, indel=0.02)
+    eng = OracleEngine(cm, nthreads=2)
+    ev = T.Evaluator(eng, cm)
+    topo, steps = ev.wagner(leaves)
+    assert len(steps) == 10 and sorted(v for v in topo.nodes if topo.is_leaf(v)) == list(range(1, 13))
+    assert all(len(n) in (1, 3) for n in topo.nodes.values()) and len(topo.nodes) == 2 * 12 - 2
+    # every step saw every edge of the tree it was added to (2 k - 3 edges for k taxa)
+    assert [s["edges"] for s in steps] == [2 * k - 3 for k in range(2, 12)]
+    # the cached evaluation equals a from-scratch evaluation of the same topology
+    warm = ev.evaluate(topo, leaves, keep=True)
+    cold = T.Evaluator(OracleEngine(cm, nthreads=2), cm).evaluate(topo, leaves)
+    assert (warm.adjusted, warm.unadjusted, warm.root) == (cold.adjusted, cold.unadjusted, cold.root)
+    assert warm.medians < cold.medians  # the build left its medians behind
+    # the last sweep, pair by pair: distance(new taxon, median across the edge) is minimal on the chosen edge
+    last = steps[-1]
+    assert last["delta"] >= 0
+
+
+@pytest.mark.gpu
+def test_wagner_gpu_matches_cpu_checker():
+    from oracle import oracle
+    from oracle_engine import OracleEngine
+    from poyd_b200 import synth
+
+    oracle.build(ref=True)
+    for cm in (CM.default_nucleotides(), CM.nucleotides(2, 1, 1)):
+        leaves = synth.taxa_on_random_tree(24, 400, seed=11, subst=0.05, indel=0.01)
+        g = T.GpuEngine(cm, device=0)
+        try:
+            evg = T.Evaluator(g, cm)
+            tg, sg = evg.wagner(leaves)
+            cg = evg.evaluate(tg, leaves, keep=True)
+        finally:
+            g.close()
+        evc = T.Evaluator(OracleEngine(cm, nthreads=8), cm)
+        tc, sc = evc.wagner(leaves)
+        cc = evc.evaluate(tc, leaves, keep=True)
+        assert sg == sc and tg.nodes == tc.nodes
+        assert (cg.adjusted, cg.unadjusted, cg.root) == (cc.adjusted, cc.unadjusted, cc.root)
+        for v in cc.singles:
+            assert all(np.array_equal(x, y) for x, y in zip(cg.singles[v], cc.singles[v]))
