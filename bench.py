@@ -48,6 +48,9 @@ WORKLOADS = {
     "protein300": ("configs[2] (3a): protein pairs 300 aa, 22x22 matrix 1/2, deltaw as the product computes it "
                    "(full matrix, SURVEY.md A15), align_2 + medians", 1, 10),
     "protein300_band16": ("configs[2] (3b): protein pairs 300 aa, explicit deltaw 16, align_2 + medians", 1, 10),
+    "tree": ("configs[4]-style host-driver workload (one GPU per tree): Wagner build with batched candidate-edge sweeps + "
+             "all-directions downpass, root selection, single assignment and adjusted cost (poyd_b200/tree.py) of a "
+             "synthetic --taxa x --bp DNA data set, affine gaps (1, 2, opening 3)", 3, 50),
 }
 
 
@@ -169,6 +172,93 @@ class ClockSampler:
         return out
 
 
+def bench_tree(args, rank, local_rank, world, threads):
+    """Secondary workload: the tree-level driver end to end (host buffers in every call).  One step = one Wagner build
+    + one full evaluation of the built tree; every rank works on its own data set (independent replicas)."""
+    from poyd_b200 import cost_matrix as CM, synth, tree as T
+
+    cm = CM.nucleotides(1, 2, 3)
+    leaves = synth.taxa_on_random_tree(args.taxa, args.bp, seed=5 + rank)
+
+    def one_pass(engine, lv):
+        ev = T.Evaluator(engine, cm)
+        engine.log.clear()
+        t0 = time.perf_counter()
+        topo, steps = ev.wagner(lv)
+        r = ev.evaluate(topo, lv, keep=True)
+        dt = time.perf_counter() - t0
+        return dt, r, T.logged_cells(engine.log, True), sum(len(x[1]) for x in engine.log), len(engine.log)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle
+        from oracle.tree_engine import OracleEngine
+
+        oracle.build(ref=True)
+        sub = {k: v for k, v in leaves.items() if k <= min(args.taxa, 60)}
+        dt, r, cells, npairs, ncalls = one_pass(OracleEngine(cm, nthreads=threads), sub)
+        v = cells / dt * 1e-9
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+                          "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "int32", "data": "synthetic",
+                          "config": {"workload": WORKLOADS["tree"][0], "taxa": len(sub), "bp": args.bp, "pairs": npairs,
+                                     "batches": ncalls, "adjusted_cost": r.adjusted},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                                           "sample": f"the first {len(sub)} taxa, same driver, CPU checker engine"},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = T.GpuEngine(cm, device=local_rank)
+    small = {k: v for k, v in leaves.items() if k <= min(args.taxa, 24)}
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_pass(eng, small)
+    l0 = eng.al.launch_count()
+    tot_dt, tot_cells = 0.0, 0
+    steps = max(1, min(args.steps, 2))
+    for _ in range(steps):
+        dt, r, cells, npairs, ncalls = one_pass(eng, leaves)
+        tot_dt += dt
+        tot_cells += cells
+    launches = eng.al.launch_count() - l0
+    t = torch.tensor([tot_dt / steps, float(tot_cells / steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sec, cells_all = float(tm[0]), float(t[1])
+    else:
+        sec, cells_all = float(t[0]), float(t[1])
+    if rank == 0:
+        v = cells_all / sec * 1e-9
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 2),
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOADS["tree"][0], "taxa": args.taxa, "bp": args.bp, "pairs": npairs, "batches": ncalls,
+                           "adjusted_cost": r.adjusted, "timing": "host wall clock around the driver (every call moves host "
+                           "buffers in and out); small batches, so latency- not roofline-bound"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+                "gpu_launches": int(launches)}
+        if not args.skip_cpu and world == 1:
+            from oracle import oracle
+            from oracle.tree_engine import OracleEngine
+
+            oracle.build(ref=True)
+            sub = {k: v_ for k, v_ in leaves.items() if k <= min(args.taxa, 60)}
+            dt, rc, cells, _, _ = one_pass(OracleEngine(cm, nthreads=threads), sub)
+            line["cpu_baseline"] = {"value": cells / dt * 1e-9, "unit": UNIT, "cores": threads, "kind": "reference",
+                                    "sample": f"the first {len(sub)} taxa, same driver, CPU checker engine, {dt:.1f} s"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bind_to_gpu_numa_node(local_rank: int) -> str:
     """Multi-rank runs: pin this process (and so its pinned host buffers, first touch) to the CPUs of the NUMA node its GPU
     hangs off, so the 8 ranks' host copies do not all cross one socket.  No-op where sysfs has no answer."""
@@ -202,6 +292,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--taxa", type=int, default=150, help="tree workload: taxa")
+    ap.add_argument("--bp", type=int, default=1500, help="tree workload: bases per taxon")
     ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS),
                     help="affine500 is the headline configuration; the others are reported in DESIGN.md")
     args = ap.parse_args()
@@ -210,6 +302,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = host_threads()
+
+    if args.workload == "tree":
+        return bench_tree(args, rank, local_rank, world, threads)
 
     if args.impl == "reference":
         # rank 0 alone runs the CPU arm; the other ranks exit without work

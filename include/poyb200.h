@@ -65,6 +65,12 @@ extern "C" {
 
 /* Flat image of the reference's `struct cm` (src/cm.h:32-46).  cost/median/worst have (1<<lcm)*(1<<lcm)
  * entries indexed (a << lcm) + b (src/cm.c:501-504); prepend_cost/tail_cost have 1<<lcm entries. */
+#define POYB200_WANT_CLOSEST 16u  /* instead of the median: the `median` rows receive what Sequence.Align.closest s1 s2
+                                     (src/sequence.ml:967-1033, s1 = operand a, s2 = operand b) builds from the aligned
+                                     pair -- get_closest column by column, gaps removed, a gap prepended --, its length in
+                                     out_len[4 p]; `cost` stays the alignment cost.  The caller handles the two early exits
+                                     of closest (empty s2; s1 = s2) itself.  Excludes POYB200_WANT_MEDIAN. */
+
 typedef struct poyb200_cm {
     int32_t a_sz, lcm, gap, cost_model_type, combinations, gap_open, is_metric, all_elements;
     const int32_t *cost;

@@ -1,5 +1,6 @@
-"""Test-only engine for poyd_b200.tree: the three batch calls answered by the CPU checker (oracle/), so the host
-driver can be pinned against the reference's tree-cost goldens without a GPU.  Never imported by the package."""
+"""Checker-side engine for poyd_b200.tree: the three batch calls answered by the CPU checker (compiled reference /
+port).  Test infrastructure like everything under oracle/: used by tests/ and by bench.py's cpu_baseline leg only, never
+imported by the package."""
 import numpy as np
 
 from oracle import oracle
@@ -13,6 +14,7 @@ class OracleEngine:
         self.nthreads = nthreads
         self.calls = 0
         self.pairs = 0
+        self.log = []
 
     def close(self):
         pass
@@ -32,6 +34,7 @@ class OracleEngine:
         self.calls += 1
         self.pairs += len(pp)
         dw = None if self.cm.cost_model_type == 1 else self._deltaw(pool, pp, hint)
+        self.log.append((str(mode), pool.len[pp[:, 0]].copy(), pool.len[pp[:, 1]].copy(), dw))
         return self.chk.batch(mode, pool.pool, pool.off, pool.len, pp, deltaw=dw, nthreads=self.nthreads)
 
     def median(self, store, pairs):

@@ -318,7 +318,7 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
     ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
     ctx->dcm = DevCM{cm->a_sz, cm->lcm, cm->gap, cm->cost_model_type, cm->combinations, cm->gap_open,
-                     ctx->d_cost.p, ctx->d_median.p, ctx->d_prepend.p, ctx->d_tail.p};
+                     ctx->d_cost.p, ctx->d_median.p, ctx->d_prepend.p, ctx->d_tail.p, cm->all_elements};
     ctx->has_cm = true;
     return POYB200_OK;
 }
@@ -514,7 +514,10 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         k_and &= pt.klass_and;
     }
     if (bt && b->n_pairs > 0) {
-        if ((b->want & POYB200_WANT_MEDIAN) && !b->median) return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN without buffer");
+        if ((b->want & (POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST)) && !b->median)
+            return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN / WANT_CLOSEST without the median buffer");
+        if ((b->want & POYB200_WANT_MEDIAN) && (b->want & POYB200_WANT_CLOSEST))
+            return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN and WANT_CLOSEST share the median rows: ask for one");
         if ((b->want & POYB200_WANT_MEDIANWG) && !b->medianwg) return fail(ctx, POYB200_EINVAL, "WANT_MEDIANWG without buffer");
         if ((b->want & POYB200_WANT_ALIGNED) && (!b->aligned_a || !b->aligned_b))
             return fail(ctx, POYB200_EINVAL, "WANT_ALIGNED without buffers");
@@ -629,7 +632,7 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
         if (ctx->overlap_tb && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
         CK(ctx->d_outlen.reserve(4 * n + 4));
         const size_t ob = n * (size_t) ctx->dstride + 16;
-        if (b->want & POYB200_WANT_MEDIAN) CK(ctx->d_out[0].reserve(ob));
+        if (b->want & (POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST)) CK(ctx->d_out[0].reserve(ob));
         if (b->want & POYB200_WANT_MEDIANWG) CK(ctx->d_out[1].reserve(ob));
         if (b->want & POYB200_WANT_ALIGNED) {
             CK(ctx->d_out[2].reserve(ob));
@@ -775,7 +778,7 @@ static int fetch_range(poyb200_ctx *ctx, size_t lo, size_t hi, cudaStream_t st, 
         if (!lens_known)
             CK(cudaMemcpyAsync(b.out_len + 4 * lo, ctx->d_outlen.p + 4 * lo, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
         uint8_t *dst[4] = {b.median, b.medianwg, b.aligned_a, b.aligned_b};
-        const uint32_t need[4] = {POYB200_WANT_MEDIAN, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
+        const uint32_t need[4] = {POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST, POYB200_WANT_MEDIANWG, POYB200_WANT_ALIGNED, POYB200_WANT_ALIGNED};
         // right-aligned device rows -> right-aligned caller rows
         const size_t wfull = (size_t) std::min<long long>(ctx->dstride, b.out_stride);
         int wmax[4] = {0, 0, 0, 0};

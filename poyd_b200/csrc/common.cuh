@@ -80,6 +80,7 @@ struct DevCM {
     const int *cost;
     const uint8_t *median;
     const int *prepend, *tail;
+    int all_elements;
 };
 
 struct OutPtrs {
@@ -94,5 +95,24 @@ struct OutPtrs {
 
 __device__ __forceinline__ int cm_cost(const DevCM &c, int a, int b) { return __ldg(c.cost + (a << c.lcm) + b); }
 __device__ __forceinline__ int cm_median(const DevCM &c, int a, int b) { return __ldg(c.median + (a << c.lcm) + b); }
+
+// One column of Sequence.Align.closest (src/sequence.ml:986-1018): a = element of the aligned s1 (the parent), b = element
+// of the aligned s2.  Combination alphabets: Cost_matrix.Two_D.get_closest (src/cost_matrix.ml:681-700) -- b loses its gap
+// bit (or collapses to the gap when both carry it), then the lowest set bit of b with the strictly smallest cost a x wins.
+// Other alphabets: b, unless it is the `all` code, then a (or 1 when a is `all` too).
+__device__ __forceinline__ int closest_elem(const DevCM &c, int a, int b) {
+    if (!c.combinations) return (b == c.all_elements) ? ((a == c.all_elements) ? 1 : a) : b;
+    const int gap = c.gap;
+    if (a != gap && b != gap) b = ((a & gap) && (b & gap)) ? gap : (b & ~gap);
+    int best = a, cur = 0x7fffffff;
+    for (int bit = 0; bit < c.lcm; bit++) {
+        const int x = 1 << bit;
+        if (b & x) {
+            const int nc = cm_cost(c, a, x);
+            if (nc < cur) { best = x; cur = nc; }
+        }
+    }
+    return best;
+}
 
 }  // namespace poyb200

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     const uint8_t *dbase = dir + t.dir_off;
     const int dcap = (int) out.stride;
     const size_t row = (size_t) t.pair * out.stride;
-    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
+    const bool w_clo = out.want & 16;
+    const bool w_med = (out.want & 1) && !w_clo, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
     RevWriter med, wg, ri, rj;
     RevBitWriter bi, bj, bw;
     {
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
         bj.init((rows_b_ ? out.bits_a : out.bits_b) + brow, (int) out.bstride * 8);
         bw.init(out.bits_wg + brow, (int) out.bstride * 8);
     }
-    med.init(out.median + (w_med ? row : 0), dcap);
+    med.init(out.median + ((w_med || w_clo) ? row : 0), dcap);
     wg.init(out.medianwg + (w_wg ? row : 0), dcap);
     // resi belongs to the row sequence; rows may be the caller's operand b (algn.c:2606-2616)
     const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
@@ -83,12 +84,14 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     rj.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
     int i = t.lr - 1, j = t.lc - 1;
     int ic = si[i], jc = sj[j];
-    int nmed = 0, nwg = 0, nres = 0, med_first = -1;
+    int nmed = 0, nwg = 0, nres = 0, med_first = -1, nclo = 0;
     enum { M_TODO, M_VERT, M_HORI, M_DIAG, M_ALGN };
     int mode = M_TODO;
 #define PUT_MED(v) do { nmed++; med_first = (v); if (w_med) med.put(v); } while (0)
 #define PUT_WG(v) do { nwg++; if (w_wg) wg.put(v); if (w_bits) bw.put((v) != TMPGAP); } while (0)
-#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } if (w_bits) { bi.put((a) != TMPGAP); bj.put((b) != TMPGAP); } } while (0)
+#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } if (w_bits) { bi.put((a) != TMPGAP); bj.put((b) != TMPGAP); } \
+        if (w_clo) { const int sel_ = rows_b ? closest_elem(cm, (b), (a)) : closest_elem(cm, (a), (b)); \
+                     if (sel_ != TMPGAP) { nclo++; med.put(sel_); } } } while (0)
     while (i != 0 && j != 0) {
         const int d = j - i;
         int b;
@@ -146,12 +149,13 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
 #undef PUT_MED
 #undef PUT_WG
 #undef PUT_RES
-    if (w_med) med.flush();
+    if (w_clo) { med.put(TMPGAP); nclo++; }  // `prepend res gap`, src/sequence.ml:980
+    if (w_med || w_clo) med.flush();
     if (w_wg) wg.flush();
     if (w_al) { ri.flush(); rj.flush(); }
     if (w_bits) { bi.flush(); bj.flush(); bw.flush(); }
     int *ol = out.out_len + 4 * (size_t) t.pair;
-    ol[0] = nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
+    ol[0] = w_clo ? nclo : nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
     }
     __syncwarp();
   }
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     const uint8_t *dbase = dir + t.dir_off;
     const int dcap = (int) out.stride, gap = cm.gap;
     const size_t row = (size_t) t.pair * out.stride;
-    const bool w_med = out.want & 1, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
+    const bool w_clo = out.want & 16;
+    const bool w_med = (out.want & 1) || w_clo, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
     const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
     const bool swaped = (t.flags & TF_SWAPED) != 0;
     RevWriter med, wg, r1, r2;
@@ -213,7 +218,10 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
         const int mm = cm_median(cm, ea, eb);
         if (w_wg) wg.put(mm);
         if (w_bits) { b1.put(x != gap); b2.put(y != gap); bw.put(mm != gap); }
-        if (mm != gap) { nmed++; if (w_med) med.put(mm); }
+        if (w_clo) {
+            const int sel = closest_elem(cm, ea, eb);
+            if (sel != gap) { nmed++; med.put(sel); }
+        } else if (mm != gap) { nmed++; if (w_med) med.put(mm); }
     }
     nmed++;
     if (w_med) { med.put(gap); med.flush(); }

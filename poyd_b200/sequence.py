@@ -27,7 +27,7 @@ import numpy as np
 from . import _lib
 from .cost_matrix import CostMatrix
 
-WANT_MEDIAN, WANT_MEDIANWG, WANT_ALIGNED, WANT_BITSETS = 1, 2, 4, 8
+WANT_MEDIAN, WANT_MEDIANWG, WANT_ALIGNED, WANT_BITSETS, WANT_CLOSEST = 1, 2, 4, 8, 16
 MODE_COST_2, MODE_ALIGN_2, MODE_COST_AFFINE_3, MODE_ALIGN_AFFINE_3 = 0, 1, 2, 3
 
 
@@ -201,7 +201,7 @@ class Align:
             stride = (stride + 15) // 16 * 16
             res.lens = np.zeros((n, 4), np.int32)
             b.out_len, b.out_stride = res.lens.ctypes.data, stride
-            if want & WANT_MEDIAN:
+            if want & (WANT_MEDIAN | WANT_CLOSEST):
                 res.median = np.zeros((n, stride), np.uint8)
                 b.median = res.median.ctypes.data
             if want & WANT_MEDIANWG:
@@ -248,6 +248,45 @@ class Align:
         b, res = self.make_batch(pool, pairs, deltaw=dw, swaped=swaped, want=want)
         self._check(self.L.poyb200_batch_align_2(self.h, C.byref(b)))
         return res
+
+    def closest(self, pool: SeqPool, pairs) -> List[np.ndarray]:
+        """``Sequence.Align.closest s1 s2 cm m`` (src/sequence.ml:967-1033) for every pair (s1 = pair[0], s2 = pair[1]):
+        the sequence of s2's elements closest to s1's along their alignment, gaps removed.  The alignment, the
+        column rule (``Cost_matrix.Two_D.get_closest``) and the compaction run in the traceback kernel
+        (POYB200_WANT_CLOSEST); the two early exits -- empty s2, s1 = s2 -- are decided here."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        gap = self.cm.gap
+        out: List[Optional[np.ndarray]] = [None] * len(pairs)
+        todo = []
+        for k, (i, j) in enumerate(pairs):
+            s1, s2 = pool.seq(int(i)), pool.seq(int(j))
+            if np.all(s2 == gap):  # is_empty s2: (s2, 0)
+                out[k] = s2.copy()
+            elif self.cm.combine() and len(s1) == len(s2) and np.array_equal(s1, s2):
+                v = s2.copy()  # :1000-1009: gap bits cleared past the first element, get_closest of x with itself
+                v[1:] &= np.uint8(~gap & 0xFF)
+                one = np.array([self._closest_same(int(x)) for x in v], np.uint8)
+                out[k] = np.concatenate([[gap], one[one != gap]]).astype(np.uint8)
+            else:
+                todo.append(k)
+        if todo:
+            r = self.align_2(pool, pairs[todo], WANT_CLOSEST)
+            for q, k in enumerate(todo):
+                out[k] = r.get("median", q).copy()
+        return out  # type: ignore[return-value]
+
+    def _closest_same(self, x: int) -> int:
+        """get_closest cm x x for one element (src/cost_matrix.ml:681-700)."""
+        gap, b = self.cm.gap, x
+        if x != gap:
+            b = gap if (x & gap) else (x & ~gap)
+        best, cur = x, None
+        for bit in range(self.cm.lcm):
+            if b & (1 << bit):
+                nc = int(self.cm.cost[x, 1 << bit])
+                if cur is None or nc < cur:
+                    best, cur = 1 << bit, nc
+        return best
 
     def _median(self, which: int, a: np.ndarray, b: np.ndarray, lens: np.ndarray):
         a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)

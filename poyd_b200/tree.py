@@ -183,9 +183,15 @@ class GpuEngine:
         self.al = S.Align(cm, device=device)
         self.calls = 0
         self.pairs = 0
+        self.log: List[Tuple[str, np.ndarray, np.ndarray, Optional[np.ndarray]]] = []  # (kind, len a, len b, deltaw)
 
     def close(self) -> None:
         self.al.close()
+
+    def _note(self, kind: str, pool, pp, dw=None) -> None:
+        self.calls += 1
+        self.pairs += len(pp)
+        self.log.append((kind, pool.len[pp[:, 0]].copy(), pool.len[pp[:, 1]].copy(), None if dw is None else np.asarray(dw).copy()))
 
     @staticmethod
     def _pool(store: _Seq[np.ndarray], pairs: np.ndarray):
@@ -196,26 +202,46 @@ class GpuEngine:
         """``SeqCS.DOS.median`` for every pair: (cost, median)."""
         pool, pp = self._pool(store, pairs)
         r = self.al.align_2(pool, pp, S.WANT_MEDIAN)
-        self.calls += 1
-        self.pairs += len(pp)
+        self._note("median", pool, pp, None if self.al.is_affine else self.al.deltaw_for(pool, pp))
         return r.cost, [r.get("median", p).copy() for p in range(len(pp))]
 
     def align(self, store, pairs):
         """``Sequence.Align.align_2`` for every pair: the two aligned sequences."""
         pool, pp = self._pool(store, pairs)
         r = self.al.align_2(pool, pp, S.WANT_ALIGNED)
-        self.calls += 1
-        self.pairs += len(pp)
+        self._note("align", pool, pp, None if self.al.is_affine else self.al.deltaw_for(pool, pp))
         return [(r.get("aligned_a", p).copy(), r.get("aligned_b", p).copy()) for p in range(len(pp))]
+
+    def closest(self, store, pairs):
+        """``Sequence.Align.closest parent mine`` for every pair, fused into the traceback kernel."""
+        pool, pp = self._pool(store, pairs)
+        self._note("closest", pool, pp, None if self.al.is_affine else self.al.deltaw_for(pool, pp))
+        return self.al.closest(pool, pp)
 
     def distance(self, store, pairs):
         """``SeqCS.DOS.distance`` (src/seqCS.ml:856-866): ``cost_2 ~deltaw:(max 8 |la - lb|)``."""
         pool, pp = self._pool(store, pairs)
         la, lb = pool.len[pp[:, 0]].astype(np.int64), pool.len[pp[:, 1]].astype(np.int64)
         hint = np.maximum(np.abs(la - lb), 8)
-        self.calls += 1
-        self.pairs += len(pp)
+        self._note("distance", pool, pp, None if self.al.is_affine else self.al.deltaw_for(pool, pp, hint))
         return self.al.cost_2(pool, pp, deltaw=hint)
+
+
+def logged_cells(log, affine: bool) -> int:
+    """DP cells the reference visits for the calls an engine logged, counted after the fact."""
+    total = 0
+    for _, la, lb, dw in log:
+        la, lb = la.astype(np.int64), lb.astype(np.int64)
+        if affine:
+            key = la * 65536 + lb
+            u, cnt = np.unique(key, return_counts=True)
+            total += sum(S.cells_affine(int(k) >> 16, int(k) & 65535) * int(c) for k, c in zip(u, cnt))
+        else:
+            l1, l2 = np.maximum(la, lb), np.minimum(la, lb)
+            key = (l1 * 65536 + l2) * 65536 + dw.astype(np.int64)
+            u, cnt = np.unique(key, return_counts=True)
+            total += sum(S.cells_linear(int(k) >> 32, (int(k) >> 16) & 65535, int(k) & 65535) * int(c) for k, c in zip(u, cnt))
+    return int(total)
 
 
 # ---- Cost_matrix.Two_D.get_closest as a table ------------------------------------------------------------------------
@@ -278,9 +304,9 @@ class Evaluator:
         out: List[Optional[Tuple[int, int]]] = [None] * len(jobs)
         todo, where = [], []
         for k, (a, b) in enumerate(jobs):
-            if _is_empty(store[a], self.gap):
+            if self._emp(a):
                 out[k] = (b, 0)
-            elif _is_empty(store[b], self.gap):
+            elif self._emp(b):
                 out[k] = (a, 0)
             else:
                 todo.append((a, b))
@@ -300,7 +326,7 @@ class Evaluator:
         pre: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
         for k, (p, m) in enumerate(jobs):
             s1, s2 = store[p], store[m]
-            if _is_empty(s2, gap):
+            if self._emp(m):
                 out[k] = m
             elif self._closest is not None and len(s1) == len(s2) and np.array_equal(s1, s2):
                 mask = np.uint8(~gap & 0xFF)
@@ -311,7 +337,11 @@ class Evaluator:
             else:
                 todo.append((p, m))
                 where.append(k)
-        if todo:
+        if todo and hasattr(self.e, "closest"):  # the fused kernel (GpuEngine)
+            for k, res in zip(where, self.e.closest(store, np.array(todo, np.int32))):
+                store.append(res)
+                out[k] = len(store) - 1
+        elif todo:  # engines that only align: the column rule is applied here
             al = self.e.align(store, np.array(todo, np.int32))
             for k, ab in zip(where, al):
                 pre[k] = ab
@@ -337,6 +367,14 @@ class Evaluator:
         self._leafsig: Dict[int, int] = {}
         self.n_medians = 0
         self._next_sig = 0
+        self._empty: Dict[int, bool] = {}
+
+    def _emp(self, i: int) -> bool:
+        """Sequence.is_empty of store[i], remembered (the store only grows)."""
+        e = self._empty.get(i)
+        if e is None:
+            e = self._empty[i] = _is_empty(self.store[i], self.gap)
+        return e
 
     def _new_sig(self) -> int:
         self._next_sig += 1
@@ -483,7 +521,7 @@ class Evaluator:
         for (p, v) in edges:
             for l in range(n_loci):
                 s1, s2 = store[singles[p][l]], store[singles[v][l]]
-                if not (_is_empty(s1, self.gap) or _is_empty(s2, self.gap)):  # else missing_distance = 0
+                if not (self._emp(singles[p][l]) or self._emp(singles[v][l])):  # else missing_distance = 0
                     jobs.append((singles[p][l], singles[v][l]))
         adjusted = int(self.e.distance(store, np.array(jobs, np.int32)).astype(np.int64).sum()) if jobs else 0
         return TreeCost(adjusted=adjusted, unadjusted=int(best), root=root,
@@ -517,7 +555,7 @@ class Evaluator:
             for k, e in enumerate(edges):
                 for l in range(n_loci):
                     m = E[e][0][l]
-                    if not (_is_empty(self.store[cl[l]], self.gap) or _is_empty(self.store[m], self.gap)):
+                    if not (self._emp(cl[l]) or self._emp(m)):
                         jobs.append((cl[l], m))
                         owner.append(k)
             delta = np.zeros(len(edges), np.int64)
@@ -536,7 +574,7 @@ class Evaluator:
 
     def _nonempty_parent(self, store, parent: int, mine: int) -> int:
         # DOS.to_single (src/seqCS.ml:734-739): an empty parent is replaced by the vertex's own sequence
-        return mine if _is_empty(store[parent], self.gap) else parent
+        return mine if self._emp(parent) else parent
 
 
 def tree_cost(engine, cm: CostMatrix, fasta: str, tree_file: str, which: int = 0) -> TreeCost:

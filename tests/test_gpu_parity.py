@@ -497,3 +497,40 @@ def test_dos_median_payload_bitsets(S, checker_factory, affine):
         for p in range(0, len(pairs), 7):
             assert np.array_equal(g2.bitset("a", p), g.bitset("a", p)) and np.array_equal(g2.bitset("wg", p), g.bitset("wg", p))
         al.close()
+
+
+@pytest.mark.parametrize("kind", ["affine", "linear", "protein"])
+def test_closest_fused_kernel(S, checker_factory, kind):
+    """Sequence.Align.closest (src/sequence.ml:967-1033) fused into the traceback (POYB200_WANT_CLOSEST) against the
+    column rule applied to the checker's aligned pair: get_closest as a table for DNA (tree.closest_table, a restatement
+    of src/cost_matrix.ml:681-700), the `all`-code rule for protein (:986-997)."""
+    from poyd_b200 import cost_matrix as CM, synth, tree as T
+
+    cm = {"affine": CM.nucleotides(1, 2, 3), "linear": CM.default_nucleotides(), "protein": CM.default_aminoacids()}[kind]
+    alphabet = "protein" if kind == "protein" else "dna"
+    pool, pairs = synth.ragged_batch(1200, max_len=240, seed=51, alphabet=alphabet, gap_ambiguity=0.0 if kind == "protein" else 0.06)
+    pairs = np.concatenate([pairs, np.stack([pairs[:40, 0], pairs[:40, 0]], axis=1)])  # s1 = s2 early exit
+    al = S.Align(cm)
+    got = al.closest(pool, pairs)
+    chk = checker_factory(cm)
+    mode = 3 if kind == "affine" else 1
+    o = chk.batch(mode, pool.pool, pool.off, pool.len, pairs, deltaw=None if kind == "affine" else al.deltaw_for(pool, pairs))
+    tab = T.closest_table(cm) if cm.combine() else None
+    for p, (i, j) in enumerate(pairs):
+        s1, s2 = pool.seq(int(i)), pool.seq(int(j))
+        if np.all(s2 == cm.gap):
+            want = s2
+        else:
+            n = int(o["lens"][p, 2])
+            a1, b1 = o["ra"][p, :n], o["rb"][p, :n]
+            if tab is not None and len(s1) == len(s2) and np.array_equal(s1, s2):
+                a1 = s1.copy()
+                a1[1:] &= np.uint8(~cm.gap & 0xFF)
+                b1 = a1
+            if tab is not None:
+                sel = tab[a1, b1]
+            else:
+                sel = np.where(b1 == cm.all_elements, np.where(a1 == cm.all_elements, 1, a1), b1).astype(np.uint8)
+            want = np.concatenate([[cm.gap], sel[sel != cm.gap]]).astype(np.uint8)
+        assert np.array_equal(got[p], want), f"{kind} pair {p}"
+    al.close()

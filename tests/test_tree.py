@@ -52,7 +52,7 @@ def test_closest_table_rules():
 
 @pytest.mark.parametrize("k", range(REGIMES))
 def test_reference_tree_costs_cpu_checker(tmp_path, k, checker_factory):
-    from oracle_engine import OracleEngine
+    from oracle.tree_engine import OracleEngine
 
     cm = _cm(k)
     eng = OracleEngine(cm, nthreads=4)
@@ -89,7 +89,7 @@ def _newick(topo):
 
 @pytest.mark.parametrize("affine", [False, True])
 def test_wagner_sweep_and_cache_cpu_checker(affine, checker_factory):
-    from oracle_engine import OracleEngine
+    from oracle.tree_engine import OracleEngine
     from poyd_b200 import synth
 
     cm = CM.nucleotides(2, 1, 1) if affine else CM.default_nucleotides()
@@ -114,7 +114,7 @@ def test_wagner_sweep_and_cache_cpu_checker(affine, checker_factory):
 @pytest.mark.gpu
 def test_wagner_gpu_matches_cpu_checker():
     from oracle import oracle
-    from oracle_engine import OracleEngine
+    from oracle.tree_engine import OracleEngine
     from poyd_b200 import synth
 
     oracle.build(ref=True)
