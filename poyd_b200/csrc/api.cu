@@ -685,13 +685,17 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         const int nt = (int) (ch.end - ch.begin);
         // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
         // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
-        const int blocks = std::min((nt + 127) / 128, ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128));
+        const int max_blocks = ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128);
+        // walkers per warp: 32 when the batch fills the grid, fewer (down to 1) when it does not
+        int wpw = (nt + max_blocks * 4 - 1) / (max_blocks * 4);
+        wpw = std::min(32, std::max(1, wpw));
+        const int blocks = std::min((nt + 4 * wpw - 1) / (4 * wpw), max_blocks);
         if (affine)
             aff_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                           next_counter(ctx));
+                                                           next_counter(ctx), wpw);
         else
             lin_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                           next_counter(ctx));
+                                                           next_counter(ctx), wpw);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));

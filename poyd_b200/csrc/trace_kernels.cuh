@@ -48,18 +48,25 @@ struct RevBitWriter {
     }
 };
 
+// A walk is a chain of dependent loads; the direction line it will need two tiles (8 diagonal moves) further on is
+// requested early so that the common case -- a run of matches along one diagonal -- finds it in L1.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // backtrace_affine (src/algn.c:1983-2097).  dcap = device row stride (multiple of 16).
 __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
-                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter) {
-  // walkers take pairs from a shared counter, a warp's worth at a time: no wave-quantisation tail
+                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter,
+                                                            int wpw) {
+  // walkers take pairs from a shared counter, `wpw` per warp at a time: no wave-quantisation tail.  Large batches run 32
+  // walkers per warp (throughput); small ones spread over more warps with fewer walkers each, because the walkers of a
+  // warp diverge (five modes, different moves) and a lone walker steps several times faster than one of 32.
   for (;;) {
     int base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, 32);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, wpw);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= ntasks) break;
     const int ti = base + (threadIdx.x & 31);
-    if (ti < ntasks) {
+    if ((int) (threadIdx.x & 31) < wpw && ti < ntasks) {
     const Task t = tasks[ti];
     const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;
@@ -84,6 +91,10 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     rj.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
     int i = t.lr - 1, j = t.lc - 1;
     int ic = si[i], jc = sj[j];
+    const uint64_t tile_bytes = (uint64_t) t.G * 8 * t.BL;
+    // dd / twoK == (dd * recip) >> 16 for dd < 16384: twoK is 8..16 for the stripe kernels (stripes <= 512 diagonals) and
+    // 0xFFFF for the generic ones, where the quotient is 0 for every dd the 16384-element cap allows
+    const uint32_t recip = (65536u + t.twoK - 1) / t.twoK;
     int nmed = 0, nwg = 0, nres = 0, med_first = -1, nclo = 0;
     enum { M_TODO, M_VERT, M_HORI, M_DIAG, M_ALGN };
     int mode = M_TODO;
@@ -97,11 +108,21 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
         int b;
         if (d < t.dlo) b = AFF_LEFT_EDGE_BYTE;
         else if (d > t.dhi) b = AFF_RIGHT_EDGE_BYTE;
-        else b = __ldg(dbase + dir_index(t, i, j));
+        else {
+            // dir_index with the division by twoK done as a multiplication (dd < 16384, see recip)
+            const uint32_t dd = (uint32_t) (d - t.dbase), T = (uint32_t) (i + j - t.tshift);
+            const uint32_t lane = (dd * recip) >> 16, m = (dd - lane * t.twoK) >> 1;
+            const uint64_t idx = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
+            b = __ldg(dbase + idx);
+            if (idx >= 2 * tile_bytes) prefetch_l1(dbase + idx - 2 * tile_bytes);
+        }
+        // the reference spends one iteration on m_todo and re-reads the same cell in the next one (:2003-2013):
+        // same cell, same byte, so the mode is resolved and carried out in one pass
         if (mode == M_TODO) {
             const int m = (b >> 2) & 3;
             mode = (m == AM_H) ? M_HORI : (m == AM_A) ? M_ALGN : (m == AM_V) ? M_VERT : M_DIAG;
-        } else if (mode == M_VERT) {
+        }
+        if (mode == M_VERT) {
             if (b & AB_ENDV) mode = M_TODO;
             if (!(ic & TMPGAP)) { PUT_MED(ic | TMPGAP); PUT_WG(ic | TMPGAP); } else PUT_WG(TMPGAP);
             PUT_RES(ic, TMPGAP);
@@ -166,15 +187,18 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
 // algn_get_median_2d_with_gaps (:4024-4035) -- what SeqCS.DOS.median asks for (src/seqCS.ml:757-766).
 __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                             const uint8_t *__restrict__ pool,
-                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter) {
-  // walkers take pairs from a shared counter, a warp's worth at a time: no wave-quantisation tail
+                                                            const uint8_t *__restrict__ dir, OutPtrs out, int *work_counter,
+                                                            int wpw) {
+  // walkers take pairs from a shared counter, `wpw` per warp at a time: no wave-quantisation tail.  Large batches run 32
+  // walkers per warp (throughput); small ones spread over more warps with fewer walkers each, because the walkers of a
+  // warp diverge (five modes, different moves) and a lone walker steps several times faster than one of 32.
   for (;;) {
     int base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, 32);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(work_counter, wpw);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= ntasks) break;
     const int ti = base + (threadIdx.x & 31);
-    if (ti < ntasks) {
+    if ((int) (threadIdx.x & 31) < wpw && ti < ntasks) {
     const Task t = tasks[ti];
     const uint8_t *s1 = pool + t.off_r, *s2 = pool + t.off_c;
     const uint8_t *dbase = dir + t.dir_off;

@@ -74,9 +74,17 @@ class SeqPool:
     def count(self, gap: int) -> np.ndarray:
         """``Sequence.count gap s`` = seq_CAML_count (src/seq.c:570-582) for every sequence: the number of
         elements with ``code land gap <> 0`` (a bitwise test even for sequential alphabets)."""
-        hit = (self.pool & np.uint8(gap)) != 0
-        cs = np.concatenate([[0], np.cumsum(hit, dtype=np.int64)])
-        return (cs[self.off + self.len] - cs[self.off]).astype(np.int32)
+        cache = self.__dict__.setdefault("_count_cache", {})
+        if gap not in cache:
+            hit = (self.pool & np.uint8(gap)) != 0
+            off = np.asarray(self.off, np.int64)
+            if len(off) and np.all(off[1:] >= off[:-1] + self.len[:-1]):
+                # ordered, non-overlapping pool (what this class builds; padding bytes are 0 and never hit): one pass
+                cache[gap] = np.add.reduceat(hit, off, dtype=np.int32).astype(np.int32) * (self.len > 0)
+            else:
+                cs = np.concatenate([[0], np.cumsum(hit, dtype=np.int64)])
+                cache[gap] = (cs[off + self.len] - cs[off]).astype(np.int32)
+        return cache[gap]
 
 
 @dataclass
