@@ -114,13 +114,13 @@ struct poyb200_ctx {
     int host_threads = 8;
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
     bool in_order = true;           // tasks[k].pair == k
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
     DevBuf<uint8_t> d_dir2;        // second direction buffer: traceback of chunk k overlaps the fill of chunk k+1
     uint8_t *cur_dir = nullptr;
     bool overlap_tb = true;        // POYB200_OVERLAP_TB=0: fill and traceback strictly serial on one stream
     std::vector<cudaEvent_t> ev_fill, ev_tb;
     cudaEvent_t ev_in = nullptr;
-    std::vector<cudaEvent_t> ev_done;
+    std::vector<cudaEvent_t> ev_done, ev_pool;
     bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
     // 3-D
     bool has_cm3 = false;
@@ -238,7 +238,18 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&ctx->s_tb, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_len, cudaStreamNonBlocking);
+    {
+        // The traceback stream outranks the compute stream: when a fill ends, the walkers of its chunk are placed before the
+        // CTAs of the next (persistent, SM-filling) fill, instead of waiting for that fill to drain.  POYB200_TB_PRIORITY=0
+        // switches it off.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char *pe = getenv("POYB200_TB_PRIORITY");
+        const bool want = !pe || atoi(pe) != 0;
+        if (cudaStreamCreateWithPriority(&ctx->s_tb, cudaStreamNonBlocking, want ? hi : lo) != cudaSuccess)
+            cudaStreamCreateWithFlags(&ctx->s_tb, cudaStreamNonBlocking);
+    }
     cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
     ctx->host_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     size_t free_b = 0, total_b = 0;
@@ -272,9 +283,11 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->chunk_ev) cudaEventDestroy(e);
     for (auto &e : ctx->ev_done) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_len) cudaStreamDestroy(ctx->s_len);
     if (ctx->s_tb) cudaStreamDestroy(ctx->s_tb);
     for (auto &e : ctx->ev_fill) cudaEventDestroy(e);
     for (auto &e : ctx->ev_tb) cudaEventDestroy(e);
@@ -570,13 +583,43 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         }
         if (ntasks > begin) ctx->chunks.push_back(Chunk{begin, ntasks, off});
     }
-    // Taper: the results of the last chunk cannot overlap any compute, so cut it into quarters.
-    if (bt && ctx->chunks.size() >= 2) {
-        const Chunk last = ctx->chunks.back();
-        const size_t len = last.end - last.begin;
-        if (len >= 4096) {
+    // Taper: the results of the last chunk cannot overlap any compute, and where the download runs about as fast as the
+    // kernels (all four sequences: 6.4 ms against 7 ms per 131 072 pairs) nothing of it can be hidden later either.  The last
+    // ~1.5 chunks are therefore re-cut into pieces that shrink towards the end (..., 65 536, 32 768, 16 384, 16 384), so that
+    // what is still to be downloaded when the last kernel ends is one small piece.
+    if (bt && !over && ctx->chunks.size() >= 2) {  // (chunks cut by the band budget are left alone)
+        size_t begin = ctx->chunks.back().begin;
+        ctx->chunks.pop_back();
+        while (ctx->chunks.size() >= 2 && ntasks - begin < CP + CP / 2) {
+            begin = ctx->chunks.back().begin;
             ctx->chunks.pop_back();
-            for (int q = 0; q < 4; q++) ctx->chunks.push_back(Chunk{last.begin + len * q / 4, last.begin + len * (q + 1) / 4, 0});
+        }
+        std::vector<Chunk> tail;
+        size_t end = ntasks;
+        const size_t piece[4] = {16384, 16384, 32768, 65536};
+        for (int q = 0; q < 4 && end - begin >= 2 * piece[q]; q++) {
+            tail.push_back(Chunk{end - piece[q], end, 0});
+            end -= piece[q];
+        }
+        while (end > begin) {
+            const size_t len = std::min(CP, end - begin);
+            tail.push_back(Chunk{end - len, end, 0});
+            end -= len;
+        }
+        for (size_t k = tail.size(); k-- > 0;) ctx->chunks.push_back(tail[k]);
+    }
+    // ... and the first chunk likewise (1/8, 1/8, 1/4, 1/2): nothing can be downloaded before the first chunk is traced back,
+    // and where the download is the longer leg (all four sequences) every millisecond it starts earlier is a millisecond
+    // off the call
+    if (bt && ctx->chunks.size() >= 2) {
+        const Chunk first = ctx->chunks.front();
+        const size_t len = first.end - first.begin;
+        if (len >= 8192) {
+            const size_t cut[5] = {0, len / 8, len / 4, len / 2, len};
+            std::vector<Chunk> head;
+            for (int q = 0; q < 4; q++) head.push_back(Chunk{first.begin + cut[q], first.begin + cut[q + 1], 0});
+            ctx->chunks.erase(ctx->chunks.begin());
+            ctx->chunks.insert(ctx->chunks.begin(), head.begin(), head.end());
         }
     }
     // 2. per chunk, in parallel: stable grouping by class (counting sort into the second array) and band layout
@@ -840,23 +883,53 @@ static double now_ms() {
 static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     static const bool trace = getenv("POYB200_TRACE") != nullptr;
     const double t0 = now_ms();
+    if (!ctx || !b) return POYB200_EINVAL;
+    // The pool does not depend on the plan: its first slices travel while the (multi-threaded, ~5.5 ns per pair) planner runs,
+    // so the first chunk finds its operands on the device when the plan is ready.  Only as many slices as the planner's
+    // run time covers (~290 bytes per pair at the link's 52 GB/s) go early: copies queue FIFO on the copy engine and the task
+    // array, which the plan produces, must not wait behind the whole pool (measured: +21 ms on 1 M pairs when it did).
+    constexpr size_t SLICE = (size_t) 32 << 20;
+    const size_t nslices = (b->pool && b->n_pairs > 0) ? (b->pool_bytes + SLICE - 1) / SLICE : 0;
+    const size_t nearly = std::min(nslices, ((size_t) std::max(b->n_pairs, 0) * 290 + SLICE - 1) / SLICE);
+    cudaSetDevice(ctx->device);
+    auto upload_slices = [&](size_t k0, size_t k1) -> int {
+        for (size_t k = k0; k < k1; k++) {
+            const size_t lo = k * SLICE, len = std::min(SLICE, b->pool_bytes - lo);
+            CK(cudaMemcpyAsync(ctx->d_pool.p + lo, b->pool + lo, len, cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaEventRecord(ctx->ev_pool[k], ctx->s_in));
+        }
+        return POYB200_OK;
+    };
+    if (nslices) {
+        CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+        while (ctx->ev_pool.size() < nslices) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_pool.push_back(e);
+        }
+        if (int urc = upload_slices(0, nearly)) return urc;
+    }
     int rc = stage_impl(ctx, mode, b, false);
-    if (rc) return rc;
+    if (rc) {
+        cudaStreamSynchronize(ctx->s_in);  // the caller may release its pool after an error
+        return rc;
+    }
     const double t1 = now_ms();
     const size_t n = ctx->tasks.size(), nch = ctx->chunks.size();
-    if (n == 0) return POYB200_OK;
+    if (n == 0) {
+        cudaStreamSynchronize(ctx->s_in);
+        return POYB200_OK;
+    }
     rc = prepare_events(ctx);
     if (rc) return rc;
     rc = reset_counters(ctx);
     if (rc) return rc;
-    constexpr size_t SLICE = (size_t) 32 << 20;
-    const size_t nslices = (b->pool_bytes + SLICE - 1) / SLICE;
     while (ctx->ev_done.size() < nch + nslices + 1) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->ev_done.push_back(e);
     }
-    cudaEvent_t *ev_slice = ctx->ev_done.data() + nch, ev_tasks = ctx->ev_done[nch + nslices];
+    cudaEvent_t *ev_slice = ctx->ev_pool.data();
     // last pool byte each chunk needs (prefix maximum: slices arrive in order)
     std::vector<size_t> need(nch, 0);
     parallel_for(ctx->host_threads, nch, [&](size_t lo, size_t hi, int) {
@@ -870,14 +943,11 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         }
     }, 1);
     for (size_t ci = 1; ci < nch; ci++) need[ci] = std::max(need[ci], need[ci - 1]);
+    // the task array follows the early slices, the rest of the pool follows the task array
     CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, ctx->s_in));
-    CK(cudaEventRecord(ev_tasks, ctx->s_in));
-    for (size_t k = 0; k < nslices; k++) {
-        const size_t lo = k * SLICE, len = std::min(SLICE, b->pool_bytes - lo);
-        CK(cudaMemcpyAsync(ctx->d_pool.p + lo, b->pool + lo, len, cudaMemcpyHostToDevice, ctx->s_in));
-        CK(cudaEventRecord(ev_slice[k], ctx->s_in));
-    }
-    CK(cudaStreamWaitEvent(ctx->stream, ev_tasks, 0));
+    CK(cudaEventRecord(ctx->ev_done[nch + nslices], ctx->s_in));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[nch + nslices], 0));
+    if (int urc = upload_slices(nearly, nslices)) return urc;
     size_t waited = 0;  // slices the compute stream already waits for
     for (size_t ci = 0; ci < nch; ci++) {
         const size_t upto = std::min(nslices, (need[ci] + SLICE - 1) / SLICE);
@@ -897,15 +967,22 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         for (size_t ci = 0; ci < nch; ci++) {
             const Chunk &ch = ctx->chunks[ci];
             if (bt) {
-                CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_tb[ci], 0));  // s_in is idle once the pool is up
+                // the lengths travel on a stream of their own: behind the pool slices on s_in they would hold the download of
+                // the first chunks back until the whole pool is up (measured: 21 of 77 ms per 1 M pairs)
+                CK(cudaStreamWaitEvent(ctx->s_len, ctx->ev_tb[ci], 0));
                 CK(cudaMemcpyAsync(b->out_len + 4 * ch.begin, ctx->d_outlen.p + 4 * ch.begin, 4 * (ch.end - ch.begin) * sizeof(int),
-                                   cudaMemcpyDeviceToHost, ctx->s_in));
-                CK(cudaStreamSynchronize(ctx->s_in));
+                                   cudaMemcpyDeviceToHost, ctx->s_len));
+                CK(cudaStreamSynchronize(ctx->s_len));
+                if (trace) fprintf(stderr, "[poyb200]   chunk %zu (%zu pairs) traced back at +%.1f ms\n", ci, ch.end - ch.begin, now_ms() - t0);
             } else {
                 CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_tb[ci], 0));
             }
             rc = fetch_range(ctx, ch.begin, ch.end, ctx->s_out, bt);
             if (rc) return rc;
+            if (trace && atoi(getenv("POYB200_TRACE")) >= 2) {
+                cudaStreamSynchronize(ctx->s_out);
+                fprintf(stderr, "[poyb200]   chunk %zu downloaded at +%.1f ms\n", ci, now_ms() - t0);
+            }
         }
     }
     if (!ctx->in_order) {
