@@ -96,80 +96,70 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     // 0xFFFF for the generic ones, where the quotient is 0 for every dd the 16384-element cap allows
     const uint32_t recip = (65536u + t.twoK - 1) / t.twoK;
     int nmed = 0, nwg = 0, nres = 0, med_first = -1, nclo = 0;
-    enum { M_TODO, M_VERT, M_HORI, M_DIAG, M_ALGN };
+    // The reference's mode machine (m_todo / vertical / horizontal / diagonal / align, :2003-2075) and its two tails
+    // (`while (i)`, `while (j)`, :2076-2091) as ONE branch-free step: the 32 walkers of a warp are in different modes, and with
+    // a branch per mode the warp issued every branch (ncu: ~250 warp instructions per step); here every walker runs the same
+    // instructions and the mode only selects values.  Modes carry the AM_* codes of the direction byte, 4 = m_todo.
+    constexpr int M_TODO = 4;
     int mode = M_TODO;
-#define PUT_MED(v) do { nmed++; med_first = (v); if (w_med) med.put(v); } while (0)
-#define PUT_WG(v) do { nwg++; if (w_wg) wg.put(v); if (w_bits) bw.put((v) != TMPGAP); } while (0)
-#define PUT_RES(a, b) do { nres++; if (w_al) { ri.put(a); rj.put(b); } if (w_bits) { bi.put((a) != TMPGAP); bj.put((b) != TMPGAP); } \
-        if (w_clo) { const int sel_ = rows_b ? closest_elem(cm, (b), (a)) : closest_elem(cm, (a), (b)); \
-                     if (sel_ != TMPGAP) { nclo++; med.put(sel_); } } } while (0)
-    while (i != 0 && j != 0) {
-        const int d = j - i;
-        int b;
-        if (d < t.dlo) b = AFF_LEFT_EDGE_BYTE;
-        else if (d > t.dhi) b = AFF_RIGHT_EDGE_BYTE;
-        else {
-            // dir_index with the division by twoK done as a multiplication (dd < 16384, see recip)
-            const uint32_t dd = (uint32_t) (d - t.dbase), T = (uint32_t) (i + j - t.tshift);
-            const uint32_t lane = (dd * recip) >> 16, m = (dd - lane * t.twoK) >> 1;
-            const uint64_t idx = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
-            b = __ldg(dbase + idx);
-            if (idx >= 2 * tile_bytes) prefetch_l1(dbase + idx - 2 * tile_bytes);
+    while ((i | j) != 0) {
+        const bool inside = (i != 0) & (j != 0);
+        int b = 0;
+        if (inside) {
+            const int d = j - i;
+            if (d < t.dlo) b = AFF_LEFT_EDGE_BYTE;
+            else if (d > t.dhi) b = AFF_RIGHT_EDGE_BYTE;
+            else {
+                // dir_index with the division by twoK done as a multiplication (dd < 16384, see recip)
+                const uint32_t dd = (uint32_t) (d - t.dbase), T = (uint32_t) (i + j - t.tshift);
+                const uint32_t lane = (dd * recip) >> 16, m = (dd - lane * t.twoK) >> 1;
+                const uint64_t idx = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL + m;
+                b = __ldg(dbase + idx);
+                if (idx >= 2 * tile_bytes) prefetch_l1(dbase + idx - 2 * tile_bytes);
+            }
         }
-        // the reference spends one iteration on m_todo and re-reads the same cell in the next one (:2003-2013):
-        // same cell, same byte, so the mode is resolved and carried out in one pass
-        if (mode == M_TODO) {
-            const int m = (b >> 2) & 3;
-            mode = (m == AM_H) ? M_HORI : (m == AM_A) ? M_ALGN : (m == AM_V) ? M_VERT : M_DIAG;
+        // m_todo reads the cell and the next iteration acts on the same cell (:2003-2013): resolved in place.  Outside the
+        // matrix the tails move vertically while rows are left, then horizontally.
+        const int eff = inside ? ((mode == M_TODO) ? ((b >> 2) & 3) : mode) : ((i != 0) ? AM_V : AM_H);
+        const bool isH = eff == AM_H, isV = eff == AM_V, isA = eff == AM_A, isD = eff == AM_D;
+        const int a_el = isH ? TMPGAP : ic, b_el = isV ? TMPGAP : jc;  // the column of resi / resj
+        const int x = isV ? ic : jc;                                    // the element an indel column is built from
+        const int p = cm_median(cm, ic & 15, jc & 15);
+        const int wgv = isA ? p : ((isD || (x & TMPGAP)) ? TMPGAP : (x | TMPGAP));
+        const bool emit = isA || (!isD && !(x & TMPGAP));
+        nres++;
+        nwg++;
+        if (w_al) { ri.put(a_el); rj.put(b_el); }
+        if (w_wg) wg.put(wgv);
+        if (w_bits) { bi.put(a_el != TMPGAP); bj.put(b_el != TMPGAP); bw.put(wgv != TMPGAP); }
+        if (w_clo) {
+            const int sel = rows_b ? closest_elem(cm, b_el, a_el) : closest_elem(cm, a_el, b_el);
+            if (sel != TMPGAP) { nclo++; med.put(sel); }
         }
-        if (mode == M_VERT) {
-            if (b & AB_ENDV) mode = M_TODO;
-            if (!(ic & TMPGAP)) { PUT_MED(ic | TMPGAP); PUT_WG(ic | TMPGAP); } else PUT_WG(TMPGAP);
-            PUT_RES(ic, TMPGAP);
-            i--;
-            ic = si[i];
-        } else if (mode == M_HORI) {
-            if (b & AB_ENDH) mode = M_TODO;
-            if (!(jc & TMPGAP)) { PUT_MED(jc | TMPGAP); PUT_WG(jc | TMPGAP); } else PUT_WG(TMPGAP);
-            PUT_RES(TMPGAP, jc);
-            j--;
-            jc = sj[j];
-        } else if (mode == M_DIAG) {
-            if (b & AB_ENDB) mode = M_TODO;
-            PUT_RES(ic, jc);
-            PUT_WG(TMPGAP);
-            i--; j--;
-            ic = si[i]; jc = sj[j];
-        } else {
-            const int nx = b & 3;
-            if (nx == AN_H) mode = M_HORI;
-            else if (nx == AN_D) mode = M_DIAG;
-            else if (nx == AN_V) mode = M_VERT;
-            const int p = cm_median(cm, ic & 15, jc & 15);
-            PUT_MED(p); PUT_WG(p);
-            PUT_RES(ic, jc);
-            i--; j--;
-            ic = si[i]; jc = sj[j];
+        if (emit) {
+            nmed++;
+            med_first = wgv;
+            if (w_med) med.put(wgv);
         }
-    }
-    while (i != 0) {
-        if (!(ic & TMPGAP)) { PUT_MED(ic | TMPGAP); PUT_WG(ic | TMPGAP); } else PUT_WG(TMPGAP);
-        PUT_RES(ic, TMPGAP);
-        i--;
+        const int nx = b & 3;
+        const int after_align = (nx == AN_H) ? AM_H : (nx == AN_D) ? AM_D : (nx == AN_V) ? AM_V : AM_A;
+        const int endbit = isV ? AB_ENDV : isH ? AB_ENDH : AB_ENDB;
+        mode = isA ? after_align : ((b & endbit) ? M_TODO : eff);
+        i -= !isH;
+        j -= !isV;
         ic = si[i];
-    }
-    while (j != 0) {
-        if (!(jc & TMPGAP)) { PUT_MED(jc | TMPGAP); PUT_WG(jc | TMPGAP); } else PUT_WG(TMPGAP);
-        PUT_RES(TMPGAP, jc);
-        j--;
         jc = sj[j];
     }
-    PUT_RES(TMPGAP, TMPGAP);
-    PUT_WG(TMPGAP);
-    if (med_first != TMPGAP) PUT_MED(TMPGAP);  // :2093 (an empty median counts as "not a gap")
-#undef PUT_MED
-#undef PUT_WG
-#undef PUT_RES
+    // the leading column: (gap, gap), a gap in medianwg, and a gap in front of the median unless it starts with one
+    nres++;
+    nwg++;
+    if (w_al) { ri.put(TMPGAP); rj.put(TMPGAP); }
+    if (w_bits) { bi.put(false); bj.put(false); bw.put(false); }
+    if (w_wg) wg.put(TMPGAP);
+    if (med_first != TMPGAP) {  // :2093 (an empty median counts as "not a gap")
+        nmed++;
+        if (w_med) med.put(TMPGAP);
+    }
     if (w_clo) { med.put(TMPGAP); nclo++; }  // `prepend res gap`, src/sequence.ml:980
     if (w_med || w_clo) med.flush();
     if (w_wg) wg.flush();
