@@ -48,8 +48,9 @@ WORKLOADS = {
     "protein300": ("configs[2] (3a): protein pairs 300 aa, 22x22 matrix 1/2, deltaw as the product computes it "
                    "(full matrix, SURVEY.md A15), align_2 + medians", 1, 10),
     "protein300_band16": ("configs[2] (3b): protein pairs 300 aa, explicit deltaw 16, align_2 + medians", 1, 10),
-    "tree": ("configs[4]-style host-driver workload (one GPU per tree): Wagner build with batched candidate-edge sweeps + "
-             "all-directions downpass, root selection, single assignment and adjusted cost (poyd_b200/tree.py) of a "
+    "tree": ("configs[4]-style host-driver workload (one GPU per tree): Wagner build with batched candidate-edge sweeps, "
+             "all-directions downpass, root selection, single assignment and adjusted cost of the built tree, then --spr SPR "
+             "neighbours evaluated exactly in lockstep (poyd_b200/tree.py); "
              "synthetic --taxa x --bp DNA data set, affine gaps (1, 2, opening 3)", 3, 50),
 }
 
@@ -186,6 +187,11 @@ def bench_tree(args, rank, local_rank, world, threads):
         t0 = time.perf_counter()
         topo, steps = ev.wagner(lv)
         r = ev.evaluate(topo, lv, keep=True)
+        if args.spr > 0:  # exact evaluation of a sample of the SPR neighbourhood, all trees in lockstep
+            nb = T.spr_neighbours(topo, limit=args.spr, seed=7)
+            rs = ev.evaluate_many(nb, lv, keep=True)
+            r.stats["spr_trees"] = len(nb)
+            r.stats["spr_best"] = min(x.adjusted for x in rs) if rs else None
         dt = time.perf_counter() - t0
         return dt, r, T.logged_cells(engine.log, True), sum(len(x[1]) for x in engine.log), len(engine.log)
 
@@ -203,7 +209,8 @@ def bench_tree(args, rank, local_rank, world, threads):
                           "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "int32", "data": "synthetic",
                           "config": {"workload": WORKLOADS["tree"][0], "taxa": len(sub), "bp": args.bp, "pairs": npairs,
-                                     "batches": ncalls, "adjusted_cost": r.adjusted},
+                                     "batches": ncalls, "adjusted_cost": r.adjusted, "spr_trees": r.stats.get("spr_trees"),
+                                     "spr_best": r.stats.get("spr_best")},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                                            "sample": f"the first {len(sub)} taxa, same driver, CPU checker engine"},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -240,7 +247,7 @@ def bench_tree(args, rank, local_rank, world, threads):
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOADS["tree"][0], "taxa": args.taxa, "bp": args.bp, "pairs": npairs, "batches": ncalls,
-                           "adjusted_cost": r.adjusted, "timing": "host wall clock around the driver (every call moves host "
+                           "adjusted_cost": r.adjusted, "spr_trees": r.stats.get("spr_trees"), "spr_best": r.stats.get("spr_best"), "timing": "host wall clock around the driver (every call moves host "
                            "buffers in and out); small batches, so latency- not roofline-bound"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
                 "gpu_launches": int(launches)}
@@ -294,6 +301,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--taxa", type=int, default=150, help="tree workload: taxa")
     ap.add_argument("--bp", type=int, default=1500, help="tree workload: bases per taxon")
+    ap.add_argument("--spr", type=int, default=100, help="tree workload: SPR neighbours evaluated exactly, in lockstep")
     ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS),
                     help="affine500 is the headline configuration; the others are reported in DESIGN.md")
     args = ap.parse_args()

@@ -174,6 +174,50 @@ class Topology:
         return out
 
 
+def spr_neighbours(topo: Topology, limit: Optional[int] = None, seed: int = 0) -> List[Topology]:
+    """The SPR neighbourhood of a tree (what ``Ptree.single_spr_round`` walks, src/ptree.ml:1141-1168): every subtree is
+    pruned with its attachment vertex and regrafted on every other edge.  Vertex codes are kept (the attachment vertex
+    moves with the subtree), the handle stays in the part that is not pruned.  ``limit`` draws a seeded sample."""
+    def repl(tup, old, new):
+        return tuple(new if z == old else z for z in tup)
+
+    out: List[Topology] = []
+    moves = []
+    for p, nb in topo.nodes.items():
+        if len(nb) != 3 or p == topo.handle:
+            continue
+        for c in nb:
+            x, y = [z for z in nb if z != c]
+            pruned, stack = {p, c}, [c]
+            while stack:
+                v = stack.pop()
+                for w in topo.nodes[v]:
+                    if w not in pruned:
+                        pruned.add(w)
+                        stack.append(w)
+            if topo.handle in pruned:
+                continue
+            for u in topo.nodes:
+                if u in pruned:
+                    continue
+                for v in topo.nodes[u]:
+                    if v in pruned or v < u or {u, v} == {x, y}:
+                        continue
+                    moves.append((p, c, x, y, u, v))
+    if limit is not None and len(moves) > limit:
+        rng = np.random.default_rng(seed)
+        moves = [moves[i] for i in sorted(rng.choice(len(moves), size=limit, replace=False))]
+    for (p, c, x, y, u, v) in moves:
+        n2 = dict(topo.nodes)
+        n2[x] = repl(n2[x], p, y)
+        n2[y] = repl(n2[y], p, x)
+        n2[u] = repl(n2[u], v, p)
+        n2[v] = repl(n2[v], u, p)
+        n2[p] = (u, v, c)
+        out.append(Topology(n2, topo.handle, topo.n_taxa))
+    return out
+
+
 # ---- engines --------------------------------------------------------------------------------------------------
 class GpuEngine:
     """The three batch calls of the driver on :class:`poyd_b200.sequence.Align` (CUDA; no CPU path)."""
@@ -363,11 +407,13 @@ class Evaluator:
         self.store: List[np.ndarray] = []
         self._sig: Dict[Tuple[int, int], int] = {}          # (sig x, sig y) ordered -> sig id of the median node
         self._node: Dict[int, Tuple[List[int], int, int]] = {}  # sig id -> (store index per locus, total cost, min_child_code)
-        self._edge: Dict[Tuple[int, int], Tuple[List[int], int]] = {}
+        self._edge: Dict[Tuple[int, int], Optional[Tuple[List[int], int]]] = {}
         self._leafsig: Dict[int, int] = {}
         self.n_medians = 0
         self._next_sig = 0
         self._empty: Dict[int, bool] = {}
+        self._clo: Dict[Tuple[int, int], int] = {}    # closest by (parent, mine) store index
+        self._dist: Dict[Tuple[int, int], int] = {}   # DOS.distance by store index pair
 
     def _emp(self, i: int) -> bool:
         """Sequence.is_empty of store[i], remembered (the store only grows)."""
@@ -391,13 +437,10 @@ class Evaluator:
             self._node[sig] = (idx, 0, code)
         return sig
 
-    def directional(self, topo: Topology, leaves: Dict[int, List[np.ndarray]]) -> Dict[Tuple[int, int], int]:
-        """Signature of every directional node ``(u, v)`` = u looking away from v (``AllDirNode.not_with v``), all
-        missing medians computed level by level, one batch per level."""
-        n_loci = len(next(iter(leaves.values())))
-        store = self.store
+    def _collect(self, topo: Topology, leaves: Dict[int, List[np.ndarray]]) -> Dict[Tuple[int, int], int]:
+        """Signature of every directional node ``(u, v)`` = u looking away from v (``AllDirNode.not_with v``).  Medians
+        that are not in the cache yet are only *registered* (``self._fresh``); :meth:`_flush` computes them."""
         sig: Dict[Tuple[int, int], int] = {}
-        pending: Dict[Tuple[int, int], int] = {}   # directed pair -> level, for the ones whose median is not cached
         for u in topo.nodes:
             for v in topo.nodes[u]:
                 stack = [(u, v)]
@@ -417,117 +460,174 @@ class Evaluator:
                         continue
                     sx, sy = sig[(x, a)], sig[(y, a)]
                     # Node.cs_median: the operand with the smaller min_child_code first (src/node.ml:343-348)
-                    if not self._minc(sx, pending) < self._minc(sy, pending):
+                    if not self._minc(sx) < self._minc(sy):
                         sx, sy = sy, sx
                     s_ = self._sig.get((sx, sy))
                     if s_ is None:
                         s_ = self._sig[(sx, sy)] = self._new_sig()
-                        self._fresh[s_] = (sx, sy, 1 + max(self._fresh.get(sx, (0, 0, 0))[2], self._fresh.get(sy, (0, 0, 0))[2]))
+                        lv = 1 + max(self._fresh.get(sx, (0, 0, 0, 0))[2], self._fresh.get(sy, (0, 0, 0, 0))[2])
+                        self._fresh[s_] = (sx, sy, lv, min(self._minc(sx), self._minc(sy)))
                     sig[(a, b)] = s_
                     stack.pop()
-        # compute the fresh signatures, level by level
-        if self._fresh:
-            top = max(l for _, _, l in self._fresh.values())
-            for lv in range(1, top + 1):
-                keys = [k for k, (_, _, l) in self._fresh.items() if l == lv]
-                jobs = []
-                for k in keys:
-                    sx, sy, _ = self._fresh[k]
-                    for l in range(n_loci):
-                        jobs.append((self._node[sx][0][l], self._node[sy][0][l]))
-                res = self._medians(store, jobs)
-                self.n_medians += len(jobs)
-                for i, k in enumerate(keys):
-                    sx, sy, _ = self._fresh[k]
-                    r = res[i * n_loci:(i + 1) * n_loci]
-                    nx, ny = self._node[sx], self._node[sy]
-                    self._node[k] = ([j for j, _ in r], nx[1] + ny[1] + sum(c for _, c in r), min(nx[2], ny[2]))
-            self._fresh.clear()
         return sig
 
-    def _minc(self, s_: int, pending) -> int:
-        if s_ in self._node:
-            return self._node[s_][2]
-        sx, sy, _ = self._fresh[s_]
-        return min(self._minc(sx, pending), self._minc(sy, pending))
+    def _flush(self, n_loci: int) -> None:
+        """Computes the registered medians level by level: one batch per dependency level, whatever number of trees
+        registered them."""
+        if not self._fresh:
+            return
+        top = max(v[2] for v in self._fresh.values())
+        by_level: List[List[int]] = [[] for _ in range(top + 1)]
+        for k, v in self._fresh.items():
+            by_level[v[2]].append(k)
+        for lv in range(1, top + 1):
+            keys = by_level[lv]
+            jobs = []
+            for k in keys:
+                sx, sy = self._fresh[k][0], self._fresh[k][1]
+                for l in range(n_loci):
+                    jobs.append((self._node[sx][0][l], self._node[sy][0][l]))
+            res = self._medians(self.store, jobs)
+            self.n_medians += len(jobs)
+            for i, k in enumerate(keys):
+                sx, sy = self._fresh[k][0], self._fresh[k][1]
+                r = res[i * n_loci:(i + 1) * n_loci]
+                nx, ny = self._node[sx], self._node[sy]
+                self._node[k] = ([j for j, _ in r], nx[1] + ny[1] + sum(c for _, c in r), min(nx[2], ny[2]))
+        self._fresh.clear()
+
+    def directional(self, topo: Topology, leaves: Dict[int, List[np.ndarray]]) -> Dict[Tuple[int, int], int]:
+        """Signatures of all directional nodes of one tree, their medians computed."""
+        sig = self._collect(topo, leaves)
+        self._flush(len(next(iter(leaves.values()))))
+        return sig
+
+    def _minc(self, s_: int) -> int:
+        return self._node[s_][2] if s_ in self._node else self._fresh[s_][3]
 
     def edge_medians(self, topo: Topology, sig: Dict[Tuple[int, int], int], edges: List[Tuple[int, int]],
                      n_loci: int) -> Dict[Tuple[int, int], Tuple[List[int], int]]:
         """``refresh_all_edges`` (src/allDirChar.ml:672-700): the median across every edge and its root cost."""
-        E: Dict[Tuple[int, int], Tuple[List[int], int]] = {}
-        jobs, todo = [], []
-        for (a, b) in edges:
-            sa, sb = sig[(a, b)], sig[(b, a)]
-            if not self._node[sa][2] < self._node[sb][2]:
-                sa, sb = sb, sa
-            hit = self._edge.get((sa, sb))
-            if hit is not None:
-                E[(a, b)] = hit
-                continue
-            todo.append(((a, b), sa, sb))
-            for l in range(n_loci):
-                jobs.append((self._node[sa][0][l], self._node[sb][0][l]))
+        return self._edge_medians_many([(sig, edges)], n_loci)[0]
+
+    def _edge_medians_many(self, trees, n_loci: int):
+        jobs, todo, keys = [], [], []
+        for sig, edges in trees:
+            ks = []
+            for (a, b) in edges:
+                sa, sb = sig[(a, b)], sig[(b, a)]
+                if not self._node[sa][2] < self._node[sb][2]:
+                    sa, sb = sb, sa
+                ks.append((sa, sb))
+                if (sa, sb) not in self._edge:
+                    self._edge[(sa, sb)] = None  # claimed: computed once for all the trees that share the edge
+                    todo.append((sa, sb))
+                    for l in range(n_loci):
+                        jobs.append((self._node[sa][0][l], self._node[sb][0][l]))
+            keys.append(ks)
         res = self._medians(self.store, jobs)
         self.n_medians += len(jobs)
-        for i, (e, sa, sb) in enumerate(todo):
+        for i, (sa, sb) in enumerate(todo):
             r = res[i * n_loci:(i + 1) * n_loci]
-            E[e] = self._edge[(sa, sb)] = ([j for j, _ in r], self._node[sa][1] + self._node[sb][1] + sum(c for _, c in r))
-        return E
+            self._edge[(sa, sb)] = ([j for j, _ in r], self._node[sa][1] + self._node[sb][1] + sum(c for _, c in r))
+        return [{e: self._edge[k] for e, k in zip(edges, ks)} for (_, edges), ks in zip(trees, keys)]
+
+    def _closest_cached(self, jobs: List[Tuple[int, int]]) -> List[int]:
+        """``closest parent mine`` by store index, each distinct (parent, mine) computed once."""
+        new = []
+        for j in jobs:
+            if j not in self._clo:
+                self._clo[j] = -1
+                new.append(j)
+        if new:
+            for j, r in zip(new, self._closest_batch(self.store, new)):
+                self._clo[j] = r
+        return [self._clo[j] for j in jobs]
 
     def evaluate(self, topo: Topology, leaves: Dict[int, List[np.ndarray]], keep: bool = False) -> TreeCost:
         """Downpass + uppass of one tree.  ``keep=True`` keeps the median cache for the next tree over the same leaves."""
+        return self.evaluate_many([topo], leaves, keep=keep)[0]
+
+    def evaluate_many(self, topos: List[Topology], leaves: Dict[int, List[np.ndarray]], keep: bool = False) -> List[TreeCost]:
+        """Downpass + uppass of several trees over the same leaves -- an SPR/TBR neighbourhood, the candidates of an
+        exhaustive join -- in lockstep: the batches of every phase hold the work of ALL trees, and whatever the trees
+        share (subtree medians, edge medians, single assignments below a common root, edge distances) is computed once."""
         if not keep or not hasattr(self, "store"):
             self._reset()
-        self._fresh: Dict[int, Tuple[int, int, int]] = {}
+        self._fresh = {}
         n_loci = len(next(iter(leaves.values())))
         store = self.store
         nb0, nm0 = getattr(self.e, "calls", 0), self.n_medians
-        sig = self.directional(topo, leaves)
-        D = {k: self._node[v] for k, v in sig.items()}
-        edges = topo.pre_order_edges()
-        E = self.edge_medians(topo, sig, edges, n_loci)
-        # general_pick_best_root with blindly_trust_downpass
-        h = topo.handle
-        root = (h, topo.nodes[h][0])  # create_root: the handle and its parent
-        best = E[root][1]
-        for e in sorted(edges, key=lambda e: (-e[0], -e[1])):
-            c = E[e][1]
-            if abs(best) > abs(c):
-                best, root = c, e
-        # assign_single (uppass)
-        a, b = root
-        singles: Dict[int, List[int]] = {}
-        rs = self._closest_batch(store, [(self._nonempty_parent(store, E[root][0][l], D[(a, b)][0][l]), D[(a, b)][0][l])
-                                         for l in range(n_loci)])
-        frontier = [(b, a, rs), (a, b, rs)]  # (parent vertex, current vertex, parent's singles)
+        sigs = [self._collect(t, leaves) for t in topos]
+        self._flush(n_loci)
+        edges_all = [t.pre_order_edges() for t in topos]
+        Es = self._edge_medians_many(list(zip(sigs, edges_all)), n_loci)
+        # general_pick_best_root with blindly_trust_downpass, tree by tree
+        roots, bests = [], []
+        for topo, edges, E in zip(topos, edges_all, Es):
+            h = topo.handle
+            root = (h, topo.nodes[h][0])  # create_root: the handle and its parent
+            best = E[root][1]
+            for e in sorted(edges, key=lambda e: (-e[0], -e[1])):
+                c = E[e][1]
+                if abs(best) > abs(c):
+                    best, root = c, e
+            roots.append(root)
+            bests.append(best)
+        # assign_single (uppass): all trees advance one depth per batch
+        D = [{k: self._node[v][0] for k, v in sig.items()} for sig in sigs]
+        singles: List[Dict[int, List[int]]] = [dict() for _ in topos]
+        jobs = []
+        for ti, (root, E) in enumerate(zip(roots, Es)):
+            a, b = root
+            for l in range(n_loci):
+                mine = D[ti][(a, b)][l]
+                jobs.append((self._nonempty_parent(store, E[root][0][l], mine), mine))
+        rs = self._closest_cached(jobs)
+        frontier = []  # (tree, parent vertex, current vertex, parent's singles)
+        for ti, (a, b) in enumerate(roots):
+            r = rs[ti * n_loci:(ti + 1) * n_loci]
+            frontier += [(ti, b, a, r), (ti, a, b, r)]
         while frontier:
             jobs = []
-            for (p, cur, ps) in frontier:
-                mine = D[(cur, p)][0]
+            for (ti, p, cur, ps) in frontier:
+                mine = D[ti][(cur, p)]
                 for l in range(n_loci):
                     jobs.append((self._nonempty_parent(store, ps[l], mine[l]), mine[l]))
-            res = self._closest_batch(store, jobs)
+            res = self._closest_cached(jobs)
             nxt = []
-            for k, (p, cur, ps) in enumerate(frontier):
+            for k, (ti, p, cur, ps) in enumerate(frontier):
                 sg = res[k * n_loci:(k + 1) * n_loci]
-                singles[cur] = sg
-                if not topo.is_leaf(cur):
-                    x, y = topo.other_two_nbrs(p, cur)
-                    nxt.append((cur, x, sg))
-                    nxt.append((cur, y, sg))
+                singles[ti][cur] = sg
+                if not topos[ti].is_leaf(cur):
+                    x, y = topos[ti].other_two_nbrs(p, cur)
+                    nxt.append((ti, cur, x, sg))
+                    nxt.append((ti, cur, y, sg))
             frontier = nxt
         # check_cost: distances between single assignments along the edges, oriented away from the handle
-        jobs = []
-        for (p, v) in edges:
-            for l in range(n_loci):
-                s1, s2 = store[singles[p][l]], store[singles[v][l]]
-                if not (self._emp(singles[p][l]) or self._emp(singles[v][l])):  # else missing_distance = 0
-                    jobs.append((singles[p][l], singles[v][l]))
-        adjusted = int(self.e.distance(store, np.array(jobs, np.int32)).astype(np.int64).sum()) if jobs else 0
-        return TreeCost(adjusted=adjusted, unadjusted=int(best), root=root,
-                        singles={v: [store[i] for i in ix] for v, ix in singles.items()},
-                        root_costs={e: c for e, (_, c) in E.items()}, batches=getattr(self.e, "calls", 0) - nb0,
-                        medians=self.n_medians - nm0, stats={"edges": len(edges), "loci": n_loci, "sequences": len(store)})
+        new = []
+        for ti, edges in enumerate(edges_all):
+            for (p, v) in edges:
+                for l in range(n_loci):
+                    j = (singles[ti][p][l], singles[ti][v][l])
+                    if j not in self._dist:
+                        if self._emp(j[0]) or self._emp(j[1]):
+                            self._dist[j] = 0  # missing_distance
+                        else:
+                            self._dist[j] = -1
+                            new.append(j)
+        if new:
+            for j, c in zip(new, self.e.distance(store, np.array(new, np.int32))):
+                self._dist[j] = int(c)
+        out = []
+        for ti, (topo, edges, E) in enumerate(zip(topos, edges_all, Es)):
+            adjusted = sum(self._dist[(singles[ti][p][l], singles[ti][v][l])] for (p, v) in edges for l in range(n_loci))
+            out.append(TreeCost(adjusted=int(adjusted), unadjusted=int(bests[ti]), root=roots[ti],
+                                singles={v: [store[i] for i in ix] for v, ix in singles[ti].items()},
+                                root_costs={e: c for e, (_, c) in E.items()}, batches=getattr(self.e, "calls", 0) - nb0,
+                                medians=self.n_medians - nm0,
+                                stats={"edges": len(edges), "loci": n_loci, "sequences": len(store), "trees": len(topos)}))
+        return out
 
     # -- Wagner build with a batched candidate-edge sweep (Ptree.make_wagner_tree, src/ptree.ml:948-1060) --------------
     def wagner(self, leaves: Dict[int, List[np.ndarray]], order: Optional[List[int]] = None):

@@ -134,3 +134,31 @@ def test_wagner_gpu_matches_cpu_checker():
         assert (cg.adjusted, cg.unadjusted, cg.root) == (cc.adjusted, cc.unadjusted, cc.root)
         for v in cc.singles:
             assert all(np.array_equal(x, y) for x, y in zip(cg.singles[v], cc.singles[v]))
+
+
+def test_spr_neighbourhood_in_lockstep_cpu_checker(checker_factory):
+    """evaluate_many over an SPR neighbourhood: every tree gets exactly what a cold evaluation of it alone gives, in far
+    fewer engine calls, because the batches hold all trees and shared medians / singles / distances are computed once."""
+    from oracle.tree_engine import OracleEngine
+    from poyd_b200 import synth
+
+    cm = CM.nucleotides(2, 1, 1)
+    leaves = synth.taxa_on_random_tree(10, 100, seed=9, subst=0.08, indel=0.03)
+    ev = T.Evaluator(OracleEngine(cm, nthreads=2), cm)
+    topo, _ = ev.wagner(leaves)
+    nbrs = T.spr_neighbours(topo, limit=24, seed=1)
+    assert len(nbrs) == 24
+    for t in nbrs:  # still binary trees over the same taxa
+        assert sorted(v for v in t.nodes if t.is_leaf(v)) == list(range(1, 11))
+        assert all(u in t.nodes[v] for u in t.nodes for v in t.nodes[u])
+        assert len(t.pre_order_edges()) == 2 * 10 - 3
+    many = ev.evaluate_many(nbrs, leaves, keep=True)
+    lock_calls = many[0].batches
+    solo_calls = 0
+    for t, r in zip(nbrs, many):
+        cold = T.Evaluator(OracleEngine(cm, nthreads=2), cm).evaluate(t, leaves)
+        solo_calls += cold.batches
+        assert (r.adjusted, r.unadjusted, r.root) == (cold.adjusted, cold.unadjusted, cold.root)
+        for v in cold.singles:
+            assert all(np.array_equal(x, y) for x, y in zip(r.singles[v], cold.singles[v]))
+    assert lock_calls * 5 < solo_calls
