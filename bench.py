@@ -187,12 +187,17 @@ def bench_tree(args, rank, local_rank, world, threads):
         t0 = time.perf_counter()
         topo, steps = ev.wagner(lv)
         r = ev.evaluate(topo, lv, keep=True)
+        t1 = time.perf_counter()
+        n1, c1 = sum(len(x[1]) for x in engine.log), len(engine.log)
         if args.spr > 0:  # exact evaluation of a sample of the SPR neighbourhood, all trees in lockstep
             nb = T.spr_neighbours(topo, limit=args.spr, seed=7)
             rs = ev.evaluate_many(nb, lv, keep=True)
             r.stats["spr_trees"] = len(nb)
             r.stats["spr_best"] = min(x.adjusted for x in rs) if rs else None
         dt = time.perf_counter() - t0
+        r.stats["phases"] = {"wagner_and_evaluation": {"seconds": round(t1 - t0, 3), "pairs": n1, "calls": c1},
+                             "spr_lockstep": {"seconds": round(t0 + dt - t1, 3), "pairs": sum(len(x[1]) for x in engine.log) - n1,
+                                              "calls": len(engine.log) - c1}}
         return dt, r, T.logged_cells(engine.log, True), sum(len(x[1]) for x in engine.log), len(engine.log)
 
     if args.impl == "reference":
@@ -247,7 +252,7 @@ def bench_tree(args, rank, local_rank, world, threads):
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOADS["tree"][0], "taxa": args.taxa, "bp": args.bp, "pairs": npairs, "batches": ncalls,
-                           "adjusted_cost": r.adjusted, "spr_trees": r.stats.get("spr_trees"), "spr_best": r.stats.get("spr_best"), "timing": "host wall clock around the driver (every call moves host "
+                           "adjusted_cost": r.adjusted, "spr_trees": r.stats.get("spr_trees"), "spr_best": r.stats.get("spr_best"), "phases": r.stats.get("phases"), "timing": "host wall clock around the driver (every call moves host "
                            "buffers in and out); small batches, so latency- not roofline-bound"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
                 "gpu_launches": int(launches)}
@@ -301,7 +306,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--taxa", type=int, default=150, help="tree workload: taxa")
     ap.add_argument("--bp", type=int, default=1500, help="tree workload: bases per taxon")
-    ap.add_argument("--spr", type=int, default=100, help="tree workload: SPR neighbours evaluated exactly, in lockstep")
+    ap.add_argument("--spr", type=int, default=400, help="tree workload: SPR neighbours evaluated exactly, in lockstep")
     ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS),
                     help="affine500 is the headline configuration; the others are reported in DESIGN.md")
     args = ap.parse_args()
