@@ -5,6 +5,9 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <vector>
 
 #include "../../include/poyb200.h"
@@ -420,6 +423,74 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
 // ---------------------------------------------------------------------------------------------------------
 // planning
 // ---------------------------------------------------------------------------------------------------------
+// Persistent host workers for the planner: starting 32 std::threads costs more than a planning pass over 1 M pairs takes
+// per thread, and a call makes four such passes.  Workers sleep on a condition variable between passes.
+class WorkerPool {
+public:
+    static WorkerPool &get() {
+        static WorkerPool p;
+        return p;
+    }
+    // runs job(t) for t in [0, n): t = 0 on the calling thread, the others on workers
+    void run(int n, const std::function<void(int)> &job) {
+        std::unique_lock<std::mutex> call(call_m_);  // one parallel region at a time
+        ensure(n - 1);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = &job;
+            want_ = n - 1;
+            pending_ = n - 1;
+            gen_++;
+        }
+        cv_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+
+private:
+    void ensure(int n) {
+        while ((int) th_.size() < n) {
+            const int id = (int) th_.size() + 1;
+            std::unique_lock<std::mutex> g(m_);
+            const uint64_t seen = gen_;
+            g.unlock();
+            th_.emplace_back([this, id, seen] { loop(id, seen); });
+        }
+    }
+    void loop(int id, uint64_t seen) {
+        std::unique_lock<std::mutex> g(m_);
+        for (;;) {
+            cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            if (id <= want_) {
+                const std::function<void(int)> *job = job_;
+                g.unlock();
+                (*job)(id);
+                g.lock();
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::mutex m_, call_m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> th_;
+    const std::function<void(int)> *job_ = nullptr;
+    uint64_t gen_ = 0;
+    int want_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
 // Runs fn(lo, hi, slot) over [0, n) on up to `ctx->host_threads` threads.
 template <typename F>
 static void parallel_for(int nthreads, size_t n, F fn, size_t grain = 32768) {
@@ -428,10 +499,8 @@ static void parallel_for(int nthreads, size_t n, F fn, size_t grain = 32768) {
         fn((size_t) 0, n, 0);
         return;
     }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; t++)
-        th.emplace_back([=] { fn(n * t / nthreads, n * (t + 1) / nthreads, t); });
-    for (auto &x : th) x.join();
+    const std::function<void(int)> job = [&](int t) { fn(n * t / nthreads, n * (t + 1) / nthreads, t); };
+    WorkerPool::get().run(nthreads, job);
 }
 
 static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
