@@ -86,6 +86,8 @@ void caml_invalid_argument(const char *msg) __attribute__((noreturn));
 value caml_copy_double(double d);
 #define copy_double caml_copy_double
 value caml_alloc_tuple(mlsize_t n);
+value caml_alloc_string(mlsize_t len);
+#define Bytes_val(v) ((unsigned char *) (v))
 #define alloc_tuple caml_alloc_tuple
 value caml_alloc(mlsize_t n, int tag);
 value caml_copy_string(const char *s);

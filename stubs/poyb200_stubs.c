@@ -315,3 +315,159 @@ value poyb200_CAML_batch_cost_2(value seqs, value pairs, value deltaw, value cm)
     free(cst);
     CAMLreturn(costs);
 }
+
+/* ---- (3) the DOS.median payload and the uppass ------------------------------------------------------------------ */
+
+/* Gathers the distinct operands into a pinned pool (16-byte aligned starts).  Returns the pool; fills off / len. */
+static uint8_t *pool_of(value seqs, int ns, int64_t *off, int32_t *len, size_t *total_out) {
+    size_t total = 0;
+    for (int s = 0; s < ns; s++) {
+        seqt q;
+        Seq_custom_val(q, Field(seqs, s));
+        off[s] = (int64_t) total;
+        len[s] = q->len;
+        total += ((size_t) q->len + 15) & ~(size_t) 15;
+    }
+    uint8_t *pool = (uint8_t *) poyb200_host_alloc(total + 16);
+    for (int s = 0; s < ns; s++) {
+        seqt q;
+        Seq_custom_val(q, Field(seqs, s));
+        memcpy(pool + off[s], q->begin, (size_t) q->len);
+    }
+    *total_out = total;
+    return pool;
+}
+
+/* A right-aligned, most-significant-bit-first row of the library -> the byte string of an extlib BitSet of n bits
+ * (bit i lives in byte i / 8 at position i mod 8). */
+static void bitset_of_row(const uint8_t *row, int64_t stride, int n, unsigned char *dst, int dst_bytes) {
+    memset(dst, 0, (size_t) dst_bytes);
+    const int64_t first = 8 * stride - n;
+    for (int i = 0; i < n; i++) {
+        const int64_t p = first + i;
+        if ((row[p >> 3] >> (7 - (p & 7))) & 1) dst[i >> 3] |= (unsigned char) (1 << (i & 7));
+    }
+}
+
+/* external batch_median : s array -> int array -> int array -> Cost_matrix.Two_D.m -> s array ->
+ *                          (int array * int array * string array * string array * string array)
+ *   = "poyb200_CAML_batch_median"
+ * What SeqCS.DOS.median computes for every pair (src/seqCS.ml:747-776), both gap models: the cost, the median (into
+ * the n preallocated sequences of `median`), and the three gap bitsets of tmpa, tmpb, seqmwg -- returned as the
+ * alignment length and three byte strings per pair, ready for `Packed (len, {BitSet.data; len}, Raw operand)`.
+ * deltaw: n values for linear matrices (Sequence.Align.cost_2's deltaw, :691-714), ignored for affine ones. */
+value poyb200_CAML_batch_median(value seqs, value pairs, value deltaw, value cm, value median) {
+    CAMLparam5(seqs, pairs, deltaw, cm, median);
+    CAMLlocal5(res, costs, lens, ba, bb);
+    CAMLlocal2(bm, str);
+    const int ns = (int) Wosize_val(seqs), n = (int) Wosize_val(pairs) / 2;
+    struct cm *c = Cost_matrix_struct(cm);
+    poyb200_ctx *ctx = ctx_for(c);
+    int64_t *off = (int64_t *) malloc(sizeof(int64_t) * (size_t) (ns + 1));
+    int32_t *len = (int32_t *) malloc(sizeof(int32_t) * (size_t) (ns + 1));
+    int32_t *pr = (int32_t *) malloc(sizeof(int32_t) * 3 * (size_t) (n + 1)), *dw = pr + 2 * (size_t) (n + 1);
+    size_t total = 0;
+    uint8_t *pool = pool_of(seqs, ns, off, len, &total);
+    int maxcap = 16;
+    for (int p = 0; p < 2 * n; p++) pr[p] = Int_val(Field(pairs, p));
+    for (int p = 0; p < n; p++) {
+        dw[p] = Int_val(Field(deltaw, p));
+        const int cap = len[pr[2 * p]] + len[pr[2 * p + 1]] + 2;
+        if (cap > maxcap) maxcap = cap;
+    }
+    const int64_t stride = (maxcap + 15) & ~15, bstride = ((stride / 8) + 3) & ~3;
+    uint8_t *out = (uint8_t *) poyb200_host_alloc((size_t) n * (size_t) (stride + 3 * bstride) + 16);
+    int32_t *cst = (int32_t *) malloc(sizeof(int32_t) * (size_t) (n + 1));
+    int32_t *olen = (int32_t *) malloc(sizeof(int32_t) * 4 * (size_t) (n + 1));
+    poyb200_batch bt = {0};
+    bt.pool = pool; bt.pool_bytes = total; bt.seq_off = off; bt.seq_len = len; bt.n_seqs = ns;
+    bt.pairs = pr; bt.n_pairs = n; bt.deltaw = dw; bt.cost = cst;
+    bt.want = POYB200_WANT_MEDIAN | POYB200_WANT_BITSETS;
+    bt.median = out; bt.out_stride = stride; bt.out_len = olen;
+    bt.bits_a = out + (size_t) n * stride; bt.bits_b = bt.bits_a + (size_t) n * bstride;
+    bt.bits_wg = bt.bits_b + (size_t) n * bstride; bt.bits_stride = bstride;
+    int rc = (c->cost_model_type == 1) ? poyb200_batch_align_affine_3(ctx, &bt) : poyb200_batch_align_2(ctx, &bt);
+    if (rc == POYB200_OK)
+        for (int p = 0; p < n; p++) {
+            seqt q;
+            Seq_custom_val(q, Field(median, p));
+            fill_seq(q, out + ((size_t) p + 1) * stride, olen[4 * p]);
+        }
+    poyb200_host_free(pool);
+    free(off); free(len); free(pr);
+    if (rc != POYB200_OK) { poyb200_host_free(out); free(cst); free(olen); fail_with_ctx("poyb200_batch_median"); }
+    /* from here on the OCaml heap is allocated; no raw `struct seq` pointer is live any more */
+    costs = caml_alloc_tuple(n);
+    lens = caml_alloc_tuple(n);
+    ba = caml_alloc_tuple(n);
+    bb = caml_alloc_tuple(n);
+    bm = caml_alloc_tuple(n);
+    for (int p = 0; p < n; p++) {
+        const int cols = olen[4 * p + 2], nb = (cols + 7) / 8;
+        Store_field(costs, p, Val_int(cst[p]));
+        Store_field(lens, p, Val_int(cols));
+        const uint8_t *rows[3] = {bt.bits_a + (size_t) p * bstride, bt.bits_b + (size_t) p * bstride,
+                                  bt.bits_wg + (size_t) p * bstride};
+        value dst[3] = {ba, bb, bm};
+        for (int k = 0; k < 3; k++) {
+            str = caml_alloc_string(nb);
+            bitset_of_row(rows[k], bstride, cols, Bytes_val(str), nb);
+            Store_field(dst[k], p, str);
+        }
+    }
+    poyb200_host_free(out);
+    free(cst); free(olen);
+    res = caml_alloc_tuple(5);
+    Store_field(res, 0, costs); Store_field(res, 1, lens); Store_field(res, 2, ba); Store_field(res, 3, bb);
+    Store_field(res, 4, bm);
+    CAMLreturn(res);
+}
+
+/* external batch_closest : s array -> int array -> int array -> Cost_matrix.Two_D.m -> s array -> int array
+ *   = "poyb200_CAML_batch_closest"
+ * Sequence.Align.closest s1 s2 (src/sequence.ml:967-1033) for every pair (s1 = pairs.(2p), s2 = pairs.(2p+1)) whose
+ * early exits (empty s2, s1 = s2) the caller has already taken: fills `out.(p)` (capacity >= len a + len b + 2) with the
+ * closest sequence and returns the alignment costs (`cst` of align_2; the re-costing of :1026 is a batch_cost_2 call). */
+value poyb200_CAML_batch_closest(value seqs, value pairs, value deltaw, value cm, value outv) {
+    CAMLparam5(seqs, pairs, deltaw, cm, outv);
+    CAMLlocal1(costs);
+    const int ns = (int) Wosize_val(seqs), n = (int) Wosize_val(pairs) / 2;
+    struct cm *c = Cost_matrix_struct(cm);
+    poyb200_ctx *ctx = ctx_for(c);
+    int64_t *off = (int64_t *) malloc(sizeof(int64_t) * (size_t) (ns + 1));
+    int32_t *len = (int32_t *) malloc(sizeof(int32_t) * (size_t) (ns + 1));
+    int32_t *pr = (int32_t *) malloc(sizeof(int32_t) * 3 * (size_t) (n + 1)), *dw = pr + 2 * (size_t) (n + 1);
+    size_t total = 0;
+    uint8_t *pool = pool_of(seqs, ns, off, len, &total);
+    int maxcap = 16;
+    for (int p = 0; p < 2 * n; p++) pr[p] = Int_val(Field(pairs, p));
+    for (int p = 0; p < n; p++) {
+        dw[p] = Int_val(Field(deltaw, p));
+        const int cap = len[pr[2 * p]] + len[pr[2 * p + 1]] + 2;
+        if (cap > maxcap) maxcap = cap;
+    }
+    const int64_t stride = (maxcap + 15) & ~15;
+    uint8_t *out = (uint8_t *) poyb200_host_alloc((size_t) n * (size_t) stride + 16);
+    int32_t *cst = (int32_t *) malloc(sizeof(int32_t) * (size_t) (n + 1));
+    int32_t *olen = (int32_t *) malloc(sizeof(int32_t) * 4 * (size_t) (n + 1));
+    poyb200_batch bt = {0};
+    bt.pool = pool; bt.pool_bytes = total; bt.seq_off = off; bt.seq_len = len; bt.n_seqs = ns;
+    bt.pairs = pr; bt.n_pairs = n; bt.deltaw = dw; bt.cost = cst;
+    bt.want = POYB200_WANT_CLOSEST;
+    bt.median = out; bt.out_stride = stride; bt.out_len = olen;
+    int rc = (c->cost_model_type == 1) ? poyb200_batch_align_affine_3(ctx, &bt) : poyb200_batch_align_2(ctx, &bt);
+    if (rc == POYB200_OK)
+        for (int p = 0; p < n; p++) {
+            seqt q;
+            Seq_custom_val(q, Field(outv, p));
+            fill_seq(q, out + ((size_t) p + 1) * stride, olen[4 * p]);
+        }
+    poyb200_host_free(pool);
+    poyb200_host_free(out);
+    free(off); free(len); free(pr); free(olen);
+    if (rc != POYB200_OK) { free(cst); fail_with_ctx("poyb200_batch_closest"); }
+    costs = caml_alloc_tuple(n);
+    for (int p = 0; p < n; p++) Store_field(costs, p, Val_int(cst[p]));
+    free(cst);
+    CAMLreturn(costs);
+}
