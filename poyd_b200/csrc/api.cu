@@ -111,6 +111,7 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     int trace_threads_per_sm = 512;
+    int tb_block = 128;    // threads per block of the traceback kernels (POYB200_TB_BLOCK: 32, 64 or 128)
     int allow_noeb = 1;   // POYB200_NOEB=0 disables the no-gap-bit fast path of the affine stripe kernels
     int allow_fast = 1;   // POYB200_FAST=0: no aff_fast_kernel, every batch goes to aff_stripe_kernel
     int custom_tail = 0;  // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
@@ -266,6 +267,10 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_FAST")) ctx->allow_fast = atoi(s);
     if (const char *s = getenv("POYB200_OVERLAP_TB")) ctx->overlap_tb = atoi(s) != 0;
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
+    if (const char *s = getenv("POYB200_TB_BLOCK")) {
+        const int v = atoi(s);
+        if (v == 32 || v == 64 || v == 128) ctx->tb_block = v;
+    }
     if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
     if (const char *s = getenv("POYB200_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(s));
     *out = ctx;
@@ -797,17 +802,23 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         const int nt = (int) (ch.end - ch.begin);
         // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
         // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
-        const int max_blocks = ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / 128);
+        // Block size of the walkers (POYB200_TB_BLOCK, default 128).  Measured: 32-, 64- and 128-thread blocks give the same
+        // step time (55.4-55.6 ms per 1 M pairs), and so do 384..512 walkers per SM -- the device timeline (POYB200_TRACE=3)
+        // shows why: a traceback that shares the SMs with a fill takes registers from it (the fill drops from 3 to 1-2
+        // CTAs per SM), so fill + traceback add up whichever way they are interleaved (profiles/README.md).
+        const int tb_block = ctx->tb_block;
+        const int wpb = tb_block / 32;
+        const int max_blocks = ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / tb_block);
         // walkers per warp: 32 when the batch fills the grid, fewer (down to 1) when it does not
-        int wpw = (nt + max_blocks * 4 - 1) / (max_blocks * 4);
+        int wpw = (nt + max_blocks * wpb - 1) / (max_blocks * wpb);
         wpw = std::min(32, std::max(1, wpw));
-        const int blocks = std::min((nt + 4 * wpw - 1) / (4 * wpw), max_blocks);
+        const int blocks = std::min((nt + wpb * wpw - 1) / (wpb * wpw), max_blocks);
         if (affine)
-            aff_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                           next_counter(ctx), wpw);
+            aff_traceback_kernel<<<blocks, tb_block, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                                                                next_counter(ctx), wpw);
         else
-            lin_traceback_kernel<<<blocks, 128, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                           next_counter(ctx), wpw);
+            lin_traceback_kernel<<<blocks, tb_block, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                                                                next_counter(ctx), wpw);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));
@@ -877,6 +888,17 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
         }
         ms[0] += a;
         ms[1] += b;
+        if (getenv("POYB200_TRACE") && atoi(getenv("POYB200_TRACE")) >= 3) {
+            // device timeline of the chunk relative to the first fill: [fill start, fill end] [traceback start, traceback end]
+            float f0 = 0.f, f1 = 0.f, t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&f0, ctx->chunk_ev[0], ctx->chunk_ev[4 * c]);
+            cudaEventElapsedTime(&f1, ctx->chunk_ev[0], ctx->chunk_ev[4 * c + 1]);
+            if (bt) {
+                cudaEventElapsedTime(&t0, ctx->chunk_ev[0], ctx->chunk_ev[4 * c + 2]);
+                cudaEventElapsedTime(&t1, ctx->chunk_ev[0], ctx->chunk_ev[4 * c + 3]);
+            }
+            fprintf(stderr, "[poyb200]   chunk %zu: fill %.2f..%.2f  traceback %.2f..%.2f ms\n", c, f0, f1, t0, t1);
+        }
     }
     return POYB200_OK;
 }
