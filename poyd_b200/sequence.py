@@ -257,7 +257,7 @@ class Align:
         self._check(self.L.poyb200_batch_align_2(self.h, C.byref(b)))
         return res
 
-    def closest(self, pool: SeqPool, pairs) -> List[np.ndarray]:
+    def closest(self, pool: SeqPool, pairs, prechecked: bool = False) -> List[np.ndarray]:
         """``Sequence.Align.closest s1 s2 cm m`` (src/sequence.ml:967-1033) for every pair (s1 = pair[0], s2 = pair[1]):
         the sequence of s2's elements closest to s1's along their alignment, gaps removed.  The alignment, the
         column rule (``Cost_matrix.Two_D.get_closest``) and the compaction run in the traceback kernel
@@ -266,6 +266,9 @@ class Align:
         gap = self.cm.gap
         out: List[Optional[np.ndarray]] = [None] * len(pairs)
         todo = []
+        if prechecked:  # the caller has taken both early exits already (poyd_b200/tree.py does)
+            r = self.align_2(pool, pairs, WANT_CLOSEST)
+            return [r.get("median", q).copy() for q in range(len(pairs))]
         for k, (i, j) in enumerate(pairs):
             s1, s2 = pool.seq(int(i)), pool.seq(int(j))
             if np.all(s2 == gap):  # is_empty s2: (s2, 0)

@@ -260,7 +260,7 @@ class GpuEngine:
         """``Sequence.Align.closest parent mine`` for every pair, fused into the traceback kernel."""
         pool, pp = self._pool(store, pairs)
         self._note("closest", pool, pp, None if self.al.is_affine else self.al.deltaw_for(pool, pp))
-        return self.al.closest(pool, pp)
+        return self.al.closest(pool, pp, prechecked=True)
 
     def distance(self, store, pairs):
         """``SeqCS.DOS.distance`` (src/seqCS.ml:856-866): ``cost_2 ~deltaw:(max 8 |la - lb|)``."""
