@@ -119,7 +119,8 @@ struct poyb200_ctx {
     size_t chunk_pairs = 1u << 17;  // pairs per chunk (pipelining granularity of the one-shot calls)
     bool in_order = true;           // tasks[k].pair == k
     cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
-    DevBuf<uint8_t> d_dir2;        // second direction buffer: traceback of chunk k overlaps the fill of chunk k+1
+    DevBuf<uint8_t> d_dir2, d_dir3;  // further direction buffers: the traceback of chunk k runs under the fills of chunks k+1, k+2
+    int dir_buffers = 3;           // POYB200_DIR_BUFFERS: 2 or 3
     uint8_t *cur_dir = nullptr;
     bool overlap_tb = true;        // POYB200_OVERLAP_TB=0: fill and traceback strictly serial on one stream
     std::vector<cudaEvent_t> ev_fill, ev_tb;
@@ -259,7 +260,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // direction bands of one chunk: at most a third of the free HBM, capped at 48 GB
-    ctx->dir_budget = std::min<size_t>(free_b / 3, (size_t) 48 << 30);
+    ctx->dir_budget = std::min<size_t>(free_b / 4, (size_t) 40 << 30);  // up to three direction buffers of this size
     if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
     if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
     if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
@@ -267,6 +268,7 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     if (const char *s = getenv("POYB200_FAST")) ctx->allow_fast = atoi(s);
     if (const char *s = getenv("POYB200_OVERLAP_TB")) ctx->overlap_tb = atoi(s) != 0;
     if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
+    if (const char *s = getenv("POYB200_DIR_BUFFERS")) ctx->dir_buffers = (atoi(s) >= 3) ? 3 : 2;
     if (const char *s = getenv("POYB200_TB_BLOCK")) {
         const int v = atoi(s);
         if (v == 32 || v == 64 || v == 128) ctx->tb_block = v;
@@ -300,6 +302,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     for (auto &e : ctx->ev_fill) cudaEventDestroy(e);
     for (auto &e : ctx->ev_tb) cudaEventDestroy(e);
     ctx->d_dir2.release();
+    ctx->d_dir3.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -747,6 +750,7 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
         if (ctx->overlap_tb && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
+        if (ctx->overlap_tb && ctx->chunks.size() >= 3 && ctx->dir_buffers >= 3) CK(ctx->d_dir3.reserve(maxdir));
         CK(ctx->d_outlen.reserve(4 * n + 4));
         const size_t ob = n * (size_t) ctx->dstride + 16;
         if (b->want & (POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST)) CK(ctx->d_out[0].reserve(ob));
@@ -777,10 +781,12 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     const Chunk &ch = ctx->chunks[ci];
     const bool two = bt && ctx->overlap_tb && ctx->chunks.size() >= 2;
     cudaStream_t s_tb = two ? ctx->s_tb : ctx->stream;
-    ctx->cur_dir = (two && (ci & 1)) ? ctx->d_dir2.p : ctx->d_dir.p;
+    const int nbuf = !two ? 1 : (ctx->dir_buffers >= 3 && ctx->chunks.size() >= 3) ? 3 : 2;
+    uint8_t *const bufs[3] = {ctx->d_dir.p, ctx->d_dir2.p, ctx->d_dir3.p};
+    ctx->cur_dir = bufs[ci % nbuf];
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride};
-    if (two && ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - 2], 0));  // the buffer is free again
+    if (two && ci >= (size_t) nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - nbuf], 0));  // the buffer is free again
     if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk
     size_t k = ch.begin;
