@@ -424,7 +424,8 @@ def main():
     launches = al.launch_count() - launches0
     dev_ms = e0.elapsed_time(e1) / args.steps
     f_ms, t_ms = al.last_run_ms()  # the last pass, per phase
-    fill_launches = max(1, (launches // args.steps) // 2)
+    # launches per chunk: affine = aff_fast_kernel + aff_stripe_kernel over the declined list + traceback; linear = fill + traceback
+    fill_launches = max(1, (launches // args.steps) // (3 if wl_mode == 3 else 2))
     dev_ms_max = max_over_ranks(dev_ms)
     total_cells_all = sum_over_ranks(float(cells))
     value = total_cells_all / (dev_ms_max * 1e-3) * 1e-9
