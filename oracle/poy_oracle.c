@@ -6,10 +6,12 @@
  * rows, this file describes the visited region as a diagonal stripe dlo <= j-i <= dhi plus per-cell rules,
  * which is also how the CUDA kernels see it.  Each function cites the reference lines it restates.
  *
- * PARITY PINNED: tests/test_oracle_vs_reference.py checks every entry point here bit-for-bit (costs,
+ * PARITY PINNED: tests/test_oracle.py checks every entry point here bit-for-bit (costs,
  * direction-dependent outputs, medians) against oracle/_ref/libpoyref.so, i.e. the unmodified
  * /root/reference/src/algn.c compiled in this container, on seeded random inputs; the committed
- * tests/golden/ vectors were produced by that compiled reference (tests/golden/make_golden.py).
+ * tests/golden/ vectors were produced by that compiled reference (tests/golden/make_golden.py).  The checkers are also
+ * pinned against numbers the reference's authors recorded: driven by poyd_b200/tree.py they reproduce the 52 tree costs of
+ * the reference's test/cost_tests (tests/golden/trees/tree_costs.npz, tests/test_tree.py).
  * The reference repository itself holds no per-pair golden vectors for this path.
  */
 #include <stdint.h>
