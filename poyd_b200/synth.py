@@ -123,14 +123,15 @@ def ragged_batch(n_pairs: int, max_len: int = 300, seed: int = 7, alphabet: str 
     return pool, pairs
 
 
-def taxa_on_random_tree(n_taxa: int, length: int = 1500, seed: int = 5, subst: float = 0.03, indel: float = 0.005):
+def taxa_on_random_tree(n_taxa: int, length: int = 1500, seed: int = 5, subst: float = 0.03, indel: float = 0.005,
+                        alphabet: str = "dna"):
     """Leaf sequences of a random binary tree (configs[4] of BASELINE.json: "500-taxon x 1.5 kb unaligned DNA"): a
     uniform root sequence evolves down a random-join topology, every branch applying `subst` substitutions and `indel`
     single-base indels.  Returns {taxon code 1..n: [sequence with its leading gap]} (one locus per taxon)."""
     rng = np.random.default_rng(seed)
-    bases = np.array([1, 2, 4, 8], np.uint8)
+    bases, gap = (np.array([1, 2, 4, 8], np.uint8), DNA_GAP) if alphabet == "dna" else (np.arange(1, 21, dtype=np.uint8), PROTEIN_GAP)
     # random topology by successive splits: a list of current tips, each a sequence; pick one, replace by two children
-    tips = [bases[rng.integers(0, 4, size=length)]]
+    tips = [bases[rng.integers(0, len(bases), size=length)]]
     while len(tips) < n_taxa:
         k = int(rng.integers(0, len(tips)))
         parent = tips.pop(k)
@@ -138,4 +139,4 @@ def taxa_on_random_tree(n_taxa: int, length: int = 1500, seed: int = 5, subst: f
             flat, lens = _mutate_rows(rng, parent[None, :], bases, subst, indel)
             tips.append(flat[:int(lens[0])])
     perm = rng.permutation(n_taxa)
-    return {i + 1: [np.concatenate([[DNA_GAP], tips[int(p)]]).astype(np.uint8)] for i, p in enumerate(perm)}
+    return {i + 1: [np.concatenate([[gap], tips[int(p)]]).astype(np.uint8)] for i, p in enumerate(perm)}

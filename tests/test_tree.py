@@ -118,8 +118,9 @@ def test_wagner_gpu_matches_cpu_checker():
     from poyd_b200 import synth
 
     oracle.build(ref=True)
-    for cm in (CM.default_nucleotides(), CM.nucleotides(2, 1, 1)):
-        leaves = synth.taxa_on_random_tree(24, 400, seed=11, subst=0.05, indel=0.01)
+    # DNA linear, DNA affine, and protein (no combinations: the other branch of Sequence.Align.closest, full-matrix linear fills)
+    for cm, alphabet in ((CM.default_nucleotides(), "dna"), (CM.nucleotides(2, 1, 1), "dna"), (CM.default_aminoacids(), "protein")):
+        leaves = synth.taxa_on_random_tree(24, 400 if alphabet == "dna" else 150, seed=11, subst=0.05, indel=0.01, alphabet=alphabet)
         g = T.GpuEngine(cm, device=0)
         try:
             evg = T.Evaluator(g, cm)
