@@ -163,3 +163,16 @@ def test_spr_neighbourhood_in_lockstep_cpu_checker(checker_factory):
         for v in cold.singles:
             assert all(np.array_equal(x, y) for x, y in zip(r.singles[v], cold.singles[v]))
     assert lock_calls * 5 < solo_calls
+
+
+def test_read_fasta_follows_the_reference_parser(tmp_path):
+    """Parser.Fasta for nucleotides (src/parser.ml:220-392): names trimmed, case folded, gaps dropped, IUPAC sets,
+    fragments at '#', a leading gap on every fragment, taxa in file order."""
+    p = tmp_path / "x.fas"
+    p.write_text(">Alpha   \nacg-T\nNN#ry\n\n>Beta\nAC\nGT#K?\n")
+    taxa = T.read_fasta(str(p))
+    assert [n for n, _ in taxa] == ["Alpha", "Beta"]
+    assert [f.tolist() for f in taxa[0][1]] == [[16, 1, 2, 4, 8, 15, 15], [16, 5, 10]]
+    assert [f.tolist() for f in taxa[1][1]] == [[16, 1, 2, 4, 8], [16, 12, 31]]
+    # trees: blanks or commas, annotations ignored, several trees per file
+    assert T.parse_trees("(A (B C))[12.] (A,(B,C));") == [["A", ["B", "C"]], ["A", ["B", "C"]]]
