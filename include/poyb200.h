@@ -110,8 +110,30 @@ typedef struct poyb200_batch {
 
 typedef struct poyb200_ctx poyb200_ctx;
 
-/* device < 0: keep the calling thread's current CUDA device. */
+/* Every tunable of a context.  Fill it with poyb200_default_config, change what you need, pass it to
+ * poyb200_create_ex; the library reads no environment variables.  struct_bytes versions the struct: a caller built
+ * against an older header passes a shorter one and the fields it does not know keep their defaults. */
+typedef struct poyb200_config {
+    uint32_t struct_bytes;             /* sizeof(poyb200_config) as the caller knows it */
+    int32_t force_generic;             /* 1: every pair takes the generic (any-shape) kernels; default 0 */
+    int32_t allow_fast;                /* 0: no aff_fast_kernel (pairs without gap bits take aff_stripe_kernel); default 1 */
+    int32_t allow_noeb;                /* 0: no no-gap-bit variant of aff_stripe_kernel either; default 1 */
+    int32_t overlap_traceback;         /* 0: traceback on the compute stream, one direction buffer; default 1 */
+    int32_t dir_buffers;               /* 2 or 3 direction-band buffers; default 3 */
+    int32_t traceback_threads_per_sm;  /* resident traceback walkers per SM; default 512 */
+    int32_t traceback_block;           /* 32, 64 or 128 threads per traceback CTA; default 128 */
+    int32_t traceback_priority;        /* 1: the traceback stream outranks the fill stream; default 1 */
+    int32_t chunk_pairs;               /* pairs per chunk of a one-shot call (pipelining granularity); default 65536 */
+    int32_t host_threads;              /* planner threads, 0 = min(16, hardware threads); default 0 */
+    int32_t timing;                    /* 1: CUDA events per chunk for poyb200_last_run_ms; default 1 */
+    int32_t trace;                     /* stderr timeline of every one-shot call: 0 off, 1 host, 2 + downloads, 3 + device */
+    int64_t dir_budget_bytes;          /* size limit of one direction buffer, 0 = a quarter of the free HBM, <= 40 GB */
+} poyb200_config;
+void poyb200_default_config(poyb200_config *cfg);
+
+/* device < 0: keep the calling thread's current CUDA device.  poyb200_create = poyb200_create_ex with the defaults. */
 int poyb200_create(int device, poyb200_ctx **out);
+int poyb200_create_ex(int device, const poyb200_config *cfg, poyb200_ctx **out);
 void poyb200_destroy(poyb200_ctx *ctx);
 const char *poyb200_last_error(const poyb200_ctx *ctx);
 const char *poyb200_version(void);

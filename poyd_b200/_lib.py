@@ -28,6 +28,33 @@ class Batch(C.Structure):
                 ("bits_wg", C.c_void_p), ("bits_stride", C.c_int64)]
 
 
+class Config(C.Structure):
+    """poyb200_config (include/poyb200.h): every tunable of a context."""
+    _fields_ = [("struct_bytes", C.c_uint32)] + [(n, C.c_int32) for n in (
+        "force_generic", "allow_fast", "allow_noeb", "overlap_traceback", "dir_buffers", "traceback_threads_per_sm",
+        "traceback_block", "traceback_priority", "chunk_pairs", "host_threads", "timing", "trace")] + [
+        ("dir_budget_bytes", C.c_int64)]
+
+
+def make_config(overrides=None) -> "Config":
+    """Defaults of the library, then the `key=value,...` pairs of the POYB200_CONFIG environment variable (a convenience of
+    this Python binding for tools and experiments -- the C library itself reads no environment), then `overrides`."""
+    cfg = Config()
+    lib().poyb200_default_config(C.byref(cfg))
+    names = {n for n, _ in Config._fields_} - {"struct_bytes"}
+    items = {}
+    for part in os.environ.get("POYB200_CONFIG", "").split(","):
+        if "=" in part:
+            k, v = part.split("=", 1)
+            items[k.strip()] = int(v)
+    items.update(overrides or {})
+    for k, v in items.items():
+        if k not in names:
+            raise KeyError(f"poyb200_config has no field {k!r}")
+        setattr(cfg, k, int(v))
+    return cfg
+
+
 class CM3(C.Structure):
     _fields_ = [("lcm", C.c_int32), ("gap", C.c_int32), ("cost", i32p), ("median", u8p)]
 
@@ -40,7 +67,7 @@ class Batch3(C.Structure):
 
 
 EXPORTS = [
-    "poyb200_create", "poyb200_destroy", "poyb200_last_error", "poyb200_version", "poyb200_set_cm",
+    "poyb200_create", "poyb200_create_ex", "poyb200_default_config", "poyb200_destroy", "poyb200_last_error", "poyb200_version", "poyb200_set_cm",
     "poyb200_host_alloc", "poyb200_host_free", "poyb200_batch_cost_2", "poyb200_batch_align_2",
     "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3", "poyb200_batch_median_2", "poyb200_stage",
     "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
@@ -60,6 +87,9 @@ def lib() -> C.CDLL:
             f"{SO} is missing: build it with `python -m poyd_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
     L = C.CDLL(SO)
     L.poyb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.poyb200_create_ex.argtypes = [C.c_int, C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.poyb200_default_config.argtypes = [C.POINTER(Config)]
+    L.poyb200_default_config.restype = None
     L.poyb200_destroy.argtypes = [C.c_void_p]
     L.poyb200_destroy.restype = None
     L.poyb200_last_error.argtypes = [C.c_void_p]

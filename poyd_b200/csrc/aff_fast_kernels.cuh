@@ -30,7 +30,7 @@ __host__ __device__ constexpr int fast_lut_slot(int code) {
 // tabR, tabC, LUT of the ring blocks; LUT, prepend and gap tables of the boundary phase; one mbarrier per group
 constexpr int FAST_SCR_INTS = 16;  // >= 2 K
 constexpr int FAST_TABLE_BYTES =
-    2 * 256 * 8 + 16 * FAST_LUT_ROW + STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * 8 + STRIPE_WARPS * 4 * FAST_SCR_INTS * 4;
+    2 * 256 * 8 + 16 * FAST_LUT_ROW + STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * STAGE_BAR_BYTES + STRIPE_WARPS * 4 * FAST_SCR_INTS * 4;
 // The unchecked blocks read codes past an operand's end (rows up to Q G / 2 + D - 2 past it, columns up to G K + D - 1):
 // every staged operand gets that much private slack, so the stray reads never touch another warp's buffers.
 __host__ __device__ constexpr int fast_operand_pad(int K, int G) { return (K * G + 8 + 15) & ~15; }
@@ -208,7 +208,8 @@ struct AffFast {
 template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     aff_fast_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm, const uint8_t *__restrict__ pool, uint8_t *__restrict__ dir,
-                    int *__restrict__ out_cost, int seq_bytes, int *work_counter, int *slow_list, int *slow_count, int keep_mask, int one) {
+                    int *__restrict__ out_cost, int seq_bytes, int nslots, int *work_counter, int *slow_list, int *slow_count, int keep_mask,
+                    int one) {
     // keep_mask = ~3 and one = 1 arrive as arguments so that they live in registers (see AffFast::cell, fma_add)
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
@@ -222,11 +223,10 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     uint8_t *s_lut2 = smem + 2 * 256 * 8 + 16 * FAST_LUT_ROW;
     int *s_prep = reinterpret_cast<int *>(s_lut2 + STRIPE_LUT_BYTES);
     int *s_get = s_prep + 32;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_get + 32);
+    StageBars *s_bar = reinterpret_cast<StageBars *>(s_get + 32);  // one staging ring per group (staging.cuh)
     int *s_scr = reinterpret_cast<int *>(s_bar + STRIPE_WARPS * 4);  // FAST_SCR_INTS per group
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_scr + STRIPE_WARPS * 4 * FAST_SCR_INTS);
-    if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
-    uint32_t bar_phase = 0;
+    if (threadIdx.x < STRIPE_WARPS * GPW) StageRing<G>::init_bars(&s_bar[threadIdx.x]);
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
         s_lut[fast_lut_slot(k >> 4) * (FAST_LUT_ROW / 4) + fast_lut_slot(k)] = c4;
@@ -244,14 +244,21 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     const int warp_in_block = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
     const int grp = lane32 / G, lane = lane32 % G;
     const int op_stride = seq_bytes + fast_operand_pad(K, G);
-    uint8_t *my_seq = s_seq + (size_t) ((warp_in_block * GPW + grp) * 2) * op_stride;
+    StageRing<G> ring;
+    ring.attach(&s_bar[warp_in_block * GPW + grp], s_seq + (size_t) ((warp_in_block * GPW + grp) * 2 * nslots) * op_stride, op_stride,
+                nslots, lane);
     int *my_scr = s_scr + (warp_in_block * GPW + grp) * FAST_SCR_INTS;
+    const int nbatches = (ntasks + GPW - 1) / GPW;
 
-    for (;;) {
-        int batch = 0;
-        if (lane32 == 0) batch = atomicAdd(work_counter, 1);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch * GPW >= ntasks) break;
+    int slot = 0;
+    int batch = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+    if (batch >= 0) ring.produce_task(0, tasks, ntasks, batch * GPW + grp, pool, 16);
+    while (batch >= 0) {
+        int next = -1;
+        if (nslots == 2) {  // the operands of the next batch travel under this one
+            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            if (next >= 0) ring.produce_task(slot ^ 1, tasks, ntasks, next * GPW + grp, pool, 16);
+        }
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
         Task t;
@@ -259,16 +266,15 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
         else { t = Task{}; t.lr = 1; t.lc = 1; t.dhi = -1; t.dlo = -39; }
         const int nr = t.lr - 1, nc = t.lc - 1;
         const int d0 = t.dhi + 2 - Q * G;
+        ring.wait_full(slot);
+        uint8_t *my_seq = ring.rows(slot);
+      do {  // one pass; `break` hands the batch to aff_stripe_kernel
         // spare diagonals below dlo need the left-edge rule inside the stripe: not here
         const bool low = valid && (t.dlo - d0 > 0);
         if (__any_sync(0xffffffffu, low)) {
             if (lane32 == 0) slow_list[atomicAdd(slow_count, 1)] = batch;
-            continue;
+            break;
         }
-        __syncwarp();
-        stage_pair<G>(my_seq, my_seq + op_stride, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
-                      &s_bar[warp_in_block * GPW + grp], bar_phase, 16);
-        __syncwarp();
         // gap bits beyond the leading element of either operand (scanned in shared memory, 4 bytes per load)
         int gapbits = 0;
         if (valid) {
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
         }
         if (__any_sync(0xffffffffu, gapbits != 0)) {
             if (lane32 == 0) slow_list[atomicAdd(slow_count, 1)] = batch;
-            continue;
+            break;
         }
 
         const int u_first = (-d0) >> 1;  // first double step: t = 2u + d0 in {-1, 0}
@@ -355,38 +361,40 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
             if (BT && nr == 0 && nc == 0) result = 0;
             out_cost[t.pair] = result;
         }
+      } while (0);
         __syncwarp();
+        ring.release(slot);  // this lane's last read of the staged operands is behind it
+        if (nslots == 1) {
+            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            if (next >= 0) ring.produce_task(0, tasks, ntasks, next * GPW + grp, pool, 16);
+        } else {
+            slot ^= 1;
+        }
+        batch = next;
     }
 }
 
-#ifndef POYB200_KERNELS_ONLY
+#ifdef POYB200_DEFINE_AFF_FAST  // the translation unit that owns these kernels (k_aff_fast.cu)
 template <int K, int G>
 static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
                                      int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
                                      cudaStream_t stream) {
     constexpr int GPW = 32 / G;
-    const size_t smem = FAST_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * (seq_bytes + fast_operand_pad(K, G));
     const int nbatches = (n + GPW - 1) / GPW;
     auto kern = bt ? aff_fast_kernel<K, G, true> : aff_fast_kernel<K, G, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    size_t smem = 0;
+    int nslots = 1, per_sm = 1;
+    cudaError_t e = stage_ring_config(kern, FAST_TABLE_BYTES, (size_t) STRIPE_WARPS * GPW * 2 * (seq_bytes + fast_operand_pad(K, G)),
+                                      STRIPE_WARPS * 32, smem, nslots, per_sm);
     if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STRIPE_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, work_counter, slow_list, slow_count, ~3, 1);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, work_counter, slow_list, slow_count,
+                                                      ~3, 1);
     return cudaGetLastError();
 }
 
-// True when the class has a fast kernel (ring of 8 slots: K <= 6).
-static inline bool fast_has_shape(uint32_t klass) {
-    const int s = (int) klass - 1;
-    return s >= 0 && s < N_AFF_SHAPES && AFF_SHAPES[s].K <= 6;
-}
-
-static inline cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
+cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                                       int *cost, int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
                                       cudaStream_t stream) {
     switch (klass - 1) {
@@ -400,6 +408,6 @@ static inline cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tas
     }
 }
 
-#endif  // POYB200_KERNELS_ONLY
+#endif  // POYB200_DEFINE_AFF_FAST
 
 }  // namespace poyb200

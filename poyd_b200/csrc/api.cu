@@ -11,13 +11,7 @@
 #include <vector>
 
 #include "../../include/poyb200.h"
-#include "generic_kernels.cuh"
-#include "peak.cuh"
-#include "stripe_kernels.cuh"
-#include "aff_fast_kernels.cuh"
-#include "lin_stripe_kernels.cuh"
-#include "trace_kernels.cuh"
-#include "cube_kernels.cuh"
+#include "launch.h"
 
 using namespace poyb200;
 
@@ -110,11 +104,8 @@ struct poyb200_ctx {
     size_t dir_budget = 0;
     int state_stride = 0;
     int stripe_seq_bytes = 16;
-    int trace_threads_per_sm = 512;
-    int tb_block = 128;    // threads per block of the traceback kernels (POYB200_TB_BLOCK: 32, 64 or 128)
-    int allow_noeb = 1;   // POYB200_NOEB=0 disables the no-gap-bit fast path of the affine stripe kernels
-    int allow_fast = 1;   // POYB200_FAST=0: no aff_fast_kernel, every batch goes to aff_stripe_kernel
-    int custom_tail = 0;  // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
+    poyb200_config cfg{};  // every tunable of the context (include/poyb200.h); fixed at creation
+    int custom_tail = 0;   // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int host_threads = 8;
     size_t chunk_pairs = 1u << 16;  // pairs per chunk (pipelining granularity of the one-shot calls); with three direction
                                     // buffers 65 536 and 131 072 give the same device time, and the smaller chunk lets the
@@ -122,13 +113,10 @@ struct poyb200_ctx {
     bool in_order = true;           // tasks[k].pair == k
     cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
     DevBuf<uint8_t> d_dir2, d_dir3;  // further direction buffers: the traceback of chunk k runs under the fills of chunks k+1, k+2
-    int dir_buffers = 3;           // POYB200_DIR_BUFFERS: 2 or 3
     uint8_t *cur_dir = nullptr;
-    bool overlap_tb = true;        // POYB200_OVERLAP_TB=0: fill and traceback strictly serial on one stream
     std::vector<cudaEvent_t> ev_fill, ev_tb;
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_done, ev_pool;
-    bool allow_stripe = true;  // POYB200_FORCE_GENERIC=1 routes everything through the generic kernels (tests)
     // 3-D
     bool has_cm3 = false;
     DevCM3 dcm3{};
@@ -140,7 +128,6 @@ struct poyb200_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;  // 3 per chunk: before fill, after fill, after traceback
     size_t timed_chunks = 0;
-    bool timing = true;                 // POYB200_TIMING=0 drops the per-chunk events
 };
 
 #define CK(call)                                                                           \
@@ -222,12 +209,44 @@ extern "C" int64_t poyb200_cells_affine(int32_t la, int32_t lb) {
 // ---------------------------------------------------------------------------------------------------------
 extern "C" const char *poyb200_version(void) { return "poyb200 0.1 (sm_100a)"; }
 
-extern "C" int poyb200_create(int device, poyb200_ctx **out) {
+extern "C" void poyb200_default_config(poyb200_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_bytes = (uint32_t) sizeof *cfg;
+    cfg->force_generic = 0;
+    cfg->allow_fast = 1;
+    cfg->allow_noeb = 1;
+    cfg->overlap_traceback = 1;
+    cfg->dir_buffers = 3;
+    cfg->traceback_threads_per_sm = 512;
+    cfg->traceback_block = 128;
+    cfg->traceback_priority = 1;
+    cfg->chunk_pairs = 1 << 16;
+    cfg->host_threads = 0;
+    cfg->timing = 1;
+    cfg->trace = 0;
+    cfg->dir_budget_bytes = 0;
+}
+
+extern "C" int poyb200_create_ex(int device, const poyb200_config *user, poyb200_ctx **out) {
     if (!out) return POYB200_EINVAL;
     *out = nullptr;
+    poyb200_config cfg;
+    poyb200_default_config(&cfg);
+    if (user) {
+        // a caller built against an older header passes a shorter struct: the fields it does not know keep their defaults
+        if (user->struct_bytes < sizeof(uint32_t) || user->struct_bytes > sizeof cfg) return POYB200_EINVAL;
+        memcpy(&cfg, user, user->struct_bytes);
+        cfg.struct_bytes = (uint32_t) sizeof cfg;
+    }
+    if (cfg.dir_buffers != 2 && cfg.dir_buffers != 3) return POYB200_EINVAL;
+    if (cfg.traceback_block != 32 && cfg.traceback_block != 64 && cfg.traceback_block != 128) return POYB200_EINVAL;
+    if (cfg.traceback_threads_per_sm < cfg.traceback_block || cfg.chunk_pairs < 1 || cfg.host_threads < 0 || cfg.dir_budget_bytes < 0)
+        return POYB200_EINVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return POYB200_ECUDA;  // no CPU fallback
     poyb200_ctx *ctx = new poyb200_ctx();
+    ctx->cfg = cfg;
     if (device >= 0) {
         if (cudaSetDevice(device) != cudaSuccess) {
             delete ctx;
@@ -248,38 +267,24 @@ extern "C" int poyb200_create(int device, poyb200_ctx **out) {
     cudaStreamCreateWithFlags(&ctx->s_len, cudaStreamNonBlocking);
     {
         // The traceback stream outranks the compute stream: when a fill ends, the walkers of its chunk are placed before the
-        // CTAs of the next (persistent, SM-filling) fill, instead of waiting for that fill to drain.  POYB200_TB_PRIORITY=0
-        // switches it off.
+        // CTAs of the next (persistent, SM-filling) fill, instead of waiting for that fill to drain.
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        const char *pe = getenv("POYB200_TB_PRIORITY");
-        const bool want = !pe || atoi(pe) != 0;
-        if (cudaStreamCreateWithPriority(&ctx->s_tb, cudaStreamNonBlocking, want ? hi : lo) != cudaSuccess)
+        if (cudaStreamCreateWithPriority(&ctx->s_tb, cudaStreamNonBlocking, cfg.traceback_priority ? hi : lo) != cudaSuccess)
             cudaStreamCreateWithFlags(&ctx->s_tb, cudaStreamNonBlocking);
     }
     cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
-    ctx->host_threads = (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    ctx->host_threads = cfg.host_threads > 0 ? cfg.host_threads : (int) std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    ctx->chunk_pairs = (size_t) cfg.chunk_pairs;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // direction bands of one chunk: at most a third of the free HBM, capped at 48 GB
-    ctx->dir_budget = std::min<size_t>(free_b / 4, (size_t) 40 << 30);  // up to three direction buffers of this size
-    if (const char *s = getenv("POYB200_DIR_BUDGET_MB")) ctx->dir_budget = (size_t) atoll(s) << 20;
-    if (const char *s = getenv("POYB200_FORCE_GENERIC")) ctx->allow_stripe = (atoi(s) == 0);
-    if (const char *s = getenv("POYB200_TIMING")) ctx->timing = (atoi(s) != 0);
-    if (const char *s = getenv("POYB200_NOEB")) ctx->allow_noeb = atoi(s);
-    if (const char *s = getenv("POYB200_FAST")) ctx->allow_fast = atoi(s);
-    if (const char *s = getenv("POYB200_OVERLAP_TB")) ctx->overlap_tb = atoi(s) != 0;
-    if (const char *s = getenv("POYB200_TRACE_THREADS")) ctx->trace_threads_per_sm = atoi(s);
-    if (const char *s = getenv("POYB200_DIR_BUFFERS")) ctx->dir_buffers = (atoi(s) >= 3) ? 3 : 2;
-    if (const char *s = getenv("POYB200_TB_BLOCK")) {
-        const int v = atoi(s);
-        if (v == 32 || v == 64 || v == 128) ctx->tb_block = v;
-    }
-    if (const char *s = getenv("POYB200_CHUNK_PAIRS")) ctx->chunk_pairs = (size_t) std::max(1ll, atoll(s));
-    if (const char *s = getenv("POYB200_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(s));
+    // direction bands of one chunk: a quarter of the free HBM, capped at 40 GB (up to three buffers of this size)
+    ctx->dir_budget = cfg.dir_budget_bytes > 0 ? (size_t) cfg.dir_budget_bytes : std::min<size_t>(free_b / 4, (size_t) 40 << 30);
     *out = ctx;
     return POYB200_OK;
 }
+
+extern "C" int poyb200_create(int device, poyb200_ctx **out) { return poyb200_create_ex(device, nullptr, out); }
 
 extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     if (!ctx) return;
@@ -292,6 +297,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->tasks_tmp.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
     for (auto &b : ctx->d_out) b.release();
+    for (auto &b : ctx->d_bits) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->chunk_ev) cudaEventDestroy(e);
     for (auto &e : ctx->ev_done) cudaEventDestroy(e);
@@ -369,7 +375,19 @@ static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, 
 
 // Work counters: one zeroed int per persistent launch of a call (reset in bulk by reset_counters).
 constexpr size_t MAX_COUNTERS = 1 << 16;
-static int *next_counter(poyb200_ctx *ctx) { return ctx->d_counters.p + (ctx->counter_next++ % MAX_COUNTERS); }
+// A call that launches more than MAX_COUNTERS persistent kernels (tiny chunks) starts over on a re-zeroed array: the
+// memset is ordered on the compute stream, which every launch of the call is ordered after (fills run on it, tracebacks
+// wait for an event recorded on it), and a counter is only reused MAX_COUNTERS launches -- many chunks -- later.
+static int *next_counter(poyb200_ctx *ctx) {
+    if (ctx->counter_next == MAX_COUNTERS) {
+        cudaStreamSynchronize(ctx->s_tb);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemsetAsync(ctx->d_counters.p, 0, MAX_COUNTERS * sizeof(int), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->counter_next = 0;
+    }
+    return ctx->d_counters.p + ctx->counter_next++;
+}
 static int reset_counters(poyb200_ctx *ctx) {
     CK(ctx->d_counters.reserve(MAX_COUNTERS));
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, MAX_COUNTERS * sizeof(int), ctx->stream));
@@ -389,7 +407,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     if (klass != KLASS_GENERIC) {
         // pairs without gap bits take aff_fast_kernel; the batches it declines are listed for aff_stripe_kernel
         const int *list = nullptr, *count = nullptr;
-        if (affine && ctx->allow_fast && ctx->allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
+        if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
@@ -400,7 +418,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             count = cnt;
         }
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->allow_noeb, next_counter(ctx), list, count, ctx->stream);
+                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->cfg.allow_noeb, next_counter(ctx), list, count, ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -410,23 +428,14 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     const size_t nwarps = (size_t) blocks * warps_per_block;
     if (affine) {
         CK(ctx->d_aff_state.reserve(nwarps * ctx->state_stride));
-        if (bt)
-            aff_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
-                                                                      ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
-        else
-            aff_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p,
-                                                                       ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
+        CK(aff_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p, ctx->state_stride, ctx->cur_dir,
+                              ctx->d_costs.p, ctx->stream));
     } else {
         CK(ctx->d_lin_state.reserve(nwarps * ctx->state_stride));
-        if (bt)
-            lin_generic_kernel<true><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
-                                                                      ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
-        else
-            lin_generic_kernel<false><<<blocks, 128, 0, ctx->stream>>>(d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p,
-                                                                       ctx->state_stride, ctx->cur_dir, ctx->d_costs.p);
+        CK(lin_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p, ctx->state_stride, ctx->cur_dir,
+                              ctx->d_costs.p, ctx->stream));
     }
     ctx->launches++;
-    CK(cudaGetLastError());
     return POYB200_OK;
 }
 
@@ -549,7 +558,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     }
     if (!ctx->tasks.resize((size_t) b->n_pairs)) return fail(ctx, POYB200_ENOMEM, "pinned allocation of the task array failed");
     const DevCM dcm = ctx->dcm;
-    const bool allow_stripe = ctx->allow_stripe;
+    const bool allow_stripe = (!ctx->cfg.force_generic);
     parallel_for(NT, (size_t) b->n_pairs, [&](size_t lo, size_t hi, int slot) {
         Part pt;  // thread-local: the parts[] entries share cache lines
         struct Commit {
@@ -577,6 +586,10 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             if (affine) {
                 affine_band(t.lr - 1, t.lc - 1, t.dlo, t.dhi);
             } else {
+                if (b->deltaw[p] < 0 || b->deltaw[p] > (1 << 20)) {
+                    pt.err = POYB200_EINVAL;
+                    return;
+                }
                 LinBand lb2 = linear_band(t.lr, t.lc, b->deltaw[p]);
                 t.dlo = lb2.dlo;
                 t.dhi = lb2.dhi;
@@ -598,7 +611,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     int maxW = 1, max_stripe_len = 16;
     uint32_t k_or = 0, k_and = 0xffffffffu;
     for (auto &pt : parts) {
-        if (pt.err) return fail(ctx, POYB200_EINVAL, "pair index out of range");
+        if (pt.err) return fail(ctx, POYB200_EINVAL, "pair index out of range, or deltaw negative / absurdly large");
         maxcap = std::max(maxcap, pt.maxcap);
         maxW = std::max(maxW, pt.maxW);
         max_stripe_len = std::max(max_stripe_len, pt.max_stripe_len);
@@ -751,8 +764,8 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     for (auto &c : ctx->chunks) maxdir = std::max(maxdir, c.dir_bytes);
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
-        if (ctx->overlap_tb && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
-        if (ctx->overlap_tb && ctx->chunks.size() >= 3 && ctx->dir_buffers >= 3) CK(ctx->d_dir3.reserve(maxdir));
+        if (ctx->cfg.overlap_traceback && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
+        if (ctx->cfg.overlap_traceback && ctx->chunks.size() >= 3 && ctx->cfg.dir_buffers >= 3) CK(ctx->d_dir3.reserve(maxdir));
         CK(ctx->d_outlen.reserve(4 * n + 4));
         const size_t ob = n * (size_t) ctx->dstride + 16;
         if (b->want & (POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST)) CK(ctx->d_out[0].reserve(ob));
@@ -781,15 +794,15 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     const bool affine = (mode == MODE_COST_AFF || mode == MODE_ALIGN_AFF);
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
     const Chunk &ch = ctx->chunks[ci];
-    const bool two = bt && ctx->overlap_tb && ctx->chunks.size() >= 2;
+    const bool two = bt && ctx->cfg.overlap_traceback && ctx->chunks.size() >= 2;
     cudaStream_t s_tb = two ? ctx->s_tb : ctx->stream;
-    const int nbuf = !two ? 1 : (ctx->dir_buffers >= 3 && ctx->chunks.size() >= 3) ? 3 : 2;
+    const int nbuf = !two ? 1 : (ctx->cfg.dir_buffers >= 3 && ctx->chunks.size() >= 3) ? 3 : 2;
     uint8_t *const bufs[3] = {ctx->d_dir.p, ctx->d_dir2.p, ctx->d_dir3.p};
     ctx->cur_dir = bufs[ci % nbuf];
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride};
     if (two && ci >= (size_t) nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - nbuf], 0));  // the buffer is free again
-    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
+    if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk
     size_t k = ch.begin;
     while (k < ch.end) {
@@ -800,13 +813,13 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         if (rc) return rc;
         k = e;
     }
-    if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 1], ctx->stream));
+    if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 1], ctx->stream));
     if (bt) {
         if (two) {
             CK(cudaEventRecord(ctx->ev_fill[ci], ctx->stream));
             CK(cudaStreamWaitEvent(s_tb, ctx->ev_fill[ci], 0));
         }
-        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 2], s_tb));
+        if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 2], s_tb));
         const int nt = (int) (ch.end - ch.begin);
         // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
         // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
@@ -814,29 +827,24 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         // step time (55.4-55.6 ms per 1 M pairs), and so do 384..512 walkers per SM -- the device timeline (POYB200_TRACE=3)
         // shows why: a traceback that shares the SMs with a fill takes registers from it (the fill drops from 3 to 1-2
         // CTAs per SM), so fill + traceback add up whichever way they are interleaved (profiles/README.md).
-        const int tb_block = ctx->tb_block;
+        const int tb_block = ctx->cfg.traceback_block;
         const int wpb = tb_block / 32;
-        const int max_blocks = ctx->sm_count * std::max(1, ctx->trace_threads_per_sm / tb_block);
+        const int max_blocks = ctx->sm_count * std::max(1, ctx->cfg.traceback_threads_per_sm / tb_block);
         // walkers per warp: 32 when the batch fills the grid, fewer (down to 1) when it does not
         int wpw = (nt + max_blocks * wpb - 1) / (max_blocks * wpb);
         wpw = std::min(32, std::max(1, wpw));
         const int blocks = std::min((nt + wpb * wpw - 1) / (wpb * wpw), max_blocks);
-        if (affine)
-            aff_traceback_kernel<<<blocks, tb_block, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                                next_counter(ctx), wpw);
-        else
-            lin_traceback_kernel<<<blocks, tb_block, 0, s_tb>>>(ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                                                                next_counter(ctx), wpw);
+        CK(traceback_launch(affine, blocks, tb_block, ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                            next_counter(ctx), wpw, s_tb));
         ctx->launches++;
-        CK(cudaGetLastError());
-        if (ctx->timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));
+        if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));
     }
     CK(cudaEventRecord(ctx->ev_tb[ci], s_tb));  // chunk ci is complete
     return POYB200_OK;
 }
 
 static int prepare_events(poyb200_ctx *ctx) {
-    while (ctx->timing && ctx->chunk_ev.size() < 4 * ctx->chunks.size()) {
+    while (ctx->cfg.timing && ctx->chunk_ev.size() < 4 * ctx->chunks.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->chunk_ev.push_back(e);
@@ -848,7 +856,7 @@ static int prepare_events(poyb200_ctx *ctx) {
         ctx->ev_fill.push_back(e);
         ctx->ev_tb.push_back(f);
     }
-    ctx->timed_chunks = ctx->timing ? ctx->chunks.size() : 0;
+    ctx->timed_chunks = ctx->cfg.timing ? ctx->chunks.size() : 0;
     return POYB200_OK;
 }
 
@@ -896,7 +904,7 @@ extern "C" int poyb200_last_run_ms(poyb200_ctx *ctx, float ms[2]) {
         }
         ms[0] += a;
         ms[1] += b;
-        if (getenv("POYB200_TRACE") && atoi(getenv("POYB200_TRACE")) >= 3) {
+        if (ctx->cfg.trace >= 3) {
             // device timeline of the chunk relative to the first fill: [fill start, fill end] [traceback start, traceback end]
             float f0 = 0.f, f1 = 0.f, t0 = 0.f, t1 = 0.f;
             cudaEventElapsedTime(&f0, ctx->chunk_ev[0], ctx->chunk_ev[4 * c]);
@@ -979,10 +987,10 @@ static double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
-    static const bool trace = getenv("POYB200_TRACE") != nullptr;
+static int one_shot_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     const double t0 = now_ms();
     if (!ctx || !b) return POYB200_EINVAL;
+    const bool trace = ctx->cfg.trace >= 1;
     // The pool does not depend on the plan: its first slices travel while the (multi-threaded, ~5.5 ns per pair) planner runs,
     // so the first chunk finds its operands on the device when the plan is ready.  Only as many slices as the planner's
     // run time covers (~290 bytes per pair at the link's 52 GB/s) go early: copies queue FIFO on the copy engine and the task
@@ -1009,10 +1017,7 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         if (int urc = upload_slices(0, nearly)) return urc;
     }
     int rc = stage_impl(ctx, mode, b, false);
-    if (rc) {
-        cudaStreamSynchronize(ctx->s_in);  // the caller may release its pool after an error
-        return rc;
-    }
+    if (rc) return rc;
     const double t1 = now_ms();
     const size_t n = ctx->tasks.size(), nch = ctx->chunks.size();
     if (n == 0) {
@@ -1078,7 +1083,7 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             }
             rc = fetch_range(ctx, ch.begin, ch.end, ctx->s_out, bt);
             if (rc) return rc;
-            if (trace && atoi(getenv("POYB200_TRACE")) >= 2) {
+            if (ctx->cfg.trace >= 2) {
                 cudaStreamSynchronize(ctx->s_out);
                 fprintf(stderr, "[poyb200]   chunk %zu downloaded at +%.1f ms\n", ci, now_ms() - t0);
             }
@@ -1099,6 +1104,20 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         fprintf(stderr, "[poyb200] plan+reserve %.1f ms, enqueue %.1f ms, wait h2d %.1f, wait compute %.1f, wait d2h %.1f, total %.1f ms\n",
                 t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
     return POYB200_OK;
+}
+
+// Whatever went wrong, no copy from the caller's pool or into the caller's buffers is in flight when the call returns:
+// the caller frees them next.
+static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
+    const int rc = one_shot_impl(ctx, mode, b);
+    if (rc != POYB200_OK && ctx) {
+        const std::string keep = ctx->err;
+        for (cudaStream_t st : {ctx->s_in, ctx->stream, ctx->s_tb, ctx->s_out, ctx->s_len})
+            if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+        ctx->err = keep;
+    }
+    return rc;
 }
 
 extern "C" int poyb200_batch_cost_2(poyb200_ctx *ctx, const poyb200_batch *b) { return one_shot(ctx, MODE_COST_2, b); }
@@ -1125,11 +1144,9 @@ extern "C" int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t
     CK(cudaMemcpyAsync(ctx->d_out[2].p, a, ib, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_out[3].p, b, ib, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_outlen.p + n, len, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    median_2_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which, ctx->dcm, ctx->d_out[2].p, ctx->d_out[3].p, in_stride,
-                                                              ctx->d_outlen.p + n, n, ctx->d_out[0].p, out_stride,
-                                                              ctx->d_outlen.p);
+    CK(median_2_launch(which, ctx->dcm, ctx->d_out[2].p, ctx->d_out[3].p, in_stride, ctx->d_outlen.p + n, n, ctx->d_out[0].p, out_stride,
+                       ctx->d_outlen.p, ctx->stream));
     ctx->launches++;
-    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->d_out[0].p, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out_len, ctx->d_outlen.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1146,7 +1163,7 @@ static int peak_one(poyb200_ctx *ctx, int *d_out, double ops_per_step, double *g
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        int32_peak_kernel<KIND><<<blocks, threads, 0, ctx->stream>>>(d_out, rep + 1);
+        CK(int32_peak_launch(KIND, blocks, threads, d_out, rep + 1, ctx->stream));
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         CK(cudaEventSynchronize(ctx->ev[1]));
         float ms = 0.f;
@@ -1169,12 +1186,6 @@ extern "C" int poyb200_int32_peak(poyb200_ctx *ctx, double *gops_add, double *go
     if (rc) return rc;
     return peak_one<2>(ctx, ctx->d_costs.p, 3.0, gops_mix);
 }
-
-#ifdef POYB200_EXP_DEBUG
-extern "C" int poyb200_debug_counters(int *out) {
-    return (int) cudaMemcpyFromSymbol(out, g_dbg, sizeof(int) * 4);
-}
-#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // three sequences
@@ -1276,15 +1287,12 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
         const int nt = (int) (ch.end - ch.begin);
         const int grid = std::min(nt, grid_max);
         const int cube_threads = std::min(CUBE_THREADS, std::max(64, (max_l3 + 31) & ~31));
-        cube_fill_kernel<<<grid, cube_threads, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
-                                                                 ctx->d_ring.p, max_ring, ctx->d_dir.p, ctx->d_costs.p, bt ? 1 : 0);
+        CK(cube_fill_launch(grid, cube_threads, ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p, ctx->d_ring.p, max_ring,
+                            ctx->d_dir.p, ctx->d_costs.p, bt ? 1 : 0, ctx->stream));
         ctx->launches++;
-        CK(cudaGetLastError());
         if (bt) {
-            cube_traceback_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p,
-                                                                              ctx->d_dir.p, out);
+            CK(cube_traceback_launch(ctx->d_tasks3.p + ch.begin, nt, ctx->dcm3, ctx->d_pool.p, ctx->d_dir.p, out, ctx->stream));
             ctx->launches++;
-            CK(cudaGetLastError());
         }
     }
     CK(cudaMemcpyAsync(b->cost, ctx->d_costs.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,72 @@
+// Kernel classes: which fill kernel a pair takes and how its direction band is addressed.  Host-side planner logic shared
+// by api.cu and the kernel translation units; no device code.
+#pragma once
+#include "common.cuh"
+
+namespace poyb200 {
+
+constexpr uint32_t KLASS_GENERIC = 0;
+// klass = 1 + index into this table (affine stripe shapes: a group of G lanes owns 2 K G diagonals).  LOW is chosen at run
+// time per pair.
+struct StripeShape {
+    int K, G;
+};
+constexpr StripeShape AFF_SHAPES[] = {{5, 8}, {6, 8}, {4, 16}, {6, 16}, {4, 32}, {6, 32}, {8, 32}};
+constexpr int N_AFF_SHAPES = sizeof(AFF_SHAPES) / sizeof(AFF_SHAPES[0]);
+constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared memory
+
+struct LinShape {
+    int K, G;
+};
+constexpr LinShape LIN_SHAPES[] = {{8, 8}, {10, 8}, {12, 8}, {8, 16}, {12, 16}, {8, 32}, {10, 32}, {16, 32}};
+constexpr int N_LIN_SHAPES = sizeof(LIN_SHAPES) / sizeof(LIN_SHAPES[0]);
+constexpr uint32_t KLASS_LIN_BASE = 32;  // klass = KLASS_LIN_BASE + shape index
+constexpr int LIN_MAX_LCM = 6;
+
+// Chooses a stripe shape for an affine pair; returns false when the pair must take the generic kernel.
+static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
+    if (!affine) return false;
+    if (cm.lcm != 5 || cm.gap != 16) return false;  // aff_cell_dna assumes the nucleotide encoding
+    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
+    for (int s = 0; s < N_AFF_SHAPES; s++) {
+        const int K = AFF_SHAPES[s].K, G = AFF_SHAPES[s].G;
+        if (2 * K * G >= W + 1) {
+            t.klass = 1 + s;
+            t.G = G;
+            t.twoK = 2 * K;
+            t.BL = (K <= 4) ? 4 : 8;
+            t.dbase = t.dhi + 2 - 2 * K * G;
+            // steps are counted from a multiple of 8 double-step halves: see dir_index and aff_fast_kernels.cuh
+            t.tshift = t.dbase + ((2 * ((-t.dbase) >> 1)) & ~7);
+            return true;
+        }
+    }
+    return false;
+}
+
+// True when the class has a fast kernel (ring of 8 slots: K <= 6).
+static inline bool fast_has_shape(uint32_t klass) {
+    const int s = (int) klass - 1;
+    return s >= 0 && s < N_AFF_SHAPES && AFF_SHAPES[s].K <= 6;
+}
+
+static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
+    if (cm.lcm > LIN_MAX_LCM) return false;
+    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
+    for (int s = 0; s < N_LIN_SHAPES; s++) {
+        const int K = LIN_SHAPES[s].K, G = LIN_SHAPES[s].G;
+        if (2 * K * G >= W) {
+            const int d0 = t.dhi + 1 - 2 * K * G;
+            t.klass = KLASS_LIN_BASE + s;
+            t.G = G;
+            t.twoK = 2 * K;
+            t.BL = 4;
+            t.dbase = d0;
+            t.flags |= TF_DIR2;
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace poyb200

@@ -16,31 +16,10 @@
 // The direction cube (one byte per cell, the reference's own layout and codes) streams to HBM.
 #pragma once
 #include "common.cuh"
+#include "launch.h"
 
 namespace poyb200 {
 
-struct Task3 {
-    uint32_t off1, off2, off3;
-    int32_t l1, l2, l3;      // stored lengths (leading gap included)
-    uint32_t triple;         // index in the caller's list
-    uint32_t pad;
-    uint64_t dir_off;        // byte offset of this triple's direction cube
-};
-
-struct DevCM3 {
-    int lcm, gap;
-    const int *cost;         // (1 << lcm)^3
-    const uint8_t *median;
-};
-
-struct Out3 {
-    int *cost, *out_len, *status;
-    uint8_t *r1, *r2, *r3, *median;
-    long long stride;
-    uint32_t want;
-};
-
-constexpr int CUBE_THREADS = 512;
 // 3-D direction codes, src/matrices.h:34-40, in tag order P3, P1, P2, S3, S1, S2, SS
 __device__ __constant__ uint8_t CUBE_CODE[8] = {4, 1, 2, 32, 8, 16, 64, 0};
 constexpr int T_P3 = 0, T_P1 = 1, T_P2 = 2, T_S3 = 3, T_S1 = 4, T_S2 = 5, T_SS = 6;

@@ -17,14 +17,6 @@
 
 namespace poyb200 {
 
-struct LinShape {
-    int K, G;
-};
-constexpr LinShape LIN_SHAPES[] = {{8, 8}, {10, 8}, {12, 8}, {8, 16}, {12, 16}, {8, 32}, {10, 32}, {16, 32}};
-constexpr int N_LIN_SHAPES = sizeof(LIN_SHAPES) / sizeof(LIN_SHAPES[0]);
-constexpr uint32_t KLASS_LIN_BASE = 32;  // klass = KLASS_LIN_BASE + shape index
-constexpr int LIN_MAX_LCM = 6;
-
 struct LinWinRow {
     int lut;    // byte offset of row a in the cost LUT
     int cdel;   // 4 * cost(a, gap) + tag of DELETE
@@ -130,18 +122,17 @@ template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) lin_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                           const uint8_t *__restrict__ pool,
                                                                           uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                          int seq_bytes, int custom_tail, int *work_counter) {
+                                                                          int seq_bytes, int nslots, int custom_tail, int *work_counter) {
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
     extern __shared__ __align__(16) uint8_t smem[];
     const int dim = 1 << cm.lcm, row_ints = dim + 1;
     int *s_lut = reinterpret_cast<int *>(smem);
     int *s_gaprow = s_lut + dim * row_ints, *s_gapcol = s_gaprow + dim, *s_prep = s_gapcol + dim, *s_tail = s_prep + dim;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_tail + dim + (((dim * (row_ints + 4)) & 1) ? 1 : 0));  // 8-byte aligned
+    StageBars *s_bar = reinterpret_cast<StageBars *>(s_tail + dim + (((dim * (row_ints + 4)) & 1) ? 1 : 0));  // 8-byte aligned
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_bar + STRIPE_WARPS * 4);
     s_seq += (16 - ((uintptr_t) s_seq & 15)) & 15;
-    if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
-    uint32_t bar_phase = 0;
+    if (threadIdx.x < STRIPE_WARPS * GPW) StageRing<G>::init_bars(&s_bar[threadIdx.x]);
     for (int k = threadIdx.x; k < dim * dim; k += blockDim.x)
         s_lut[(k >> cm.lcm) * row_ints + (k & (dim - 1))] = 4 * __ldg(cm.cost + k);
     for (int k = threadIdx.x; k < dim; k += blockDim.x) {
@@ -154,29 +145,28 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) lin_stri
 
     const int warp_in_block = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
     const int grp = lane32 / G, lane = lane32 % G;
-    uint8_t *my_seq = s_seq + (size_t) ((warp_in_block * GPW + grp) * 2) * seq_bytes;
-    const int warp_global = blockIdx.x * STRIPE_WARPS + warp_in_block;
-    const int total_warps = gridDim.x * STRIPE_WARPS;
+    StageRing<G> ring;
+    ring.attach(&s_bar[warp_in_block * GPW + grp], s_seq + (size_t) ((warp_in_block * GPW + grp) * 2 * nslots) * seq_bytes, seq_bytes,
+                nslots, lane);
+    const int nbatches = (ntasks + GPW - 1) / GPW;
 
-    // batches of GPW pairs are handed out dynamically (one atomic per warp and batch): no wave-quantisation tail
-    (void) warp_global;
-    (void) total_warps;
-    for (;;) {
-        int batch = 0;
-        if (lane32 == 0) batch = atomicAdd(work_counter, 1);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch * GPW >= ntasks) break;
+    int slot = 0;
+    int batch = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+    if (batch >= 0) ring.produce_task(0, tasks, ntasks, batch * GPW + grp, pool, cm.gap);
+    while (batch >= 0) {
+        int next = -1;
+        if (nslots == 2) {  // the operands of the next batch travel under this one
+            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            if (next >= 0) ring.produce_task(slot ^ 1, tasks, ntasks, next * GPW + grp, pool, cm.gap);
+        }
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
         Task t;
         if (valid) t = tasks[ti];
         else { t = Task{}; t.lr = 1; t.lc = 1; t.dhi = 0; t.dlo = 0; }
         const int nr = t.lr - 1, nc = t.lc - 1;
-        __syncwarp();
-        stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
-                      &s_bar[warp_in_block * GPW + grp], bar_phase, cm.gap);
-        __syncwarp();
-        __syncwarp();
+        ring.wait_full(slot);
+        const uint8_t *my_seq = ring.rows(slot);
 
         const int d0 = t.dhi + 1 - Q * G;
         const int u_first = (-d0) >> 1;
@@ -256,55 +246,42 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) lin_stri
         else run(std::false_type{});
 
         if (valid && lane == lane_f) out_cost[t.pair] = result;
-        __syncwarp();
+        ring.release(slot);  // this lane's last read of the staged operands is behind it
+        if (nslots == 1) {
+            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            if (next >= 0) ring.produce_task(0, tasks, ntasks, next * GPW + grp, pool, cm.gap);
+        } else {
+            slot ^= 1;
+        }
+        batch = next;
     }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
 static inline size_t lin_table_bytes(int lcm) {
     const size_t dim = (size_t) 1 << lcm;
-    return (dim * (dim + 1) + 4 * dim + 1) * sizeof(int) + STRIPE_WARPS * 4 * 8 + 16;
+    return (dim * (dim + 1) + 4 * dim + 1) * sizeof(int) + STRIPE_WARPS * 4 * STAGE_BAR_BYTES + 16;
 }
 
-static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
-    if (cm.lcm > LIN_MAX_LCM) return false;
-    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
-    for (int s = 0; s < N_LIN_SHAPES; s++) {
-        const int K = LIN_SHAPES[s].K, G = LIN_SHAPES[s].G;
-        if (2 * K * G >= W) {
-            const int d0 = t.dhi + 1 - 2 * K * G;
-            t.klass = KLASS_LIN_BASE + s;
-            t.G = G;
-            t.twoK = 2 * K;
-            t.BL = 4;
-            t.dbase = d0;
-            t.flags |= TF_DIR2;
-            return true;
-        }
-    }
-    return false;
-}
-
+#ifdef POYB200_DEFINE_LIN_STRIPE  // the translation unit that owns these kernels (k_lin_stripe.cu)
 template <int K, int G>
 static cudaError_t lin_stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                                            int *cost, int sm_count, int seq_bytes, int custom_tail, int *work_counter, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
-    const size_t smem = lin_table_bytes(cm.lcm) + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
     auto kern = bt ? lin_stripe_kernel<K, G, true> : lin_stripe_kernel<K, G, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    size_t smem = 0;
+    int nslots = 1, per_sm = 1;
+    cudaError_t e = stage_ring_config(kern, lin_table_bytes(cm.lcm), (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes, STRIPE_WARPS * 32, smem,
+                                      nslots, per_sm);
     if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STRIPE_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, custom_tail, work_counter);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, custom_tail, work_counter);
     return cudaGetLastError();
 }
 
-static inline cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool,
+cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool,
                                             uint8_t *dir, int *cost, int sm_count, int seq_bytes, int custom_tail,
                                             int *work_counter, cudaStream_t stream) {
 #define LIN_CASE(IDX, KK, GG) \
@@ -322,5 +299,6 @@ static inline cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task 
     }
 #undef LIN_CASE
 }
+#endif  // POYB200_DEFINE_LIN_STRIPE
 
 }  // namespace poyb200

@@ -2,12 +2,10 @@
 // fraction of the INT32 ALU peak, "measured on the box by microbenchmark").
 // Each thread runs 8 independent dependent-chains so the pipes, not the latency, are the limit.
 #pragma once
-#include "common.cuh"
+#include "launch.h"
 
 namespace poyb200 {
 
-constexpr int PEAK_ITERS = 4096;
-constexpr int PEAK_CHAINS = 8;
 
 // kind 0: a += b; b += a            (2 adds per chain step)
 // kind 1: a = min(a, b); b = max(b, c); c = min(c, a) ... (3 min/max per chain step)

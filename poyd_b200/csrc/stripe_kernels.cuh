@@ -26,97 +26,17 @@
 #include <type_traits>
 
 #include "cells.cuh"
+#include "classes.h"
+#include "staging.cuh"
 
 namespace poyb200 {
-
-#ifdef POYB200_EXP_DEBUG
-__device__ int g_dbg[4];
-#endif
-constexpr uint32_t KLASS_GENERIC = 0;
-// klass = 1 + index into this table (affine stripe shapes).  LOW is chosen at run time per pair.
-struct StripeShape {
-    int K, G;
-};
-constexpr StripeShape AFF_SHAPES[] = {{5, 8}, {6, 8}, {4, 16}, {6, 16}, {4, 32}, {6, 32}, {8, 32}};
-constexpr int N_AFF_SHAPES = sizeof(AFF_SHAPES) / sizeof(AFF_SHAPES[0]);
-constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared memory
 
 constexpr int STRIPE_WARPS = 4;
 #ifndef STRIPE_MIN_BLOCKS
 #define STRIPE_MIN_BLOCKS 2
 #endif
 constexpr int STRIPE_LUT_BYTES = 16 * 17 * 8;  // == 16 * LUT_ROW_BYTES
-constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * 8;
-
-// ---- HBM -> shared-memory staging with the bulk-copy engine (TMA, cp.async.bulk) -----------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// One poll of the barrier: true once the phase with the given parity has completed.
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-
-// Stages the two operands of a group's pair: one elected lane issues two bulk copies that complete on the group's
-// mbarrier.  The wait is WARP-UNIFORM: every lane polls its own group's barrier and the loop runs until a vote says all
-// of them are through.  (Per-lane polling loops let the lanes of a warp leave at different polls; the warp then kept
-// running as separate fragments and issued every later instruction once per fragment -- a 2x slowdown, measured.)
-// Needs 16-byte aligned sources (SeqPool guarantees that); otherwise plain loads.  `phase` is the group's barrier
-// parity and flips whenever the barrier was used.  Must be called by all 32 lanes.
-template <int G>
-__device__ __forceinline__ void stage_pair(uint8_t *dst_r, uint8_t *dst_c, const uint8_t *gr, const uint8_t *gc, int lr, int lc,
-                                           int lane, bool valid, uint64_t *bar, uint32_t &phase, int pad_code) {
-#ifdef POYB200_EXP_NO_TMA
-    const bool bulk = false;  // diagnostic build: plain-load staging only
-#else
-    const bool bulk = valid && ((((uintptr_t) gr | (uintptr_t) gc) & 15) == 0);
-#endif
-#ifdef POYB200_EXP_FENCE_ALL
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-#endif
-    if (bulk) {
-        if (lane == 0) {
-            const uint32_t br = (uint32_t) (lr + 15) & ~15u, bc = (uint32_t) (lc + 15) & ~15u;
-            // the previous pair's reads of these buffers went through the generic proxy
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, br + bc);
-            bulk_g2s(dst_r, gr, br, bar);
-            bulk_g2s(dst_c, gc, bc, bar);
-        }
-    } else if (valid) {
-        for (int k = lane; k < lr; k += G) dst_r[k] = __ldg(gr + k);
-        for (int k = lane; k < lc; k += G) dst_c[k] = __ldg(gc + k);
-    } else if (lane == 0) {
-        dst_r[0] = (uint8_t) pad_code;
-        dst_c[0] = (uint8_t) pad_code;
-    }
-    bool done;
-    do {
-        done = bulk ? mbar_try_wait(bar, phase) : true;
-    } while (!__all_sync(0xffffffffu, done));
-    if (bulk) phase ^= 1u;
-    __syncwarp();
-}
+constexpr int STRIPE_TABLE_BYTES = STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * STAGE_BAR_BYTES;
 
 // All DP values are carried multiplied by 4, and each of the four states keeps a constant 2-bit tag in its low
 // bits: EH 0, CB 1, EV 2, EB 3.  The tags are the tie-break priorities of the reference's traceback:
@@ -344,12 +264,13 @@ __device__ __forceinline__ void store_dir(uint8_t *p, const uint32_t (&v)[2]) {
     else *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
 }
 
-// seq_bytes: shared-memory bytes reserved per operand (multiple of 16, >= the longest sequence of the launch).
+// seq_bytes: shared-memory bytes reserved per operand (multiple of 16, >= the longest sequence of the launch);
+// nslots: depth of the staging ring (staging.cuh).
 template <int K, int G, bool BT>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                        const uint8_t *__restrict__ pool,
                                                                        uint8_t *__restrict__ dir, int *__restrict__ out_cost,
-                                                                       int seq_bytes, int allow_noeb, int *work_counter,
+                                                                       int seq_bytes, int nslots, int allow_noeb, int *work_counter,
                                                                        const int *__restrict__ batch_list,
                                                                        const int *__restrict__ batch_count) {
     // batch_list != nullptr: only the batches aff_fast_kernel declined (aff_fast_kernels.cuh), *batch_count of them
@@ -361,10 +282,9 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
     uint8_t *s_lut = smem;  // 16 rows of LUT_ROW_BYTES: int2 {4*cost, 4*cost - 2} for cost[(a & 15) << lcm | (b & 15)]
     int *s_prep = reinterpret_cast<int *>(smem + STRIPE_LUT_BYTES);  // 32 ints: 4 * prepend[c]
     int *s_get = s_prep + 32;                                         // 32 ints: 4 * cost[c << lcm | gap]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_get + 32);  // one mbarrier per group
+    StageBars *s_bar = reinterpret_cast<StageBars *>(s_get + 32);     // one ring per group
     uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_bar + STRIPE_WARPS * 4);
-    if (threadIdx.x < STRIPE_WARPS * 4) mbar_init(&s_bar[threadIdx.x], 1);
-    uint32_t bar_phase = 0;
+    if (threadIdx.x < STRIPE_WARPS * GPW) StageRing<G>::init_bars(&s_bar[threadIdx.x]);
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
         *reinterpret_cast<int2 *>(s_lut + (k >> 4) * LUT_ROW_BYTES + (k & 15) * 8) = make_int2(c4, c4 - 2);
@@ -377,34 +297,28 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
 
     const int warp_in_block = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
     const int grp = lane32 / G, lane = lane32 % G;
-    uint8_t *my_seq = s_seq + (size_t) ((warp_in_block * GPW + grp) * 2) * seq_bytes;
-    const int warp_global = blockIdx.x * STRIPE_WARPS + warp_in_block;
-    const int total_warps = gridDim.x * STRIPE_WARPS;
+    StageRing<G> ring;
+    ring.attach(&s_bar[warp_in_block * GPW + grp], s_seq + (size_t) ((warp_in_block * GPW + grp) * 2 * nslots) * seq_bytes, seq_bytes,
+                nslots, lane);
+    const int nbatches = (ntasks + GPW - 1) / GPW;
 
-    // batches of GPW pairs are handed out dynamically (one atomic per warp and batch): no wave-quantisation tail
-    (void) warp_global;
-    (void) total_warps;
-    for (;;) {
-        int batch = 0;
-        if (lane32 == 0) batch = atomicAdd(work_counter, 1);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch_list != nullptr) {
-            if (batch >= *batch_count) break;
-            batch = batch_list[batch];
+    int slot = 0;
+    int batch = fetch_batch(work_counter, nbatches, batch_list, batch_count);
+    if (batch >= 0) ring.produce_task(0, tasks, ntasks, batch * GPW + grp, pool, 16);
+    while (batch >= 0) {
+        int next = -1;
+        if (nslots == 2) {  // the operands of the next batch travel under this one
+            next = fetch_batch(work_counter, nbatches, batch_list, batch_count);
+            if (next >= 0) ring.produce_task(slot ^ 1, tasks, ntasks, next * GPW + grp, pool, 16);
         }
-        if (batch * GPW >= ntasks) break;
         const int ti = batch * GPW + grp;
         const bool valid = ti < ntasks;
         Task t;
         if (valid) t = tasks[ti];
         else { t = Task{}; t.lr = 1; t.lc = 1; t.dhi = -1; t.dlo = -39; }
         const int nr = t.lr - 1, nc = t.lc - 1;
-        // stage both operands in shared memory
-        __syncwarp();
-        stage_pair<G>(my_seq, my_seq + seq_bytes, pool + t.off_r, pool + t.off_c, t.lr, t.lc, lane, valid,
-                      &s_bar[warp_in_block * GPW + grp], bar_phase, 16);
-        __syncwarp();
-        __syncwarp();
+        ring.wait_full(slot);
+        const uint8_t *my_seq = ring.rows(slot);
 
         const int d0 = t.dhi + 2 - Q * G;
         const int u_first = (-d0) >> 1;  // first double step: t = 2u + d0 in {-1, 0}
@@ -493,35 +407,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
                 gapbits |= (int) (w & 0x10101010u);
             }
         }
-        #ifdef POYB200_EXP_DEBUG
-        {
-            // debug: compare the staged bytes with global memory, count mismatching groups and non-noeb warps
-            int bad = 0;
-            if (valid) {
-                for (int k = lane; k < t.lr; k += G) bad |= (my_seq[k] != pool[t.off_r + k]);
-                for (int k = lane; k < t.lc; k += G) bad |= (my_seq[seq_bytes + k] != pool[t.off_c + k]);
-            }
-            const bool anybad = __any_sync(0xffffffffu, bad);
-            const bool anygap = __any_sync(0xffffffffu, gapbits != 0);
-            if (lane32 == 0) {
-                atomicAdd(&g_dbg[0], 1);
-                if (anybad) atomicAdd(&g_dbg[1], 1);
-                if (anygap) atomicAdd(&g_dbg[2], 1);
-            }
-        }
-#endif
-#ifdef POYB200_EXP_FORCE_NOEB
-        const bool noeb = allow_noeb != 0;
-#elif defined(POYB200_EXP_D)
-        const bool anyg = __any_sync(0xffffffffu, gapbits != 0);
-        if (anyg && lane32 == 0) out_cost[0] = -1;  // keeps the scan alive; never happens on the bench data
-        const bool noeb = allow_noeb != 0;
-#elif defined(POYB200_EXP_E)
-        // vote-derived flag, but no scan: gapbits comes from a single word
-        const bool noeb = !__any_sync(0xffffffffu, (my_seq[4 + lane] & 16) != 0) && cm.gap_open > 0 && allow_noeb;
-#else
         const bool noeb = !__any_sync(0xffffffffu, gapbits != 0) && cm.gap_open > 0 && allow_noeb;
-#endif
         if (any_low) run(std::true_type{}, std::false_type{});
         else if (noeb) run(std::false_type{}, std::true_type{});
         else run(std::false_type{}, std::false_type{});
@@ -530,56 +416,40 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) aff_stri
             if (BT && nr == 0 && nc == 0) result = 0;
             out_cost[t.pair] = result;
         }
-        __syncwarp();
+        ring.release(slot);  // this lane's last read of the staged operands is behind it
+        if (nslots == 1) {
+            next = fetch_batch(work_counter, nbatches, batch_list, batch_count);
+            if (next >= 0) ring.produce_task(0, tasks, ntasks, next * GPW + grp, pool, 16);
+        } else {
+            slot ^= 1;
+        }
+        batch = next;
     }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
-#ifndef POYB200_KERNELS_ONLY  // (kernel-only translation units: SASS experiments)
-
-// Chooses a stripe shape for an affine pair; returns false when the pair must take the generic kernel.
-static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
-    if (!affine) return false;
-    if (cm.lcm != 5 || cm.gap != 16) return false;  // aff_cell_dna assumes the nucleotide encoding
-    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
-    for (int s = 0; s < N_AFF_SHAPES; s++) {
-        const int K = AFF_SHAPES[s].K, G = AFF_SHAPES[s].G;
-        if (2 * K * G >= W + 1) {
-            t.klass = 1 + s;
-            t.G = G;
-            t.twoK = 2 * K;
-            t.BL = (K <= 4) ? 4 : 8;
-            t.dbase = t.dhi + 2 - 2 * K * G;
-            // steps are counted from a multiple of 8 double-step halves: see dir_index and aff_fast_kernels.cuh
-            t.tshift = t.dbase + ((2 * ((-t.dbase) >> 1)) & ~7);
-            return true;
-        }
-    }
-    return false;
-}
+#ifdef POYB200_DEFINE_AFF_STRIPE  // the translation unit that owns these kernels (k_aff_stripe.cu)
 
 template <int K, int G>
 static cudaError_t stripe_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                                        int *cost, int sm_count, int seq_bytes, int allow_noeb, int *work_counter,
                                        const int *batch_list, const int *batch_count, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
-    const size_t smem = STRIPE_TABLE_BYTES + (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes;
     const int nbatches = (n + GPW - 1) / GPW;
     auto kern = bt ? aff_stripe_kernel<K, G, true> : aff_stripe_kernel<K, G, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    size_t smem = 0;
+    int nslots = 1, per_sm = 1;
+    cudaError_t e = stage_ring_config(kern, STRIPE_TABLE_BYTES, (size_t) STRIPE_WARPS * GPW * 2 * seq_bytes, STRIPE_WARPS * 32, smem,
+                                      nslots, per_sm);
     if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STRIPE_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, allow_noeb, work_counter, batch_list,
-                                                      batch_count);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, allow_noeb, work_counter,
+                                                      batch_list, batch_count);
     return cudaGetLastError();
 }
 
-static inline cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, DevCM cm,
+cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, DevCM cm,
                                         const uint8_t *pool, uint8_t *dir, int *cost, int sm_count, int seq_bytes,
                                         int allow_noeb, int *work_counter, const int *batch_list, const int *batch_count,
                                         cudaStream_t stream) {
@@ -596,6 +466,6 @@ static inline cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, co
     }
 }
 
-#endif  // POYB200_KERNELS_ONLY
+#endif  // POYB200_DEFINE_AFF_STRIPE
 
 }  // namespace poyb200

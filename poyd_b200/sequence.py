@@ -128,13 +128,15 @@ def deltaw_calc(s1len: np.ndarray, s2len: np.ndarray, deltaw: Optional[np.ndarra
 class Align:
     """``Sequence.Align`` bound to one cost matrix and one GPU."""
 
-    def __init__(self, cm: CostMatrix, device: int = -1):
+    def __init__(self, cm: CostMatrix, device: int = -1, config: Optional[dict] = None):
+        """config: overrides of poyb200_config fields (include/poyb200.h), e.g. {"force_generic": 1}."""
         self.L = _lib.lib()
         self.cm = cm
         h = C.c_void_p()
-        rc = self.L.poyb200_create(device, C.byref(h))
+        cfg = _lib.make_config(config)
+        rc = self.L.poyb200_create_ex(device, C.byref(cfg), C.byref(h))
         if rc != 0:
-            raise PoyB200Error(f"poyb200_create failed ({rc}): no usable CUDA device; there is no CPU fallback")
+            raise PoyB200Error(f"poyb200_create_ex failed ({rc}): bad config or no usable CUDA device; there is no CPU fallback")
         self.h = h
         self._set_cm(cm)
         self._keep = None
@@ -398,8 +400,8 @@ class Align3(Align):
     """``Sequence.Align.align_3`` / ``cost_3`` / ``median_3`` (src/sequence.ml:727-762, 871-893, 934-947) over a batch
     of triples, with the reference's cube semantics as executed."""
 
-    def __init__(self, cm: CostMatrix, cm3, device: int = -1):
-        super().__init__(cm, device)
+    def __init__(self, cm: CostMatrix, cm3, device: int = -1, config: Optional[dict] = None):
+        super().__init__(cm, device, config)
         self._t3 = [np.ascontiguousarray(cm3.cost, np.int32), np.ascontiguousarray(cm3.median, np.uint8)]
         c = _lib.CM3(cm3.lcm, cm3.gap, self._t3[0].ctypes.data_as(_lib.i32p), self._t3[1].ctypes.data_as(_lib.u8p))
         self._check(self.L.poyb200_set_cm_3d(self.h, C.byref(c)))

@@ -218,9 +218,8 @@ def test_affine_every_stripe_shape(S, checker_factory, monkeypatch):
     chk = checker_factory(cm)
     o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
     oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
-    for force in ("0", "1"):
-        monkeypatch.setenv("POYB200_FORCE_GENERIC", force)
-        al = S.Align(cm)
+    for force in (0, 1):
+        al = S.Align(cm, config={"force_generic": force})
         g = al.align_affine_3(pool, pairs, ALL)
         assert_aligned_equal(g, o, label=f"affine shapes force_generic={force}")
         assert np.array_equal(al.cost_2(pool, pairs), oc), f"affine cost shapes force_generic={force}"
@@ -233,8 +232,7 @@ def test_affine_generic_matches_on_headline_shape(S, checker_factory, monkeypatc
     cm = CM.nucleotides(1, 2, 3)
     pool, pairs = synth.pair_batch(300, 500, seed=8, min_len=450, gap_ambiguity=0.05)
     o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
-    monkeypatch.setenv("POYB200_FORCE_GENERIC", "1")
-    al = S.Align(cm)
+    al = S.Align(cm, config={"force_generic": 1})
     assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), o, label="generic kernel, cfg2 shape")
     al.close()
 
@@ -298,9 +296,8 @@ def test_linear_custom_tail_and_prepend_costs(S, checker_factory, monkeypatch):
     cm.prepend_cost[1:32] = rng.integers(0, 4, size=31)
     pool, pairs = synth.ragged_batch(400, max_len=200, seed=15, gap_ambiguity=0.02)
     chk = checker_factory(cm)
-    for force in ("0", "1"):
-        monkeypatch.setenv("POYB200_FORCE_GENERIC", force)
-        al = S.Align(cm)
+    for force in (0, 1):
+        al = S.Align(cm, config={"force_generic": force})
         for dwv in (2, 20, 200):
             dw = np.full(len(pairs), dwv, np.int32)
             g = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
@@ -315,14 +312,12 @@ def test_linear_generic_matches_stripe(S, checker_factory, monkeypatch):
     cm = CM.default_nucleotides()
     pool, pairs = synth.pair_batch(300, 500, seed=6, min_len=450)
     chk = checker_factory(cm)
-    monkeypatch.setenv("POYB200_FORCE_GENERIC", "1")
-    al = S.Align(cm)
+    al = S.Align(cm, config={"force_generic": 1})
     dw = al.deltaw_for(pool, pairs)
     o = chk.batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=8)
     assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear generic cfg2-lin")
     al.close()
-    monkeypatch.setenv("POYB200_FORCE_GENERIC", "0")
-    al = S.Align(cm)
+    al = S.Align(cm, config={"force_generic": 0})
     assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear stripe cfg2-lin")
     # explicit swaped flag of the external (algn_CAML_backtrack_2d): both values, on equal-length operands
     same = np.nonzero(pool.len[pairs[:, 0]] == pool.len[pairs[:, 1]])[0][:64]

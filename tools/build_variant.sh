@@ -1,5 +1,11 @@
 #!/bin/bash
-# usage: tools/build_variant.sh NAME [-DMACRO ...]   -> build/lib_NAME.so (experimental builds; POYB200_SO selects one)
+# usage: tools/build_variant.sh NAME [-DMACRO ...]   -> build/lib_NAME.so
+# Experimental builds of the whole library with extra macros; POYB200_SO=build/lib_NAME.so makes the Python binding load one.
 name=$1; shift
 mkdir -p build
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" -o build/lib_$name.so poyd_b200/csrc/api.cu
+python - "$name" "$@" <<'PY'
+import sys
+sys.path.insert(0, ".")
+from poyd_b200 import build
+print(build.build(defines=sys.argv[2:], out=f"build/lib_{sys.argv[1]}.so"))
+PY

@@ -23,5 +23,5 @@ for cm_name, cm in (("affine", CM.nucleotides(1, 2, 3)), ("linear", CM.default_n
                     f()
                 ms = (time.perf_counter() - t0) / reps * 1e3
                 print(f"{cm_name} L={L} n={n} {label}: {ms:.3f} ms/call  ({ms / n * 1e3:.1f} us/pair)", flush=True)
-    os.environ["POYB200_TRACE"] = "1"
+    os.environ["POYB200_CONFIG"] = "trace=1,timing=1"
     al.close()

@@ -1,6 +1,5 @@
 import os, sys, time
-os.environ["POYB200_TRACE"] = "1"
-os.environ["POYB200_TIMING"] = "1"
+os.environ["POYB200_CONFIG"] = "trace=1,timing=1"
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from poyd_b200 import cost_matrix as CM, sequence as S, synth

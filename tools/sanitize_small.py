@@ -21,14 +21,12 @@ al.align_2(pool, pairs, 7)
 al.align_2(pool2, pairs2, 7)
 al.cost_2(pool, pairs)
 al.close()
-os.environ["POYB200_FORCE_GENERIC"] = "1"
-al = S.Align(CM.nucleotides(1, 2, 3))
+al = S.Align(CM.nucleotides(1, 2, 3), config={"force_generic": 1})
 al.align_affine_3(pool, pairs[:16], 7)
 al.close()
-al = S.Align(CM.default_nucleotides())
+al = S.Align(CM.default_nucleotides(), config={"force_generic": 1})
 al.align_2(pool, pairs[:16], 7)
 al.close()
-os.environ["POYB200_FORCE_GENERIC"] = "0"
 cm = CM.default_nucleotides()
 a3 = S.Align3(cm, CM.of_two_dim(cm))
 tri = np.arange(12, dtype=np.int32).reshape(-1, 3)
