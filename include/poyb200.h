@@ -16,6 +16,10 @@
  *   algn_CAML_median_2_no_gaps  src/algn.c:4198, sequence.ml:753      poyb200_batch_median_2 (which = 2)
  *   algn_CAML_cost_affine_3     src/algn.c:2628, sequence.ml:465      poyb200_batch_cost_affine_3
  *   algn_CAML_align_affine_3    src/algn.c:2551, sequence.ml:461      poyb200_batch_align_affine_3
+ *   algn_CAML_worst_2 / verify_2 src/algn.c:3382, 3395                poyb200_batch_worst_2 (which = 0 / 1)
+ *   algn_CAML_simple_3 / backtrack_3d / align_3d  src/algn.c:3458, 3961, 4005   poyb200_batch_align_3
+ *   algn_CAML_median_3          src/algn.c:4224, sequence.ml:762      poyb200_batch_median_3
+ * stubs/poyb200_stubs.c defines the algn_CAML_* symbols themselves on top of these entry points.
  *
  * Sequences are the reference's `struct seq` payloads (src/seq.h:48-58): one byte per element (SEQT =
  * unsigned char), the first element being the leading gap, so a sequence of n bases has length n + 1.
@@ -159,6 +163,12 @@ int poyb200_batch_align_affine_3(poyb200_ctx *ctx, const poyb200_batch *b);  /* 
 int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride,
                            const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len);
 
+/* algn_CAML_worst_2 (src/algn.c:3382, sequence.ml `max_cost_2`; which = 0, needs the `worst` table of the loaded matrix) and
+ * algn_CAML_verify_2 (src/algn.c:3395; which = 1): algn_calculate_from_2_aligned (:3311-3371) over n already aligned pairs,
+ * rows as for poyb200_batch_median_2; out[p] receives the sum. */
+int poyb200_batch_worst_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride, const int32_t *len,
+                          int32_t n, int32_t *out);
+
 /* --- three sequences: algn_CAML_simple_3 / algn_CAML_align_3d / algn_CAML_median_3 (src/algn.c:3458-3475, 3960-3985,
  * 4225-4235; sequence.ml:727-762) ----------------------------------------------------------------------------------
  * The reference's cube fill is defective (its neighbour-row pointers lag by one row per plane) and its
@@ -192,6 +202,10 @@ typedef struct poyb200_batch3 {
 
 int poyb200_set_cm_3d(poyb200_ctx *ctx, const poyb200_cm3 *cm);
 int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b);
+/* algn_CAML_median_3 (src/algn.c:4224, sequence.ml:762) over n already aligned triples: rows of in_stride bytes, LEFT aligned,
+ * len[p] elements each; out rows RIGHT aligned.  Reproduces algn_get_median_3d as executed (a constant sequence). */
+int poyb200_batch_median_3(poyb200_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t in_stride,
+                           const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len);
 /* cells of the cube: l1 * l2 * l3 */
 int64_t poyb200_cells_3d(int32_t l1, int32_t l2, int32_t l3);
 

@@ -30,23 +30,7 @@
 #include "seq.h"
 #include "cm.h"
 
-/* ---- symbols the reference TU leaves undefined (OCaml runtime) ---------- */
-void failwith(const char *msg) { fprintf(stderr, "reference failwith: %s\n", msg); abort(); }
-value caml_alloc_custom(struct custom_operations *ops, uintnat size, mlsize_t mem, mlsize_t max) {
-    (void) mem; (void) max;
-    value *p = (value *) calloc(1, sizeof(value) + size);
-    p[0] = (value) ops;
-    return (value) p;
-}
-void caml_register_custom_operations(struct custom_operations *ops) { (void) ops; }
-value caml_copy_double(double d) { double *p = (double *) malloc(sizeof(double)); *p = d; return (value) p; }
-void caml_serialize_int_4(int32_t i) { (void) i; }
-void caml_serialize_block_1(void *d, intnat l) { (void) d; (void) l; }
-void caml_serialize_block_4(void *d, intnat l) { (void) d; (void) l; }
-int32_t caml_deserialize_sint_4(void) { return 0; }
-uint32_t caml_deserialize_uint_4(void) { return 0; }
-void caml_deserialize_block_1(void *d, intnat l) { (void) d; (void) l; }
-void caml_deserialize_block_4(void *d, intnat l) { (void) d; (void) l; }
+/* The OCaml runtime symbols the reference TU leaves undefined live in caml_runtime.c (same library). */
 
 /* ---- reference functions we call (defined in algn.o) --------------------- */
 extern cmt cm_set_val(int a_sz, int combinations, int do_aff, int gap_open, int is_metric, int all_elements, cmt res);
@@ -100,6 +84,7 @@ void ref_cm_free(void *h) {
     free(r->c.cost); free(r->c.median); free(r->c.worst); free(r->c.prepend_cost); free(r->c.tail_cost);
     free(r);
 }
+const struct cm *ref_cm_struct(void *h) { return &((ref_cm *) h)->c; }
 int ref_cm_lcm(void *h) { return ((ref_cm *) h)->c.lcm; }
 int ref_cm_gap(void *h) { return ((ref_cm *) h)->c.gap; }
 int ref_cm_a_sz(void *h) { return ((ref_cm *) h)->c.a_sz; }
@@ -355,6 +340,7 @@ void *ref_cm3_create(int a_sz_in, int combinations, int cost_model, int gap_open
     memcpy(r->c.median, median3, n);
     return r;
 }
+const struct cm_3d *ref_cm3_struct(void *h) { return &((ref_cm3 *) h)->c; }
 void ref_cm3_free(void *h) { ref_cm3 *r = (ref_cm3 *) h; free(r->c.cost); free(r->c.median); free(r); }
 
 /* Returns the cost.  If r1 != NULL also runs backtrack_3d, but only after checking on the direction cube that the

@@ -4,8 +4,9 @@
  * files it textually includes) only needs the OCaml headers for its
  * `algn_CAML_*` stubs.  No OCaml toolchain exists in this image, so this file
  * declares just enough of <caml/...> for that translation unit to compile
- * unmodified.  None of the stub entry points are ever executed by the oracle
- * driver: it calls the plain-C functions underneath them directly.
+ * unmodified.  The oracle driver calls the plain-C functions underneath the stubs; tests/test_stubs.py
+ * also executes the algn_CAML_* stubs themselves (the reference's and stubs/poyb200_stubs.c's) on blocks
+ * built by oracle/caml_runtime.c.
  */
 #ifndef POYB200_CAML_SHIM_H
 #define POYB200_CAML_SHIM_H
@@ -34,7 +35,9 @@ typedef uintptr_t mlsize_t;
 #define Is_long(x) (((x) & 1) != 0)
 #define Field(x, i) (((value *) (x))[i])
 #define Store_field(b, i, v) (Field(b, i) = (v))
-#define Wosize_val(v) ((mlsize_t) 0)
+/* blocks made by the stand-in allocators (oracle/caml_runtime.c) carry an OCaml-style header word: wosize << 10 | tag */
+#define Hd_val(v) (((uintnat *) (v))[-1])
+#define Wosize_val(v) ((mlsize_t) (Hd_val(v) >> 10))
 #define Double_val(v) (*((double *) (v)))
 #define String_val(v) ((char *) (v))
 #define Data_custom_val(v) ((void *) &Field((v), 1))

@@ -72,7 +72,7 @@ EXPORTS = [
     "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3", "poyb200_batch_median_2", "poyb200_stage",
     "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
     "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak", "poyb200_set_cm_3d",
-    "poyb200_batch_align_3", "poyb200_cells_3d",
+    "poyb200_batch_align_3", "poyb200_cells_3d", "poyb200_batch_worst_2", "poyb200_batch_median_3",
 ]
 
 _lib = None
@@ -104,6 +104,9 @@ def lib() -> C.CDLL:
               "poyb200_batch_align_affine_3"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Batch)]
     L.poyb200_batch_median_2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_int64, C.c_void_p]
+    L.poyb200_batch_worst_2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
+    L.poyb200_batch_median_3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p]
     L.poyb200_stage.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
     for f in ("poyb200_run", "poyb200_sync", "poyb200_fetch"):

@@ -86,7 +86,7 @@ struct poyb200_ctx {
     bool has_cm = false;
     poyb200_cm hcm{};  // scalars only; pointers below are device pointers
     DevCM dcm{};
-    DevBuf<int> d_cost, d_prepend, d_tail;
+    DevBuf<int> d_cost, d_prepend, d_tail, d_worst;
     DevBuf<uint8_t> d_median;
     // staged batch
     bool staged = false;
@@ -290,7 +290,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release();
+    ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release(); ctx->d_worst.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
     ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release(); ctx->d_slow_list.release();
     ctx->tasks.release();
@@ -342,6 +342,10 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     CK(cudaMemcpyAsync(ctx->d_median.p, cm->median, dim * dim, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_prepend.p, cm->prepend_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tail.p, cm->tail_cost, dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (cm->worst) {
+        CK(ctx->d_worst.reserve(dim * dim));
+        CK(cudaMemcpyAsync(ctx->d_worst.p, cm->worst, dim * dim * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->custom_tail = 0;
     for (size_t a2 = 0; a2 < dim; a2++)
@@ -350,7 +354,8 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
     ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
     ctx->dcm = DevCM{cm->a_sz, cm->lcm, cm->gap, cm->cost_model_type, cm->combinations, cm->gap_open,
-                     ctx->d_cost.p, ctx->d_median.p, ctx->d_prepend.p, ctx->d_tail.p, cm->all_elements};
+                     ctx->d_cost.p, ctx->d_median.p, ctx->d_prepend.p, ctx->d_tail.p, cm->all_elements,
+                     cm->worst ? ctx->d_worst.p : nullptr};
     ctx->has_cm = true;
     return POYB200_OK;
 }
@@ -1154,6 +1159,33 @@ extern "C" int poyb200_batch_median_2(poyb200_ctx *ctx, int which, const uint8_t
     return POYB200_OK;
 }
 
+extern "C" int poyb200_batch_worst_2(poyb200_ctx *ctx, int which, const uint8_t *a, const uint8_t *b, int64_t in_stride,
+                                     const int32_t *len, int32_t n, int32_t *out) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->has_cm) return fail(ctx, POYB200_ENOCM, "no cost matrix loaded (poyb200_set_cm)");
+    if (which < 0 || which > 1 || n < 0) return fail(ctx, POYB200_EINVAL, "bad argument");
+    if (which == 0 && !ctx->dcm.worst) return fail(ctx, POYB200_EINVAL, "poyb200_batch_worst_2: the loaded cost matrix has no worst table");
+    if (n == 0) return POYB200_OK;
+    if (!a || !b || !len || !out) return fail(ctx, POYB200_EINVAL, "NULL array");
+    for (int p = 0; p < n; p++)
+        if (len[p] < 0 || len[p] > in_stride) return fail(ctx, POYB200_EINVAL, "row length does not fit the stride");
+    cudaSetDevice(ctx->device);
+    const size_t ib = (size_t) n * in_stride;
+    CK(ctx->d_out[2].reserve(ib + 16));
+    CK(ctx->d_out[3].reserve(ib + 16));
+    CK(ctx->d_outlen.reserve(2 * (size_t) n + 4));
+    CK(cudaMemcpyAsync(ctx->d_out[2].p, a, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_out[3].p, b, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_outlen.p + n, len, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(calc_aligned_2_launch(which == 0 ? ctx->dcm.worst : ctx->dcm.cost, ctx->dcm, ctx->d_out[2].p, ctx->d_out[3].p, in_stride,
+                             ctx->d_outlen.p + n, n, ctx->d_outlen.p, ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->d_outlen.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged = false;
+    return POYB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // INT32 roofline probe
 // ---------------------------------------------------------------------------------------------------------
@@ -1204,6 +1236,36 @@ extern "C" int poyb200_set_cm_3d(poyb200_ctx *ctx, const poyb200_cm3 *cm) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->dcm3 = DevCM3{cm->lcm, cm->gap, ctx->d_cost3.p, ctx->d_median3.p};
     ctx->has_cm3 = true;
+    return POYB200_OK;
+}
+
+extern "C" int poyb200_batch_median_3(poyb200_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t in_stride,
+                                      const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len) {
+    if (!ctx) return POYB200_EINVAL;
+    if (!ctx->has_cm3) return fail(ctx, POYB200_ENOCM, "no 3-D cost matrix loaded (poyb200_set_cm_3d)");
+    if (n < 0) return fail(ctx, POYB200_EINVAL, "negative count");
+    if (n == 0) return POYB200_OK;
+    if (!a || !b || !c || !len || !out || !out_len) return fail(ctx, POYB200_EINVAL, "NULL array");
+    for (int p = 0; p < n; p++)
+        if (len[p] < 0 || len[p] > in_stride || len[p] > out_stride) return fail(ctx, POYB200_EINVAL, "row length does not fit the strides");
+    cudaSetDevice(ctx->device);
+    const size_t ib = (size_t) n * in_stride, ob = (size_t) n * out_stride;
+    CK(ctx->d_out[1].reserve(ib + 16));
+    CK(ctx->d_out[2].reserve(ib + 16));
+    CK(ctx->d_out[3].reserve(ib + 16));
+    CK(ctx->d_out[0].reserve(ob + 16));
+    CK(ctx->d_outlen.reserve(2 * (size_t) n + 4));
+    CK(cudaMemcpyAsync(ctx->d_out[1].p, a, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_out[2].p, b, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_out[3].p, c, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_outlen.p + n, len, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(median_3_launch(ctx->dcm3.median, ctx->dcm3.lcm, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p, in_stride, ctx->d_outlen.p + n, n,
+                       ctx->d_out[0].p, out_stride, ctx->d_outlen.p, ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->d_out[0].p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_len, ctx->d_outlen.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->staged = false;
     return POYB200_OK;
 }
 

@@ -81,6 +81,7 @@ struct DevCM {
     const uint8_t *median;
     const int *prepend, *tail;
     int all_elements;
+    const int *worst;  // may be null (only algn_worst_2 reads it)
 };
 
 struct OutPtrs {

@@ -33,6 +33,18 @@ cudaError_t median_2_launch(int which, DevCM cm, const uint8_t *a, const uint8_t
     return cudaGetLastError();
 }
 
+cudaError_t calc_aligned_2_launch(const int *matrix, DevCM cm, const uint8_t *a, const uint8_t *b, long long in_stride, const int *len,
+                                  int n, int *out, cudaStream_t stream) {
+    calc_aligned_2_kernel<<<(n + 127) / 128, 128, 0, stream>>>(matrix, cm, a, b, in_stride, len, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t median_3_launch(const uint8_t *median3, int lcm, const uint8_t *a, const uint8_t *b, const uint8_t *c, long long in_stride,
+                            const int *len, int n, uint8_t *out, long long out_stride, int *out_len, cudaStream_t stream) {
+    median_3_kernel<<<(n + 127) / 128, 128, 0, stream>>>(median3, lcm, a, b, c, in_stride, len, n, out, out_stride, out_len);
+    return cudaGetLastError();
+}
+
 cudaError_t int32_peak_launch(int kind, int blocks, int threads, int *out, int seed, cudaStream_t stream) {
     if (kind == 0) int32_peak_kernel<0><<<blocks, threads, 0, stream>>>(out, seed);
     else if (kind == 1) int32_peak_kernel<1><<<blocks, threads, 0, stream>>>(out, seed);

@@ -25,6 +25,10 @@ cudaError_t traceback_launch(bool affine, int blocks, int threads, const Task *d
                              const uint8_t *dir, OutPtrs out, int *work_counter, int wpw, cudaStream_t stream);
 cudaError_t median_2_launch(int which, DevCM cm, const uint8_t *a, const uint8_t *b, long long in_stride, const int *len, int n,
                             uint8_t *out, long long out_stride, int *out_len, cudaStream_t stream);
+cudaError_t calc_aligned_2_launch(const int *matrix, DevCM cm, const uint8_t *a, const uint8_t *b, long long in_stride, const int *len,
+                                  int n, int *out, cudaStream_t stream);
+cudaError_t median_3_launch(const uint8_t *median3, int lcm, const uint8_t *a, const uint8_t *b, const uint8_t *c, long long in_stride,
+                            const int *len, int n, uint8_t *out, long long out_stride, int *out_len, cudaStream_t stream);
 constexpr int PEAK_ITERS = 4096;
 constexpr int PEAK_CHAINS = 8;
 cudaError_t int32_peak_launch(int kind, int blocks, int threads, int *out, int seed, cudaStream_t stream);

@@ -308,4 +308,59 @@ __global__ void __launch_bounds__(128) median_2_kernel(int which, DevCM cm, cons
     out_len[p] = cap - pos;
 }
 
+// algn_calculate_from_2_aligned (src/algn.c:3311-3371) over already aligned pairs: the sum of matrix[a][b] over the columns
+// plus a gap opening whenever a block of gaps starts in either row, with the reference's three-state scan.  `matrix` is
+// c->worst (algn_worst_2, :3373) or c->cost (algn_verify_2, :3378).  One thread per pair; rows LEFT aligned.
+__global__ void __launch_bounds__(128) calc_aligned_2_kernel(const int *__restrict__ matrix, DevCM cm, const uint8_t *__restrict__ a,
+                                                             const uint8_t *__restrict__ b, long long in_stride,
+                                                             const int *__restrict__ len, int n, int *__restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint8_t *s1 = a + (size_t) p * in_stride, *s2 = b + (size_t) p * in_stride;
+    const int L = len[p], gap = cm.gap, go = cm.gap_open;
+    const bool comb = cm.combinations != 0;
+    int res = 0, gap_row = 0, i = 0;
+    if (L > 0) {
+        const int x = s1[0], y = s2[0];
+        if (comb ? ((gap & x) && (gap & y)) : (x == gap && y == gap)) i = 1;
+    }
+    for (; i < L; i++) {
+        const int x = s1[i], y = s2[i];
+        const bool g1 = comb ? ((x & gap) != 0) : (x == gap), g2 = comb ? ((y & gap) != 0) : (y == gap);
+        if (gap_row == 0) {
+            if (comb ? (g1 && !g2) : g1) { res += go; gap_row = 1; }
+            else if (comb ? (g2 && !g1) : g2) { res += go; gap_row = 2; }
+        } else if (gap_row == 1) {
+            if (!g1) {
+                if (comb ? (g2 && !g1) : g2) { res += go; gap_row = 2; }
+                else gap_row = 0;
+            }
+        } else {
+            if (!g2) {
+                if (g1) { res += go; gap_row = 1; }
+                else gap_row = 0;
+            }
+        }
+        res += __ldg(matrix + (x << cm.lcm) + y);
+    }
+    out[p] = res;
+}
+
+// algn_get_median_3d (src/algn.c:4160-4173) as the reference executes it: the loop never moves its three pointers, so
+// the result is len copies of median3[last a][last b][last c].  Rows LEFT aligned in, RIGHT aligned out.
+__global__ void __launch_bounds__(128) median_3_kernel(const uint8_t *__restrict__ median3, int lcm, const uint8_t *__restrict__ a,
+                                                       const uint8_t *__restrict__ b, const uint8_t *__restrict__ c, long long in_stride,
+                                                       const int *__restrict__ len, int n, uint8_t *out, long long out_stride,
+                                                       int *out_len) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int L = len[p];
+    out_len[p] = L;
+    if (L <= 0) return;
+    const size_t o = (size_t) p * in_stride + (L - 1);
+    const int m = median3[((((size_t) a[o] << lcm) + b[o]) << lcm) + c[o]];
+    uint8_t *row = out + (size_t) p * out_stride + (out_stride - L);
+    for (int k = 0; k < L; k++) row[k] = (uint8_t) m;
+}
+
 }  // namespace poyb200

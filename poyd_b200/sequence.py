@@ -53,6 +53,7 @@ class SeqPool:
         for s, o in zip(seqs, off):
             pool[o:o + len(s)] = s
         self.pool, self.off, self.len = pool, off, lens
+        self._zero_padded = True  # built here: the bytes between sequences are 0
 
     @classmethod
     def from_matrix(cls, mat: np.ndarray, lens: np.ndarray) -> "SeqPool":
@@ -63,6 +64,7 @@ class SeqPool:
         self.pool = mat.reshape(-1)
         self.off = np.arange(mat.shape[0], dtype=np.int64) * mat.shape[1]
         self.len = np.ascontiguousarray(lens, dtype=np.int32)
+        self._stride = mat.shape[1]  # the caller's rows may hold anything past lens[r]
         return self
 
     def __len__(self) -> int:
@@ -76,12 +78,24 @@ class SeqPool:
         elements with ``code land gap <> 0`` (a bitwise test even for sequential alphabets)."""
         cache = self.__dict__.setdefault("_count_cache", {})
         if gap not in cache:
-            hit = (self.pool & np.uint8(gap)) != 0
             off = np.asarray(self.off, np.int64)
-            if len(off) and np.all(off[1:] >= off[:-1] + self.len[:-1]):
-                # ordered, non-overlapping pool (what this class builds; padding bytes are 0 and never hit): one pass
+            if getattr(self, "_stride", 0):
+                # matrix-shaped pool: count inside each row's first len elements only (the padding is the caller's), by blocks
+                st, n = self._stride, len(self.len)
+                mat = self.pool[:n * st].reshape(n, st)
+                out = np.zeros(n, np.int32)
+                cols = np.arange(st, dtype=np.int32)[None, :]
+                for lo in range(0, n, 65536):
+                    hi = min(n, lo + 65536)
+                    hit = ((mat[lo:hi] & np.uint8(gap)) != 0) & (cols < self.len[lo:hi, None])
+                    out[lo:hi] = hit.sum(axis=1, dtype=np.int32)
+                cache[gap] = out
+            elif getattr(self, "_zero_padded", False) and len(off):
+                # pool built by __init__: ordered, padding bytes are 0 and never hit -- one pass
+                hit = (self.pool & np.uint8(gap)) != 0
                 cache[gap] = np.add.reduceat(hit, off, dtype=np.int32).astype(np.int32) * (self.len > 0)
             else:
+                hit = (self.pool & np.uint8(gap)) != 0
                 cs = np.concatenate([[0], np.cumsum(hit, dtype=np.int64)])
                 cache[gap] = (cs[off + self.len] - cs[off]).astype(np.int32)
         return cache[gap]

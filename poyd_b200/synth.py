@@ -87,6 +87,28 @@ def pair_batch(n_pairs: int, length: int = 500, seed: int = 2, alphabet: str = "
     return pool, pairs
 
 
+def triple_batch(n_triples: int, length: int = 300, seed: int = 4, subst: float = 0.10, indel: float = 0.02):
+    """configs[3] (SURVEY.md 8d cfg 4): `n_triples` DNA triples, a parent of `length` bases and two children at `subst`
+    substitutions / `indel` single-base indels from it, children truncated to `length`.  Returns (pool, triples) with
+    triple t = (3t, 3t+1, 3t+2) = (parent, child, child)."""
+    rng = np.random.default_rng(seed)
+    bases = np.array([1, 2, 4, 8], np.uint8)
+    seqs = []
+    parent = bases[rng.integers(0, 4, size=(n_triples, length))]
+    kids = []
+    for _ in range(2):
+        flat, clen = _mutate_rows(rng, parent, bases, subst, indel)
+        starts = np.concatenate([[0], np.cumsum(clen)[:-1]])
+        kids.append((flat, starts, np.minimum(clen, length)))
+    g = np.array([DNA_GAP], np.uint8)
+    for t in range(n_triples):
+        seqs.append(np.concatenate([g, parent[t]]))
+        for flat, starts, clen in kids:
+            seqs.append(np.concatenate([g, flat[starts[t]:starts[t] + clen[t]]]))
+    pool = SeqPool(seqs)
+    return pool, np.arange(3 * n_triples, dtype=np.int32).reshape(-1, 3)
+
+
 def ragged_batch(n_pairs: int, max_len: int = 300, seed: int = 7, alphabet: str = "dna", related: float = 0.6,
                  gap_ambiguity: float = 0.0, ambiguity: float = 0.05, min_len: int = 0):
     """Pairs of very different shapes (lengths 0..max_len, related or unrelated operands, either order),

@@ -4,7 +4,7 @@ Bar: bit-exact costs, aligned sequences and medians, including traceback tie-bre
 import numpy as np
 import pytest
 
-from helpers import assert_aligned_equal
+from helpers import assert_aligned_equal, right_rows_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -422,6 +422,32 @@ def test_three_sequence_cube_as_the_reference_executes_it(S):
     al.close()
 
 
+def test_cube_at_the_configured_size_300(S):
+    """configs[3] shape: 300 bp triples (301 x 301 x 301 cells).  A handful of triples against the compiled reference,
+    every output (cost, status, the three aligned sequences, the median)."""
+    from oracle import oracle
+    from poyd_b200 import cost_matrix as CM, synth
+
+    oracle.build(ref=True)
+    cm = CM.default_nucleotides()
+    cm3 = CM.of_two_dim(cm)
+    chk = oracle.best_checker_3(cm3)
+    pool, triples = synth.triple_batch(5, 300, seed=77)
+    assert int(pool.len.max()) == 301
+    al = S.Align3(cm, cm3)
+    g = al.align_3(pool, triples, want=3)
+    assert np.array_equal(al.cost_3(pool, triples), g.cost)
+    for t, (i1, i2, i3) in enumerate(triples):
+        cost, status, r1, r2, r3, med = chk.align_3(pool.seq(int(i1)), pool.seq(int(i2)), pool.seq(int(i3)))
+        assert g.cost[t] == cost, (t, g.cost[t], cost)
+        assert g.status[t] == status, t
+        if status == 0:
+            assert g.lens[t] == len(r1), t
+            for name, want in (("aligned_1", r1), ("aligned_2", r2), ("aligned_3", r3), ("median", med)):
+                assert np.array_equal(g.get(name, t), want), (t, name)
+    al.close()
+
+
 def test_one_million_pairs_bit_exact(S, checker_factory):
     """BASELINE.json target: bit-exact costs and medians against algn.c on >= 1 M synthetic pairs (configs[1] shape:
     500 bp DNA, affine).  Compared in slices against the compiled reference on all host threads; half of the slices carry
@@ -455,6 +481,15 @@ def test_one_million_pairs_bit_exact(S, checker_factory):
         cg = al.cost_2(pool, pairs)
         oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=threads)["cost"]
         assert np.array_equal(cg, oc), f"slice {k}: cost-only mismatch"
+        if k < 2:
+            # one leaf-like and one median-like slice: every output of align_affine_3 (median, medianwg, both aligned
+            # sequences), bytewise, and the DOS.median payload built from the same walk
+            assert_aligned_equal(al.align_affine_3(pool, pairs, ALL), o, label=f"slice {k}, all outputs")
+            gb = al.align_affine_3(pool, pairs, S.WANT_MEDIAN | S.WANT_BITSETS)
+            n2 = o["lens"][:, 2]
+            for name, key in (("a", "ra"), ("b", "rb"), ("wg", "medianwg")):
+                bits = np.unpackbits(getattr(gb, "bits_" + name), axis=1)
+                assert right_rows_equal(bits, (o[key] != cm.gap).astype(np.uint8), n2), f"slice {k}: bitset {name}"
         total += slice_pairs
     assert total >= 1_000_000
     al.close()
