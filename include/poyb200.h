@@ -216,6 +216,26 @@ int poyb200_run(poyb200_ctx *ctx);                                      /* kerne
 int poyb200_sync(poyb200_ctx *ctx);                                     /* wait for the context's stream */
 int poyb200_fetch(poyb200_ctx *ctx);                                    /* D2H into the staged batch's outputs */
 
+/* --- one batch over several GPUs of the node ----------------------------------------------------------------
+ * BASELINE.json north_star: "batches shard across the 8 B200s by pair index, with results gathered on the host".
+ * One context and one host thread per device.  The pair list is cut into contiguous ranges of about equal DP work;
+ * each device receives only the window of the pool its pairs reference and writes its results straight into the caller's
+ * buffers at its pairs' rows (the batch's buffers are shared by all shards: no gather copy).  No collective is involved:
+ * pairs are independent.  devices = NULL means 0 .. n_devices-1.  The whole pool may exceed 4 GiB here;
+ * each shard's window must not. */
+typedef struct poyb200_multi poyb200_multi;
+int poyb200_multi_create(const int *devices, int n_devices, const poyb200_config *cfg, poyb200_multi **out);
+void poyb200_multi_destroy(poyb200_multi *m);
+const char *poyb200_multi_last_error(const poyb200_multi *m);
+int poyb200_multi_set_cm(poyb200_multi *m, const poyb200_cm *cm);
+/* mode: 0 cost_2, 1 align_2, 2 cost_affine_3, 3 align_affine_3 -- the one-shot call of that mode, sharded */
+int poyb200_multi_batch(poyb200_multi *m, int mode, const poyb200_batch *b);
+int poyb200_multi_devices(const poyb200_multi *m);
+poyb200_ctx *poyb200_multi_ctx(poyb200_multi *m, int k);          /* the context of device k (borrowed) */
+int64_t poyb200_multi_launch_count(const poyb200_multi *m);
+/* pair index at which each shard of the last call began (n_devices + 1 entries, the last one = n_pairs) */
+int poyb200_multi_shards(const poyb200_multi *m, int64_t *begin, int cap);
+
 /* --- introspection for benchmarks and tests ----------------------------------------------------------- */
 /* Number of kernels launched by this context so far. */
 int64_t poyb200_launch_count(const poyb200_ctx *ctx);

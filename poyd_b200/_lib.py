@@ -108,6 +108,19 @@ def lib() -> C.CDLL:
     L.poyb200_batch_worst_2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
     L.poyb200_batch_median_3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p]
+    L.poyb200_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.poyb200_multi_destroy.argtypes = [C.c_void_p]
+    L.poyb200_multi_destroy.restype = None
+    L.poyb200_multi_last_error.argtypes = [C.c_void_p]
+    L.poyb200_multi_last_error.restype = C.c_char_p
+    L.poyb200_multi_set_cm.argtypes = [C.c_void_p, C.POINTER(CM)]
+    L.poyb200_multi_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
+    L.poyb200_multi_devices.argtypes = [C.c_void_p]
+    L.poyb200_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.poyb200_multi_ctx.restype = C.c_void_p
+    L.poyb200_multi_launch_count.argtypes = [C.c_void_p]
+    L.poyb200_multi_launch_count.restype = C.c_int64
+    L.poyb200_multi_shards.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     L.poyb200_stage.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
     for f in ("poyb200_run", "poyb200_sync", "poyb200_fetch"):
         getattr(L, f).argtypes = [C.c_void_p]

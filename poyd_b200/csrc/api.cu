@@ -105,6 +105,11 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     poyb200_config cfg{};  // every tunable of the context (include/poyb200.h); fixed at creation
+    // Shard view (poyb200_multi_*, multi.cu): the batch's `pool` pointer is the caller's pool + view_lo and holds only the
+    // bytes this shard's pairs reference; seq_off[] stays the caller's array, so view_lo is subtracted per pair and the
+    // sequences are validated per pair instead of per pool entry.
+    bool view = false;
+    int64_t view_lo = 0;
     int custom_tail = 0;   // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int host_threads = 8;
     size_t chunk_pairs = 1u << 16;  // pairs per chunk (pipelining granularity of the one-shot calls); with three direction
@@ -551,12 +556,15 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         uint32_t klass_or = 0, klass_and = 0xffffffffu;
     };
     std::vector<Part> parts((size_t) std::max(1, NT));
-    parallel_for(NT, (size_t) b->n_seqs, [&](size_t lo, size_t hi, int slot) {
-        for (size_t s = lo; s < hi; s++) {
-            if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN) parts[slot].err = POYB200_ESEQLEN;
-            else if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes) parts[slot].err = POYB200_EINVAL;
-        }
-    });
+    const bool view = ctx->view;
+    const int64_t vlo = view ? ctx->view_lo : 0;
+    if (!view)
+        parallel_for(NT, (size_t) b->n_seqs, [&](size_t lo, size_t hi, int slot) {
+            for (size_t s = lo; s < hi; s++) {
+                if (b->seq_len[s] < 1 || b->seq_len[s] > POYB200_MAX_SEQ_LEN) parts[slot].err = POYB200_ESEQLEN;
+                else if (b->seq_off[s] < 0 || (size_t) (b->seq_off[s] + b->seq_len[s]) > b->pool_bytes) parts[slot].err = POYB200_EINVAL;
+            }
+        });
     for (auto &pt : parts) {
         if (pt.err == POYB200_ESEQLEN) return fail(ctx, POYB200_ESEQLEN, "sequence empty (no leading gap) or longer than 16384");
         if (pt.err) return fail(ctx, POYB200_EINVAL, "sequence outside the pool");
@@ -577,13 +585,21 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
                 return;
             }
             const int la = b->seq_len[a], lb = b->seq_len[c];
+            if (view) {  // the shard's window of the pool: its own operands only
+                const int64_t oa = b->seq_off[a] - vlo, oc = b->seq_off[c] - vlo;
+                if (la < 1 || la > POYB200_MAX_SEQ_LEN || lb < 1 || lb > POYB200_MAX_SEQ_LEN || oa < 0 || oc < 0 ||
+                    (size_t) (oa + la) > b->pool_bytes || (size_t) (oc + lb) > b->pool_bytes) {
+                    pt.err = POYB200_EINVAL;
+                    return;
+                }
+            }
             Task t{};
             // affine_3: shorter operand on the rows, ties keep a (src/algn.c:2595); linear: longer operand on the
             // rows, ties keep a (src/sequence.ml:709-714)
             const bool rows_b = affine ? (la > lb) : (la < lb);
             const int r = rows_b ? c : a, col = rows_b ? a : c;
-            t.off_r = (uint32_t) b->seq_off[r];
-            t.off_c = (uint32_t) b->seq_off[col];
+            t.off_r = (uint32_t) (b->seq_off[r] - vlo);
+            t.off_c = (uint32_t) (b->seq_off[col] - vlo);
             t.lr = b->seq_len[r];
             t.lc = b->seq_len[col];
             t.flags = rows_b ? TF_ROWS_ARE_B : 0;
@@ -1122,6 +1138,17 @@ static int one_shot(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         cudaGetLastError();
         ctx->err = keep;
     }
+    return rc;
+}
+
+// A shard of a larger batch (multi.cu): `b->pool` points view_lo bytes into the caller's pool.
+int poyb200_one_shot_view(poyb200_ctx *ctx, int mode, const poyb200_batch *b, int64_t view_lo) {
+    if (!ctx) return POYB200_EINVAL;
+    ctx->view = true;
+    ctx->view_lo = view_lo;
+    const int rc = one_shot(ctx, mode, b);
+    ctx->view = false;
+    ctx->view_lo = 0;
     return rc;
 }
 

@@ -184,6 +184,12 @@ class Align:
     def is_affine(self) -> bool:
         return self.cm.cost_model_type == 1
 
+    _ONE_SHOT = ("poyb200_batch_cost_2", "poyb200_batch_align_2", "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3")
+
+    def _one_shot(self, mode: int, batch) -> None:
+        """The one-shot C ABI call of `mode` (H2D, kernels, D2H) on this object's device(s)."""
+        self._check(getattr(self.L, self._ONE_SHOT[mode])(self.h, C.byref(batch)))
+
     # ---- deltaw exactly as Sequence.Align.cost_2 computes it -------------------------------------------
     def deltaw_for(self, pool: SeqPool, pairs: np.ndarray, deltaw: Optional[np.ndarray] = None) -> np.ndarray:
         cnt = pool.count(self.cm.gap)
@@ -246,18 +252,18 @@ class Align:
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         if self.is_affine:
             b, res = self.make_batch(pool, pairs)
-            self._check(self.L.poyb200_batch_cost_affine_3(self.h, C.byref(b)))
+            self._one_shot(MODE_COST_AFFINE_3, b)
         else:
             dw = np.asarray(deltaw, np.int32) if raw_deltaw else self.deltaw_for(pool, pairs, deltaw)
             b, res = self.make_batch(pool, pairs, deltaw=dw)
-            self._check(self.L.poyb200_batch_cost_2(self.h, C.byref(b)))
+            self._one_shot(MODE_COST_2, b)
         return res.cost
 
     def align_affine_3(self, pool: SeqPool, pairs, want: int = WANT_MEDIAN | WANT_MEDIANWG | WANT_ALIGNED) -> Aligned:
         """``Sequence.Align.align_affine_3 si sj cm`` (src/sequence.ml:469-478): median, resi, resj, cost,
         medianwg for every pair."""
         b, res = self.make_batch(pool, pairs, want=want)
-        self._check(self.L.poyb200_batch_align_affine_3(self.h, C.byref(b)))
+        self._one_shot(MODE_ALIGN_AFFINE_3, b)
         return res
 
     def align_2(self, pool: SeqPool, pairs, want: int = WANT_ALIGNED, deltaw: Optional[np.ndarray] = None,
@@ -270,7 +276,7 @@ class Align:
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         dw = np.asarray(deltaw, np.int32) if raw_deltaw else self.deltaw_for(pool, pairs, deltaw)
         b, res = self.make_batch(pool, pairs, deltaw=dw, swaped=swaped, want=want)
-        self._check(self.L.poyb200_batch_align_2(self.h, C.byref(b)))
+        self._one_shot(MODE_ALIGN_2, b)
         return res
 
     def closest(self, pool: SeqPool, pairs, prechecked: bool = False) -> List[np.ndarray]:
@@ -379,6 +385,56 @@ class Align:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._check(self.L.poyb200_int32_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+class MultiAlign(Align):
+    """``Sequence.Align`` over several GPUs of the node in ONE process (``poyb200_multi_*``): every batch call is cut into
+    contiguous pair ranges of about equal work, one per device, each on its own host thread; results land in the same
+    arrays a single-device call fills.  `devices` = list of CUDA ordinals."""
+
+    def __init__(self, cm: CostMatrix, devices, config: Optional[dict] = None):
+        self.L = _lib.lib()
+        self.cm = cm
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        cfg = _lib.make_config(config)
+        m = C.c_void_p()
+        rc = self.L.poyb200_multi_create(arr, len(devices), C.byref(cfg), C.byref(m))
+        if rc != 0:
+            raise PoyB200Error(f"poyb200_multi_create failed ({rc}): bad config or a device is not usable; there is no CPU fallback")
+        self.m = m
+        self.h = C.c_void_p(self.L.poyb200_multi_ctx(m, 0))  # median_2 / worst_2 / probes run on the first device
+        self.devices = devices
+        self._tabs = [np.ascontiguousarray(cm.cost, np.int32), np.ascontiguousarray(cm.median, np.uint8),
+                      np.ascontiguousarray(cm.worst, np.int32), np.ascontiguousarray(cm.prepend_cost, np.int32),
+                      np.ascontiguousarray(cm.tail_cost, np.int32)]
+        c = _lib.CM(cm.a_sz, cm.lcm, cm.gap, cm.cost_model_type, cm.combinations, cm.gap_open, cm.is_metric,
+                    cm.all_elements, self._tabs[0].ctypes.data_as(_lib.i32p), self._tabs[1].ctypes.data_as(_lib.u8p),
+                    self._tabs[2].ctypes.data_as(_lib.i32p), self._tabs[3].ctypes.data_as(_lib.i32p),
+                    self._tabs[4].ctypes.data_as(_lib.i32p))
+        if self.L.poyb200_multi_set_cm(m, C.byref(c)) != 0:
+            raise PoyB200Error(self.L.poyb200_multi_last_error(m).decode())
+        self._keep = None
+
+    def close(self) -> None:
+        if getattr(self, "m", None):
+            self.L.poyb200_multi_destroy(self.m)
+            self.m = None
+            self.h = None
+
+    def _one_shot(self, mode: int, batch) -> None:
+        rc = self.L.poyb200_multi_batch(self.m, mode, C.byref(batch))
+        if rc != 0:
+            raise PoyB200Error(f"poyb200 error {rc}: {self.L.poyb200_multi_last_error(self.m).decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.L.poyb200_multi_launch_count(self.m))
+
+    def shards(self) -> np.ndarray:
+        """Pair index at which each device's shard of the last call began (len(devices) + 1 entries)."""
+        out = (C.c_int64 * (len(self.devices) + 1))()
+        n = self.L.poyb200_multi_shards(self.m, out, len(self.devices) + 1)
+        return np.array(out[:n], dtype=np.int64)
 
 
 def cells_linear(l1: int, l2: int, deltaw: int) -> int:

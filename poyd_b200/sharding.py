@@ -6,8 +6,13 @@ gathered on the host in the caller's pair order.  The only collective the design
 per-shard cost totals (what a downpass level needs when only the tree cost is wanted).
 
 poyd itself distributes whole scripts on whole trees between servants (src/poyd/PoydParallel.ml:486-514), never
-single alignments; this module is what a servant with several GPUs -- or several servants on one box -- would use
-underneath, and it is what ``bench.py --gpus N`` exercises.
+single alignments.  Two ways to use several GPUs exist in this repository:
+
+* inside ONE process: ``poyb200_multi_batch`` (csrc/multi.cu, ``sequence.MultiAlign``) -- one host thread per device,
+  results written straight into the caller's buffers; this is the north_star's "shard by pair index, gather on the host";
+* across processes (one per GPU, ``torch.distributed``): this module.  ``bench.py --gpus N`` runs its
+  ``run_sharded`` + ``cost_sum`` on the GPUs (the ``rank_sharded_gather`` block of the bench line, NCCL backend) and
+  tests/test_sharding_gloo.py runs the same host logic with two gloo ranks on the CPU.
 """
 from __future__ import annotations
 
@@ -46,6 +51,16 @@ def gather_rows(local: np.ndarray, idx: np.ndarray, n_total: int, dst: int = 0) 
     dist.all_gather(counts, torch.tensor([len(idx)], dtype=torch.int64, device=dev))
     counts = [int(c.item()) for c in counts]
     m = max(counts) if counts else 0
+    if local.ndim > 1:
+        # trailing shapes may differ between ranks (the row width of an Align result follows the shard's longest pair):
+        # agree on the widest and pad on the right
+        shp = [torch.zeros(local.ndim - 1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(shp, torch.tensor(local.shape[1:], dtype=torch.int64, device=dev))
+        widest = tuple(int(max(s[d].item() for s in shp)) for d in range(local.ndim - 1))
+        if widest != tuple(local.shape[1:]):
+            grown = np.zeros((local.shape[0],) + widest, local.dtype)
+            grown[(slice(None),) + tuple(slice(0, k) for k in local.shape[1:])] = local
+            local = grown
     pad_idx = torch.full((m,), -1, dtype=torch.int64, device=dev)
     pad_idx[: len(idx)] = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(dev)
     pad_val = torch.zeros((m,) + local.shape[1:], dtype=torch.from_numpy(local[:0].copy()).dtype, device=dev)

@@ -564,3 +564,38 @@ def test_closest_fused_kernel(S, checker_factory, kind):
             want = np.concatenate([[cm.gap], sel[sel != cm.gap]]).astype(np.uint8)
         assert np.array_equal(got[p], want), f"{kind} pair {p}"
     al.close()
+
+
+def test_multi_device_call_matches_single_device(S, checker_factory):
+    """poyb200_multi_batch (csrc/multi.cu): one batch cut into contiguous shards of about equal work, one context and one
+    host thread per shard, every shard uploading only its window of the pool and writing into the caller's rows.  On a
+    one-GPU box the three contexts share device 0 -- the host logic (cuts, pool windows, row offsets) is what is tested;
+    bench.py --gpus N runs the same call over N devices."""
+    import torch
+
+    from poyd_b200 import cost_matrix as CM, synth
+
+    ndev = torch.cuda.device_count()
+    devices = [k % ndev for k in range(3)]
+    for cm, mode in ((CM.nucleotides(1, 2, 3), 3), (CM.default_nucleotides(), 1)):
+        pool, pairs = synth.ragged_batch(900, max_len=300, seed=61, gap_ambiguity=0.05 if mode == 3 else 0.0)
+        # a candidate-edge sweep at the end: one operand shared by many pairs, far away in the pool
+        sweep = np.stack([np.zeros(200, np.int32), np.arange(1, 401, 2, dtype=np.int32)], axis=1)
+        pairs = np.concatenate([pairs, sweep])
+        ma = S.MultiAlign(cm, devices)
+        al = S.Align(cm)
+        if mode == 3:
+            g, s = ma.align_affine_3(pool, pairs, ALL | S.WANT_BITSETS), al.align_affine_3(pool, pairs, ALL | S.WANT_BITSETS)
+            o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
+        else:
+            g, s = ma.align_2(pool, pairs, ALL | S.WANT_BITSETS), al.align_2(pool, pairs, ALL | S.WANT_BITSETS)
+            o = checker_factory(cm).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=al.deltaw_for(pool, pairs), nthreads=8)
+        assert_aligned_equal(g, o, label=f"multi-device mode {mode}")
+        for p in range(0, len(pairs), 5):  # the bitsets of the sharded call = those of the one-device call
+            for name in ("a", "b", "wg"):
+                assert np.array_equal(g.bitset(name, p), s.bitset(name, p)), (mode, p, name)
+        assert np.array_equal(ma.cost_2(pool, pairs), al.cost_2(pool, pairs))
+        cuts = ma.shards()
+        assert cuts[0] == 0 and cuts[-1] == len(pairs) and np.all(np.diff(cuts) > 0), cuts
+        ma.close()
+        al.close()
