@@ -132,6 +132,8 @@ typedef struct poyb200_config {
     int32_t timing;                    /* 1: CUDA events per chunk for poyb200_last_run_ms; default 1 */
     int32_t trace;                     /* stderr timeline of every one-shot call: 0 off, 1 host, 2 + downloads, 3 + device */
     int64_t dir_budget_bytes;          /* size limit of one direction buffer, 0 = a quarter of the free HBM, <= 40 GB */
+    int32_t use_ring;                  /* 1: ring kernels (fill + traceback in one kernel) for stripes without spare diagonals;
+                                          0: aff_fast_kernel / aff_stripe_kernel + the separate traceback kernel; default 1 */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 

@@ -33,7 +33,7 @@ class Config(C.Structure):
     _fields_ = [("struct_bytes", C.c_uint32)] + [(n, C.c_int32) for n in (
         "force_generic", "allow_fast", "allow_noeb", "overlap_traceback", "dir_buffers", "traceback_threads_per_sm",
         "traceback_block", "traceback_priority", "chunk_pairs", "host_threads", "timing", "trace")] + [
-        ("dir_budget_bytes", C.c_int64)]
+        ("dir_budget_bytes", C.c_int64), ("use_ring", C.c_int32)]
 
 
 def make_config(overrides=None) -> "Config":
@@ -73,6 +73,8 @@ EXPORTS = [
     "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
     "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak", "poyb200_set_cm_3d",
     "poyb200_batch_align_3", "poyb200_cells_3d", "poyb200_batch_worst_2", "poyb200_batch_median_3",
+    "poyb200_multi_create", "poyb200_multi_destroy", "poyb200_multi_last_error", "poyb200_multi_set_cm", "poyb200_multi_batch",
+    "poyb200_multi_devices", "poyb200_multi_ctx", "poyb200_multi_launch_count", "poyb200_multi_shards",
 ]
 
 _lib = None

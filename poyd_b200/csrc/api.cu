@@ -117,6 +117,8 @@ struct poyb200_ctx {
                                     // download of the four sequences keep up (581 against 543 GCUPS end to end)
     bool in_order = true;           // tasks[k].pair == k
     cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
+    DevBuf<uint8_t> d_scratch;       // ring kernels: per-warp band slots (aff_ring_kernels.cuh)
+    size_t ring_slot_bytes = 0;      // largest band of a ring-class pair of the staged batch
     DevBuf<uint8_t> d_dir2, d_dir3;  // further direction buffers: the traceback of chunk k runs under the fills of chunks k+1, k+2
     uint8_t *cur_dir = nullptr;
     std::vector<cudaEvent_t> ev_fill, ev_tb;
@@ -221,6 +223,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->force_generic = 0;
     cfg->allow_fast = 1;
     cfg->allow_noeb = 1;
+    cfg->use_ring = 1;
     cfg->overlap_traceback = 1;
     cfg->dir_buffers = 3;
     cfg->traceback_threads_per_sm = 512;
@@ -316,6 +319,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     for (auto &e : ctx->ev_tb) cudaEventDestroy(e);
     ctx->d_dir2.release();
     ctx->d_dir3.release();
+    ctx->d_scratch.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -405,8 +409,32 @@ static int reset_counters(poyb200_ctx *ctx) {
     return POYB200_OK;
 }
 
-static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n) {
+// True when the pairs of this class are filled AND walked by the ring kernels (no separate traceback launch).
+static bool ring_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
+    return affine && ctx->cfg.use_ring && ring_has_shape(klass);
+}
+
+static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, const OutPtrs &out) {
     if (n <= 0) return POYB200_OK;
+    if (ring_class(ctx, klass, affine)) {
+        // pairs without gap bits take the instance without the block-diagonal state, which lists the batches it declines
+        // for the full instance
+        const int *list = nullptr, *count = nullptr;
+        const size_t slot = std::max<size_t>(ctx->ring_slot_bytes, 128);
+        if (ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0) {
+            CK(ctx->d_slow_list.reserve((size_t) n + 8));
+            int *cnt = next_counter(ctx);
+            CK(ring_launch(klass, bt, false, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
+                           ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), nullptr, nullptr, ctx->d_slow_list.p, cnt, ctx->stream));
+            ctx->launches++;
+            list = ctx->d_slow_list.p;
+            count = cnt;
+        }
+        CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
+                       ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
+        ctx->launches++;
+        return POYB200_OK;
+    }
     if (klass >= KLASS_LIN_BASE) {
         cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
                                           ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
@@ -417,7 +445,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     if (klass != KLASS_GENERIC) {
         // pairs without gap bits take aff_fast_kernel; the batches it declines are listed for aff_stripe_kernel
         const int *list = nullptr, *count = nullptr;
-        if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
+        if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {  // (use_ring = 0)
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
@@ -554,6 +582,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         int maxW = 1, max_stripe_len = 16;
         bool in_order_class = true;
         uint32_t klass_or = 0, klass_and = 0xffffffffu;
+        size_t ring_slot = 0;
     };
     std::vector<Part> parts((size_t) std::max(1, NT));
     const bool view = ctx->view;
@@ -621,6 +650,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             const int W = t.dhi - t.dlo + 1;
             choose_class(t, affine, bt, W, dcm, allow_stripe);
             if (t.klass != KLASS_GENERIC) pt.max_stripe_len = std::max(pt.max_stripe_len, std::max(t.lr, t.lc));
+            if (bt && ring_class(ctx, t.klass, affine)) pt.ring_slot = std::max(pt.ring_slot, ((size_t) dir_bytes(t) + 127) & ~(size_t) 127);
             else pt.maxW = std::max(pt.maxW, W);
             pt.maxcap = std::max<long long>(pt.maxcap, (long long) la + lb + 2);
             pt.klass_or |= t.klass;
@@ -631,7 +661,9 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     long long maxcap = 16;
     int maxW = 1, max_stripe_len = 16;
     uint32_t k_or = 0, k_and = 0xffffffffu;
+    ctx->ring_slot_bytes = 0;
     for (auto &pt : parts) {
+        ctx->ring_slot_bytes = std::max(ctx->ring_slot_bytes, pt.ring_slot);
         if (pt.err) return fail(ctx, POYB200_EINVAL, "pair index out of range, or deltaw negative / absurdly large");
         maxcap = std::max(maxcap, pt.maxcap);
         maxW = std::max(maxW, pt.maxW);
@@ -667,7 +699,10 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     ctx->in_order = true;
     const bool one_class = (b->n_pairs == 0) || (k_or == k_and);
     const size_t ntasks = ctx->tasks.size();
-    auto band_bytes = [&](const Task &t) { return bt ? (((size_t) dir_bytes(t) + 63) & ~(size_t) 63) : (size_t) 0; };
+    // ring-class pairs keep their band in the ring kernels' per-warp scratch, not in the chunk's direction buffer
+    auto band_bytes = [&](const Task &t) {
+        return (bt && !ring_class(ctx, t.klass, affine)) ? (((size_t) dir_bytes(t) + 63) & ~(size_t) 63) : (size_t) 0;
+    };
     // 1. cut by count; if some chunk's direction bands exceed the budget (long sequences) cut serially by bytes instead
     ctx->chunks.clear();
     const size_t CP = ctx->chunk_pairs, nch0 = (ntasks + CP - 1) / CP;
@@ -783,6 +818,11 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     CK(ctx->d_costs.reserve(n + 1));
     size_t maxdir = 16;
     for (auto &c : ctx->chunks) maxdir = std::max(maxdir, c.dir_bytes);
+    if (bt && ctx->ring_slot_bytes) {
+        // as many slots per warp as the ring kernels can use, within the direction budget (they run with fewer if need be)
+        const size_t want = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
+        CK(ctx->d_scratch.reserve(std::min(want, std::max(ctx->dir_budget, want / 8))));
+    }
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
         if (ctx->cfg.overlap_traceback && ctx->chunks.size() >= 2) CK(ctx->d_dir2.reserve(maxdir));
@@ -824,14 +864,21 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride};
     if (two && ci >= (size_t) nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - nbuf], 0));  // the buffer is free again
     if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
-    // one fill launch per kernel class present in the chunk
+    // one fill launch per kernel class present in the chunk; the classes whose fill kernel does not walk its own pairs
+    // get a traceback launch over their task range afterwards
+    struct Group { size_t begin, end; };
+    std::vector<Group> walk_groups;
     size_t k = ch.begin;
     while (k < ch.end) {
         size_t e = k;
         const uint32_t klass = ctx->tasks[k].klass;
         while (e < ch.end && ctx->tasks[e].klass == klass) e++;
-        int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k));
+        int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k), out);
         if (rc) return rc;
+        if (bt && !ring_class(ctx, klass, affine)) {
+            if (!walk_groups.empty() && walk_groups.back().end == k) walk_groups.back().end = e;
+            else walk_groups.push_back(Group{k, e});
+        }
         k = e;
     }
     if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 1], ctx->stream));
@@ -841,23 +888,21 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
             CK(cudaStreamWaitEvent(s_tb, ctx->ev_fill[ci], 0));
         }
         if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 2], s_tb));
-        const int nt = (int) (ch.end - ch.begin);
-        // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
-        // has to stay inside L1 / L2, so only trace_threads_per_sm of them run per SM at a time
-        // Block size of the walkers (POYB200_TB_BLOCK, default 128).  Measured: 32-, 64- and 128-thread blocks give the same
-        // step time (55.4-55.6 ms per 1 M pairs), and so do 384..512 walkers per SM -- the device timeline (POYB200_TRACE=3)
-        // shows why: a traceback that shares the SMs with a fill takes registers from it (the fill drops from 3 to 1-2
-        // CTAs per SM), so fill + traceback add up whichever way they are interleaved (profiles/README.md).
-        const int tb_block = ctx->cfg.traceback_block;
-        const int wpb = tb_block / 32;
-        const int max_blocks = ctx->sm_count * std::max(1, ctx->cfg.traceback_threads_per_sm / tb_block);
-        // walkers per warp: 32 when the batch fills the grid, fewer (down to 1) when it does not
-        int wpw = (nt + max_blocks * wpb - 1) / (max_blocks * wpb);
-        wpw = std::min(32, std::max(1, wpw));
-        const int blocks = std::min((nt + wpb * wpw - 1) / (wpb * wpw), max_blocks);
-        CK(traceback_launch(affine, blocks, tb_block, ctx->d_tasks.p + ch.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
-                            next_counter(ctx), wpw, s_tb));
-        ctx->launches++;
+        for (const Group &g : walk_groups) {
+            const int nt = (int) (g.end - g.begin);
+            // persistent grid: the walkers' working set (direction line + 2 sequence lines + 4 output lines each)
+            // has to stay inside L1 / L2, so only traceback_threads_per_sm of them run per SM at a time
+            const int tb_block = ctx->cfg.traceback_block;
+            const int wpb = tb_block / 32;
+            const int max_blocks = ctx->sm_count * std::max(1, ctx->cfg.traceback_threads_per_sm / tb_block);
+            // walkers per warp: 32 when the batch fills the grid, fewer (down to 1) when it does not
+            int wpw = (nt + max_blocks * wpb - 1) / (max_blocks * wpb);
+            wpw = std::min(32, std::max(1, wpw));
+            const int blocks = std::min((nt + wpb * wpw - 1) / (wpb * wpw), max_blocks);
+            CK(traceback_launch(affine, blocks, tb_block, ctx->d_tasks.p + g.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+                                next_counter(ctx), wpw, s_tb));
+            ctx->launches++;
+        }
         if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci + 3], s_tb));
     }
     CK(cudaEventRecord(ctx->ev_tb[ci], s_tb));  // chunk ci is complete
@@ -1360,6 +1405,11 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
     CK(ctx->d_tasks3.reserve((size_t) n));
     CK(ctx->d_costs.reserve((size_t) n + 1));
     CK(ctx->d_ring.reserve(max_ring * (size_t) grid_max));
+    if (bt && ctx->ring_slot_bytes) {
+        // as many slots per warp as the ring kernels can use, within the direction budget (they run with fewer if need be)
+        const size_t want = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
+        CK(ctx->d_scratch.reserve(std::min(want, std::max(ctx->dir_budget, want / 8))));
+    }
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
         CK(ctx->d_outlen.reserve((size_t) n + 4));

@@ -6,13 +6,14 @@
 namespace poyb200 {
 
 constexpr uint32_t KLASS_GENERIC = 0;
-// klass = 1 + index into this table (affine stripe shapes: a group of G lanes owns 2 K G diagonals).  LOW is chosen at run
-// time per pair.
+// klass = 1 + index into this table (affine stripe shapes: a group of G lanes owns 2 K G diagonals) when the stripe is flush
+// with dlo, KLASS_AFF_SPARE + index when the shape leaves spare diagonals below dlo (aff_stripe_kernel's LOW variant).
 struct StripeShape {
     int K, G;
 };
 constexpr StripeShape AFF_SHAPES[] = {{5, 8}, {6, 8}, {4, 16}, {6, 16}, {4, 32}, {6, 32}, {8, 32}};
 constexpr int N_AFF_SHAPES = sizeof(AFF_SHAPES) / sizeof(AFF_SHAPES[0]);
+constexpr uint32_t KLASS_AFF_SPARE = 17;
 constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared memory
 
 struct LinShape {
@@ -31,11 +32,11 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
     for (int s = 0; s < N_AFF_SHAPES; s++) {
         const int K = AFF_SHAPES[s].K, G = AFF_SHAPES[s].G;
         if (2 * K * G >= W + 1) {
-            t.klass = 1 + s;
             t.G = G;
             t.twoK = 2 * K;
             t.BL = (K <= 4) ? 4 : 8;
             t.dbase = t.dhi + 2 - 2 * K * G;
+            t.klass = (t.dlo - t.dbase > 0) ? KLASS_AFF_SPARE + s : 1 + s;
             // steps are counted from a multiple of 8 double-step halves: see dir_index and aff_fast_kernels.cuh
             t.tshift = t.dbase + ((2 * ((-t.dbase) >> 1)) & ~7);
             return true;
@@ -44,11 +45,19 @@ static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
     return false;
 }
 
-// True when the class has a fast kernel (ring of 8 slots: K <= 6).
-static inline bool fast_has_shape(uint32_t klass) {
+// Shape index of an affine stripe class (either kind), or -1.
+static inline int aff_shape_of(uint32_t klass) {
+    if (klass >= 1 && klass < 1 + (uint32_t) N_AFF_SHAPES) return (int) klass - 1;
+    if (klass >= KLASS_AFF_SPARE && klass < KLASS_AFF_SPARE + (uint32_t) N_AFF_SHAPES) return (int) (klass - KLASS_AFF_SPARE);
+    return -1;
+}
+// True when the class has a ring kernel (fill + traceback in one kernel): no spare diagonals, rings of <= 7 slots.
+static inline bool ring_has_shape(uint32_t klass) {
     const int s = (int) klass - 1;
     return s >= 0 && s < N_AFF_SHAPES && AFF_SHAPES[s].K <= 6;
 }
+// True when the class has a fast kernel (aff_fast_kernel, the ring kernels' predecessor).
+static inline bool fast_has_shape(uint32_t klass) { return ring_has_shape(klass); }
 
 static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
     if (cm.lcm > LIN_MAX_LCM) return false;

@@ -13,6 +13,12 @@ cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_ta
                           const int *batch_count, cudaStream_t stream);
 cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
                         int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count, cudaStream_t stream);
+// ring kernels (k_aff_ring.cu): fill + traceback of the pairs whose stripe has no spare diagonals.  ebf = false takes the
+// batches without gap bits and lists the others in slow_list; ebf = true takes everything it is given.
+size_t ring_scratch_bytes(int sm_count, size_t slot_bytes);
+cudaError_t ring_launch(uint32_t klass, bool bt, bool ebf, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *scratch,
+                        size_t scratch_bytes, size_t slot_bytes, OutPtrs out, int sm_count, int seq_bytes, int *work_counter,
+                        const int *batch_list, const int *batch_count, int *slow_list, int *slow_count, cudaStream_t stream);
 // ---- linear fills (k_lin_stripe.cu) -----------------------------------------------------------------------------------
 cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                               int *cost, int sm_count, int seq_bytes, int custom_tail, int *work_counter, cudaStream_t stream);

@@ -454,7 +454,7 @@ cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_ta
                                         int allow_noeb, int *work_counter, const int *batch_list, const int *batch_count,
                                         cudaStream_t stream) {
     if (!affine) return cudaErrorNotSupported;
-    switch (klass - 1) {
+    switch (aff_shape_of(klass)) {
         case 0: return stripe_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
         case 1: return stripe_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);
         case 2: return stripe_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, allow_noeb, work_counter, batch_list, batch_count, stream);

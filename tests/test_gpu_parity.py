@@ -218,11 +218,12 @@ def test_affine_every_stripe_shape(S, checker_factory, monkeypatch):
     chk = checker_factory(cm)
     o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
     oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
-    for force in (0, 1):
-        al = S.Align(cm, config={"force_generic": force})
+    # ring kernels (default), the legacy fast / stripe kernels + separate traceback, the generic kernels
+    for config in ({}, {"use_ring": 0}, {"use_ring": 0, "allow_fast": 0}, {"force_generic": 1}):
+        al = S.Align(cm, config=config)
         g = al.align_affine_3(pool, pairs, ALL)
-        assert_aligned_equal(g, o, label=f"affine shapes force_generic={force}")
-        assert np.array_equal(al.cost_2(pool, pairs), oc), f"affine cost shapes force_generic={force}"
+        assert_aligned_equal(g, o, label=f"affine shapes {config}")
+        assert np.array_equal(al.cost_2(pool, pairs), oc), f"affine cost shapes {config}"
         al.close()
 
 
