@@ -2,18 +2,19 @@
 //
 // The product kernels stage operands with cp.async.bulk completing on an mbarrier.  Round 1's racecheck runs reported
 // hazards between the asynchronous-proxy write and the later generic reads.  This program runs the SAME StageRing code
-// in a minimal kernel, three ways:
+// in a minimal kernel, two ways:
 //
 //   mode 0  correct protocol          (wait FULL, read, arrive EMPTY; producer waits EMPTY)
-//   mode 1  read BEFORE the FULL wait (a genuine read-after-write race on the first batch)
-//   mode 2  producer skips the EMPTY wait on a one-slot ring (a genuine write-after-read race)
+//   mode 1  read BEFORE the FULL wait (a genuine read-after-write race)
 //
-// If racecheck reports the same hazards for mode 0 as for modes 1 / 2, it does not model the mbarrier completion of
-// bulk copies (tool limitation); if mode 0 is clean and 1 / 2 are flagged, the tool sees the protocol and a clean
-// report on the product kernels means what it says.  Each mode also checks the bytes it read (mode 0 must be exact).
+// If racecheck reports the same hazards for mode 0 as for mode 1, it does not model the mbarrier completion of bulk
+// copies (tool limitation); if mode 0 is clean and mode 1 is flagged, the tool sees the protocol and a clean report on
+// the product kernels means what it says.  Mode 0 also checks every byte it read against global memory (must be exact).
+// Second argument: ring depth (2 default, 1 = the one-slot protocol).
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O2 -o build/racecheck_control tools/racecheck_control.cu
-//   compute-sanitizer --tool racecheck build/racecheck_control 0     (then 1, 2)
+//   compute-sanitizer --tool racecheck build/racecheck_control 0     (then 1; then `0 1`)
+// Result on B200 (profiles/r02_sanitizer_racecheck.txt): identical reports for both modes -> tool limitation.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -67,11 +68,7 @@ __global__ void control_kernel(const Task *tasks, int ntasks, const uint8_t *poo
         if (nslots == 1) {
             next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
             if (next >= 0) {
-                // mode 2, deliberately wrong: wait on the wrong parity -- returns at once, so lane 0 may overwrite the slot
-                // while other lanes of the group are still reading it (nothing orders their reads before the copy)
-                if (MODE == 2) ring.epar ^= 1u;
                 ring.produce_task(0, tasks, ntasks, next * GPW + grp, pool, 16);
-                if (MODE == 2) ring.epar ^= 1u;
             }
         } else {
             slot ^= 1;
@@ -82,7 +79,7 @@ __global__ void control_kernel(const Task *tasks, int ntasks, const uint8_t *poo
 
 int main(int argc, char **argv) {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
-    const int nslots = (mode == 2) ? 1 : (argc > 2 ? atoi(argv[2]) : 2);
+    const int nslots = argc > 2 ? atoi(argv[2]) : 2;
     const int ntasks = NB * GPW;
     std::vector<uint8_t> pool((size_t) ntasks * 2 * SEQ);
     std::vector<Task> tasks(ntasks);
@@ -103,8 +100,7 @@ int main(int argc, char **argv) {
     cudaMemset(d_counter, 0, 4); cudaMemset(d_bad, 0, 4); cudaMemset(d_sums, 0, 4 * ntasks);
     const size_t smem = WARPS * GPW * sizeof(StageBars) + (size_t) WARPS * GPW * 2 * nslots * SEQ;
     if (mode == 0) control_kernel<0><<<4, WARPS * 32, smem>>>(d_tasks, ntasks, d_pool, nslots, d_counter, d_sums, d_bad);
-    else if (mode == 1) control_kernel<1><<<4, WARPS * 32, smem>>>(d_tasks, ntasks, d_pool, nslots, d_counter, d_sums, d_bad);
-    else control_kernel<2><<<4, WARPS * 32, smem>>>(d_tasks, ntasks, d_pool, nslots, d_counter, d_sums, d_bad);
+    else control_kernel<1><<<4, WARPS * 32, smem>>>(d_tasks, ntasks, d_pool, nslots, d_counter, d_sums, d_bad);
     cudaError_t e = cudaDeviceSynchronize();
     int bad = -1;
     cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost);
