@@ -82,36 +82,81 @@ struct RingFmt {
     static constexpr int BL = (K <= 4 || DIR6) ? 4 : 8;
 };
 
-// The band of one pair as a ring kernel wrote it, read back by the walk of the same warp (plain loads: same-SM stores
-// are visible after __syncwarp; the read-only path is not allowed for data written by this kernel).
+// The band of one pair as a ring kernel wrote it, read back by the walk of the same warp.
+//
+// A walk is a chain of dependent loads: the next cell is known only when the current direction code has been decoded.
+// What IS known in advance is the order of the tiles: a step moves one or two anti-diagonals back, so the walk passes
+// through every tile of 8 anti-diagonals, in descending order, and inside a tile it cannot drift further than into the
+// neighbouring lane chunk (a chunk spans 2 K >= 8 diagonals).  Each walker therefore keeps a private two-buffer window in
+// shared memory: the three adjacent lane chunks (3 * 8 * BL contiguous bytes) of the current tile and of the next one,
+// fetched with cp.async (16-byte copies, L2 path: the band was written by this SM's own stores) one tile ahead.  The
+// per-step access is then a shared-memory load; a step that leaves the window (rare) reads global memory directly.
 template <int K, int G, bool EBF>
 struct BandRing {
     static constexpr int BL = RingFmt<K, EBF>::BL;
     static constexpr bool DIR6 = RingFmt<K, EBF>::DIR6;
+    static constexpr int CH = 8 * BL, WIN = 3 * CH;  // bytes of one lane chunk of a tile / of the window
+    static constexpr int NW = (G >= 3) ? 3 : G;      // lanes in the window
     const uint8_t *dbase;
     int dbase_d, tshift;
-    __device__ __forceinline__ int fetch(int i, int j) const {
-        const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
-        const uint32_t lane = dd / (2 * K), m = (dd - lane * (2 * K)) >> 1;
-        const uint32_t chunk = (((T >> 3) * G + lane) * 8 + (T & 7)) * BL;
-        // the walk visits every tile of 8 anti-diagonals in descending order: request the whole tile rows it will need
-        // well ahead (a tile row is G * 8 * BL contiguous bytes), once per tile (T & 7 == 7 or 6: a diagonal move skips one)
-        if ((T & 6) == 6) {
-            constexpr uint32_t TILE = G * 8 * BL;
-            const uint32_t trow = (T >> 3) * TILE;
-            if (trow >= 6 * TILE) {
+    uint32_t sbuf;   // shared address of this thread's 2 * WIN bytes
+    int cur_tile, ws0, ws1;
+
+    __device__ __forceinline__ void load_tile(int tile, int lane) {
+        const int w0 = min(max(lane - 1, 0), G - NW);
+        if (tile & 1) ws1 = w0; else ws0 = w0;
+        const uint8_t *src = dbase + ((size_t) tile * G + w0) * CH;
+        const uint32_t dst = sbuf + (tile & 1) * WIN;
 #pragma unroll
-                for (uint32_t o = 0; o < TILE; o += 128) prefetch_l2(dbase + trow - 6 * TILE + o);
-            }
-            if (trow >= 2 * TILE) prefetch_l1(dbase + chunk - 2 * TILE);
-        }
-        if (DIR6) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(dbase + chunk);
-            return (int) ((w >> (6 * m)) & 63u) | AB_ENDB;
-        }
-        return dbase[chunk + m];
+        for (int o = 0; o < NW * CH; o += 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // Before the first fetch: the tile of the walk's first cell (nr, nc) and the one below it.
+    __device__ __forceinline__ void start(int i, int j) {
+        const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
+        const int lane = (int) (dd / (2 * K)), tile = (int) (T >> 3);
+        ws0 = ws1 = 0;
+        load_tile(tile, lane);
+        if (tile > 0) load_tile(tile - 1, lane);
+        cur_tile = tile;
+        if (tile > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __device__ __forceinline__ int fetch(int i, int j) {
+        const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
+        const int lane = (int) (dd / (2 * K)), tile = (int) (T >> 3);
+        const uint32_t m = (dd - (uint32_t) lane * (2 * K)) >> 1;
+        if (tile != cur_tile) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tile == cur_tile - 1) {  // one tile down (a step moves at most two anti-diagonals): it was prefetched
+                cur_tile = tile;
+                if (tile > 0) load_tile(tile - 1, lane);  // into the buffer the walk has just left
+            } else {  // the walk spent some steps outside the band (edge cells need no fetch) and skipped a tile: start over
+                start(i, j);
+            }
+        }
+        const int rel = lane - ((tile & 1) ? ws1 : ws0);
+        const uint32_t in_chunk = (T & 7) * BL;
+        if ((unsigned) rel < (unsigned) NW) {
+            const uint32_t a = sbuf + (tile & 1) * WIN + rel * CH + in_chunk;
+            if (DIR6) {
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a));
+                return (int) ((w >> (6 * m)) & 63u) | AB_ENDB;
+            }
+            uint32_t v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + m));
+            return (int) v;
+        }
+        const uint8_t *g = dbase + ((size_t) tile * G + lane) * CH + in_chunk;
+        if (DIR6) return (int) ((*reinterpret_cast<const volatile uint32_t *>(g) >> (6 * m)) & 63u) | AB_ENDB;
+        return *reinterpret_cast<const volatile uint8_t *>(g + m);
+    }
+    __device__ __forceinline__ void finish() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
+template <int K, bool EBF>
+__host__ __device__ constexpr int ring_walk_window_bytes() { return 2 * 3 * 8 * RingFmt<K, EBF>::BL; }  // per thread
 
 template <int K, int G, bool BT, bool EBF>
 struct AffRing {
@@ -347,7 +392,8 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, EBF ? RING_MIN_BLOCKS_EB : 
     StageBars *s_bar = reinterpret_cast<StageBars *>(s_get + 32);  // one staging ring per group (staging.cuh)
     int *s_scr = reinterpret_cast<int *>(s_bar + STRIPE_WARPS * 4);  // RING_SCR_INTS per group
     int *s_pend = s_scr + STRIPE_WARPS * 4 * RING_SCR_INTS;          // RING_PEND task indices per warp
-    uint8_t *s_seq = reinterpret_cast<uint8_t *>(s_pend + STRIPE_WARPS * RING_PEND);
+    uint8_t *s_win = reinterpret_cast<uint8_t *>(s_pend + STRIPE_WARPS * RING_PEND);  // per-thread band windows of the walk
+    uint8_t *s_seq = s_win + (BT ? STRIPE_WARPS * 32 * ring_walk_window_bytes<K, EBF>() : 0);
     if (threadIdx.x < STRIPE_WARPS * GPW) StageRing<G>::init_bars(&s_bar[threadIdx.x]);
     const int go4 = 4 * cm.gap_open;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
@@ -396,7 +442,11 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, EBF ? RING_MIN_BLOCKS_EB : 
         const int ti = (lane32 < npend) ? my_pend[lane32] : -1;
         if (ti >= 0) {
             const Task t = tasks[ti];
-            BandRing<K, G, EBF> band{my_scratch + (size_t) lane32 * slot_bytes, t.dbase, t.tshift};
+            BandRing<K, G, EBF> band;
+            band.dbase = my_scratch + (size_t) lane32 * slot_bytes;
+            band.dbase_d = t.dbase;
+            band.tshift = t.tshift;
+            band.sbuf = smem_u32(s_win + (size_t) threadIdx.x * ring_walk_window_bytes<K, EBF>());
             aff_walk_pair(t, pool, band, cm, out);
         }
         __syncwarp();
@@ -562,7 +612,8 @@ static cudaError_t ring_launch_shape(bool bt, const RingLaunch &a) {
     auto kern = bt ? aff_ring_kernel<K, G, true, EBF> : aff_ring_kernel<K, G, false, EBF>;
     size_t smem = 0;
     int nslots = 1, per_sm = 1;
-    cudaError_t e = stage_ring_config(kern, RING_TABLE_BYTES, (size_t) STRIPE_WARPS * GPW * 2 * (a.seq_bytes + ring_operand_pad(K, G)),
+    const size_t fixed = RING_TABLE_BYTES + (bt ? (size_t) STRIPE_WARPS * 32 * ring_walk_window_bytes<K, EBF>() : 0);
+    cudaError_t e = stage_ring_config(kern, fixed, (size_t) STRIPE_WARPS * GPW * 2 * (a.seq_bytes + ring_operand_pad(K, G)),
                                       STRIPE_WARPS * 32, smem, nslots, per_sm);
     if (e != cudaSuccess) return e;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, a.sm_count * per_sm);

@@ -10,146 +10,7 @@
 #include <mutex>
 #include <vector>
 
-#include "../../include/poyb200.h"
-#include "launch.h"
-
-using namespace poyb200;
-
-namespace {
-
-enum Mode { MODE_COST_2 = 0, MODE_ALIGN_2 = 1, MODE_COST_AFF = 2, MODE_ALIGN_AFF = 3 };
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;  // elements
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = n + n / 8 + 64;
-        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-// Grow-only array in pinned host memory (so that its upload is a true asynchronous DMA).
-template <typename T>
-struct PinnedVec {
-    T *p = nullptr;
-    size_t n = 0, cap = 0;
-    bool resize(size_t m) {
-        if (m > cap) {
-            if (p) cudaFreeHost(p);
-            p = nullptr;
-            cap = 0;
-            const size_t want = m + m / 8 + 64;
-            if (cudaHostAlloc((void **) &p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
-            cap = want;
-        }
-        n = m;
-        return true;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        n = cap = 0;
-    }
-    size_t size() const { return n; }
-    T *data() { return p; }
-    T *begin() { return p; }
-    T *end() { return p + n; }
-    T &operator[](size_t i) { return p[i]; }
-    const T &operator[](size_t i) const { return p[i]; }
-};
-
-struct Chunk {
-    size_t begin, end;  // task range
-    size_t dir_bytes;
-};
-
-}  // namespace
-
-struct poyb200_ctx {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    // cost matrix
-    bool has_cm = false;
-    poyb200_cm hcm{};  // scalars only; pointers below are device pointers
-    DevCM dcm{};
-    DevBuf<int> d_cost, d_prepend, d_tail, d_worst;
-    DevBuf<uint8_t> d_median;
-    // staged batch
-    bool staged = false;
-    int mode = 0;
-    poyb200_batch hb{};
-    PinnedVec<Task> tasks, tasks_tmp;
-    std::vector<Chunk> chunks;
-    std::vector<size_t> class_begin;  // per chunk x class boundaries are recomputed at launch time
-    DevBuf<uint8_t> d_pool, d_dir, d_out[4], d_bits[3];
-    DevBuf<Task> d_tasks;
-    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters, d_slow_list;
-    size_t counter_next = 0;  // work counters handed to launches of the current call (zeroed once per call)
-    DevBuf<int4> d_aff_state;
-    long long dstride = 0, bstride = 0;
-    size_t dir_budget = 0;
-    int state_stride = 0;
-    int stripe_seq_bytes = 16;
-    poyb200_config cfg{};  // every tunable of the context (include/poyb200.h); fixed at creation
-    // Shard view (poyb200_multi_*, multi.cu): the batch's `pool` pointer is the caller's pool + view_lo and holds only the
-    // bytes this shard's pairs reference; seq_off[] stays the caller's array, so view_lo is subtracted per pair and the
-    // sequences are validated per pair instead of per pool entry.
-    bool view = false;
-    int64_t view_lo = 0;
-    int custom_tail = 0;   // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
-    int host_threads = 8;
-    size_t chunk_pairs = 1u << 16;  // pairs per chunk (pipelining granularity of the one-shot calls); with three direction
-                                    // buffers 65 536 and 131 072 give the same device time, and the smaller chunk lets the
-                                    // download of the four sequences keep up (581 against 543 GCUPS end to end)
-    bool in_order = true;           // tasks[k].pair == k
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
-    DevBuf<uint8_t> d_scratch;       // ring kernels: per-warp band slots (aff_ring_kernels.cuh)
-    size_t ring_slot_bytes = 0;      // largest band of a ring-class pair of the staged batch
-    DevBuf<uint8_t> d_dir2, d_dir3;  // further direction buffers: the traceback of chunk k runs under the fills of chunks k+1, k+2
-    uint8_t *cur_dir = nullptr;
-    std::vector<cudaEvent_t> ev_fill, ev_tb;
-    cudaEvent_t ev_in = nullptr;
-    std::vector<cudaEvent_t> ev_done, ev_pool;
-    // 3-D
-    bool has_cm3 = false;
-    DevCM3 dcm3{};
-    DevBuf<int> d_cost3, d_ring, d_status;
-    DevBuf<uint8_t> d_median3;
-    DevBuf<Task3> d_tasks3;
-    // stats
-    int64_t launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> chunk_ev;  // 3 per chunk: before fill, after fill, after traceback
-    size_t timed_chunks = 0;
-};
-
-#define CK(call)                                                                           \
-    do {                                                                                   \
-        cudaError_t e__ = (call);                                                          \
-        if (e__ != cudaSuccess) {                                                          \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
-            return (e__ == cudaErrorMemoryAllocation) ? POYB200_ENOMEM : POYB200_ECUDA;    \
-        }                                                                                  \
-    } while (0)
-
-static int fail(poyb200_ctx *ctx, int code, const char *msg) {
-    ctx->err = msg;
-    return code;
-}
+#include "ctx.h"
 
 // ---------------------------------------------------------------------------------------------------------
 // geometry: which cells the reference visits
@@ -424,19 +285,19 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         if (ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0) {
             CK(ctx->d_slow_list.reserve((size_t) n + 8));
             int *cnt = next_counter(ctx);
-            CK(ring_launch(klass, bt, false, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
+            CK(ring_launch(klass, bt, false, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
                            ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), nullptr, nullptr, ctx->d_slow_list.p, cnt, ctx->stream));
             ctx->launches++;
             list = ctx->d_slow_list.p;
             count = cnt;
         }
-        CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
+        CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
                        ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
         ctx->launches++;
         return POYB200_OK;
     }
     if (klass >= KLASS_LIN_BASE) {
-        cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
+        cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
                                           ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
@@ -448,14 +309,14 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {  // (use_ring = 0)
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
-            cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
+            cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
                                         ctx->stripe_seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt, ctx->stream);
             ctx->launches++;
             CK(e);
             list = ctx->d_slow_list.p;
             count = cnt;
         }
-        cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, ctx->d_costs.p,
+        cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
                                       ctx->sm_count, ctx->stripe_seq_bytes, ctx->cfg.allow_noeb, next_counter(ctx), list, count, ctx->stream);
         ctx->launches++;
         CK(e);
@@ -466,11 +327,11 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     const size_t nwarps = (size_t) blocks * warps_per_block;
     if (affine) {
         CK(ctx->d_aff_state.reserve(nwarps * ctx->state_stride));
-        CK(aff_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_aff_state.p, ctx->state_stride, ctx->cur_dir,
+        CK(aff_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_aff_state.p, ctx->state_stride, ctx->cur_dir,
                               ctx->d_costs.p, ctx->stream));
     } else {
         CK(ctx->d_lin_state.reserve(nwarps * ctx->state_stride));
-        CK(lin_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->d_pool.p, ctx->d_lin_state.p, ctx->state_stride, ctx->cur_dir,
+        CK(lin_generic_launch(bt, blocks, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_lin_state.p, ctx->state_stride, ctx->cur_dir,
                               ctx->d_costs.p, ctx->stream));
     }
     ctx->launches++;
@@ -671,7 +532,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
         k_or |= pt.klass_or;
         k_and &= pt.klass_and;
     }
-    if (bt && b->n_pairs > 0) {
+    if (bt && b->n_pairs > 0 && !ctx->device_store) {
         if ((b->want & (POYB200_WANT_MEDIAN | POYB200_WANT_CLOSEST)) && !b->median)
             return fail(ctx, POYB200_EINVAL, "WANT_MEDIAN / WANT_CLOSEST without the median buffer");
         if ((b->want & POYB200_WANT_MEDIAN) && (b->want & POYB200_WANT_CLOSEST))
@@ -813,7 +674,10 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     ctx->hb = *b;
     const bool bt = (mode == MODE_ALIGN_2 || mode == MODE_ALIGN_AFF);
     const size_t n = ctx->tasks.size();
-    CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+    if (!ctx->device_store) {
+        CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+        ctx->cur_pool = ctx->d_pool.p;
+    }
     CK(ctx->d_tasks.reserve(n + 1));
     CK(ctx->d_costs.reserve(n + 1));
     size_t maxdir = 16;
@@ -847,6 +711,8 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
 }
 
 extern "C" int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b) { return stage_impl(ctx, mode, b, true); }
+int poyb200_stage_internal(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool upload) { return stage_impl(ctx, mode, b, upload); }
+int poyb200_run_staged(poyb200_ctx *ctx) { return poyb200_run(ctx); }
 
 // Fill of chunk ci on the compute stream, its traceback on the traceback stream.  With two direction buffers the
 // (latency-bound, 128..512 walkers per SM) traceback of chunk ci runs underneath the (ALU-bound) fill of chunk ci+1.
@@ -899,7 +765,7 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
             int wpw = (nt + max_blocks * wpb - 1) / (max_blocks * wpb);
             wpw = std::min(32, std::max(1, wpw));
             const int blocks = std::min((nt + wpb * wpw - 1) / (wpb * wpw), max_blocks);
-            CK(traceback_launch(affine, blocks, tb_block, ctx->d_tasks.p + g.begin, nt, ctx->dcm, ctx->d_pool.p, ctx->cur_dir, out,
+            CK(traceback_launch(affine, blocks, tb_block, ctx->d_tasks.p + g.begin, nt, ctx->dcm, ctx->cur_pool, ctx->cur_dir, out,
                                 next_counter(ctx), wpw, s_tb));
             ctx->launches++;
         }
@@ -1075,6 +941,7 @@ static int one_shot_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     };
     if (nslices) {
         CK(ctx->d_pool.reserve(b->pool_bytes + 64));
+        ctx->cur_pool = ctx->d_pool.p;
         while (ctx->ev_pool.size() < nslices) {
             cudaEvent_t e;
             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

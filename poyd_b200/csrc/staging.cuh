@@ -152,7 +152,9 @@ static inline cudaError_t stage_ring_config(KernelT kern, size_t fixed, size_t r
                                             int &per_sm) {
     constexpr size_t SMEM_MAX = 227 * 1024;
     const size_t s1 = fixed + ring1, s2 = fixed + 2 * ring1;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min(s2, SMEM_MAX));
+    // always the architectural maximum: the attribute belongs to the (function, device), which several contexts and host
+    // threads share -- a per-launch value would race between them
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_MAX);
     if (e != cudaSuccess) return e;
     int occ1 = 0, occ2 = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, kern, threads, s1);

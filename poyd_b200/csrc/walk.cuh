@@ -66,6 +66,8 @@ struct BandBytes {
         // 0xFFFF for the generic ones, where the quotient is 0 for every dd the 16384-element cap allows
         recip = (65536u + t.twoK - 1) / t.twoK;
     }
+    __device__ __forceinline__ void start(int, int) {}
+    __device__ __forceinline__ void finish() {}
     __device__ __forceinline__ int fetch(int i, int j) const {
         const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
         const uint32_t lane = (dd * recip) >> 16, m = (dd - lane * twoK) >> 1;
@@ -79,7 +81,7 @@ struct BandBytes {
 
 // dcap = device row stride (multiple of 16).
 template <class Band>
-__device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__restrict__ pool, const Band band, const DevCM &cm,
+__device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__restrict__ pool, Band band, const DevCM &cm,
                                               const OutPtrs &out) {
     const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
     const int dcap = (int) out.stride;
@@ -102,6 +104,7 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
     rj.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
     int i = t.lr - 1, j = t.lc - 1;
     int ic = si[i], jc = sj[j];
+    if (i > 0 && j > 0) band.start(i, j);
     int nmed = 0, nwg = 0, nres = 0, med_first = -1, nclo = 0;
     // The reference's mode machine (m_todo / vertical / horizontal / diagonal / align, :2003-2075) and its two tails
     // (`while (i)`, `while (j)`, :2076-2091) as ONE branch-free step: the 32 walkers of a warp are in different modes, and with
@@ -150,6 +153,7 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
         ic = si[i];
         jc = sj[j];
     }
+    band.finish();
     // the leading column: (gap, gap), a gap in medianwg, and a gap in front of the median unless it starts with one
     nres++;
     nwg++;
