@@ -329,6 +329,123 @@ def bench_tree(args, rank, local_rank, world, threads):
         dist.destroy_process_group()
 
 
+def bench_cfg5(args, rank, local_rank, world, cores):
+    """BASELINE.json configs[4]: synthetic --taxa x --bp unaligned DNA, Wagner build + SPR search with batched downpass medians,
+    through the NATIVE driver (include/poyb200_tree.h) on device-resident stores.  N > 1: rank 0 builds the Wagner tree and
+    broadcasts it; every SPR round each rank sweeps and evaluates its shard of the tree's neighbourhood (the breaks k with
+    k mod N = rank), the ranks' finds are all-gathered and the candidate the unsharded search would have taken (smallest key)
+    becomes the next tree on every rank.  The only collectives are those few integers and the winning topology."""
+    import torch
+    import torch.distributed as dist
+
+    from poyd_b200 import cost_matrix as CM, synth, tree as T, tree_native as TN
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cm = CM.nucleotides(1, 2, 3)
+    leaves = synth.taxa_on_random_tree(args.taxa, args.bp, seed=5)
+    ev = TN.NativeEvaluator(cm, leaves, device=local_rank)
+    # warm-up: a small build on the same evaluator type (kernels loaded, buffers grown)
+    small = {k: v for k, v in leaves.items() if k <= 16}
+    w = TN.NativeEvaluator(cm, small, device=local_rank)
+    w.evaluate(w.wagner(sorted(small))[0])
+    w.close()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_nodes = 2 * args.taxa - 2
+    if rank == 0:
+        topo, steps = ev.wagner(sorted(leaves))
+        ids, nbr = TN._pack(topo)
+        pack = torch.from_numpy(np.concatenate([ids, nbr.reshape(-1), [topo.handle]]).astype(np.int32)).cuda()
+    else:
+        pack = torch.zeros(4 * n_nodes + 1, dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.broadcast(pack, src=0)
+        p = pack.cpu().numpy()
+        topo = TN._unpack(p[:n_nodes], p[n_nodes:4 * n_nodes].reshape(-1, 3), int(p[-1]), args.taxa)
+    t_build = time.perf_counter() - t0
+    start = ev.evaluate(topo, keep=True)
+    best, rounds, totals = start.adjusted, 0, {"breaks": 0, "joins_swept": 0, "exact_evaluated": 0}
+    t1 = time.perf_counter()
+    while rounds < args.spr_rounds:
+        found, key, cost, joined, st = ev.spr_round(topo, best, rank, world, window=args.spr_window)
+        for k in totals:
+            totals[k] += st[k]
+        if world > 1:
+            mine = torch.tensor([key if found else (1 << 62), cost if found else 0, rank], dtype=torch.int64, device="cuda")
+            allv = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)
+            win = min(allv, key=lambda v: int(v[0]))
+            if int(win[0]) >= (1 << 62):
+                break
+            src = int(win[2])
+            if rank == src:
+                ids, nbr = TN._pack(joined)
+                pack = torch.from_numpy(np.concatenate([ids, nbr.reshape(-1), [joined.handle]]).astype(np.int32)).cuda()
+            else:
+                pack = torch.zeros(4 * n_nodes + 1, dtype=torch.int32, device="cuda")
+            dist.broadcast(pack, src=src)
+            p = pack.cpu().numpy()
+            topo = TN._unpack(p[:n_nodes], p[n_nodes:4 * n_nodes].reshape(-1, 3), int(p[-1]), args.taxa)
+            best = int(win[1])
+        else:
+            if not found:
+                break
+            topo, best = joined, cost
+        rounds += 1
+    torch.cuda.synchronize()
+    t_spr = time.perf_counter() - t1
+    total = time.perf_counter() - t0
+    stt = ev.stats()
+    vals = torch.tensor([float(stt["cells"]), float(stt["pairs"]), float(stt["calls"]), float(totals["joins_swept"]),
+                         float(totals["exact_evaluated"]), float(totals["breaks"])], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    launches = ev.al.launch_count()
+    if rank == 0:
+        sec = float(tmax[0])
+        v = float(vals[0]) / sec * 1e-9
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "configs[4]: synthetic %d-taxon x %d bp unaligned DNA, Wagner build + SPR search (first-best, whole-sweep "
+                                       "evaluation, in-order replay) with batched downpass medians, affine gaps (1, 2, opening 3); native "
+                                       "driver on device-resident sequence stores; one neighbourhood shard per GPU" % (args.taxa, args.bp),
+                           "taxa": args.taxa, "bp": args.bp, "spr_rounds_limit": args.spr_rounds, "spr_window": args.spr_window},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(float(vals[1]) * 56), "d2h_bytes_per_step": int(float(vals[1]) * 12),
+                        "note": "the driver IS the public call: leaves go up once, per batch only task descriptors go up and costs / lengths "
+                                "/ gap counts come back"},
+                "tree": {"wagner_seconds": t_build, "spr_seconds": t_spr, "start_cost": start.adjusted, "final_cost": best,
+                         "accepted_rounds": rounds, "breaks": int(vals[5]), "joins_swept": int(vals[3]), "exact_evaluated": int(vals[4]),
+                         "pairs": int(vals[1]), "batches": int(vals[2]), "cells": int(vals[0]),
+                         "host_us_per_pair": sec * 1e6 / max(1.0, float(vals[1])) * world},
+                "gpu_launches": int(launches)}
+        if not args.skip_cpu and world == 1:
+            from oracle import oracle
+            from oracle.tree_engine import OracleEngine
+
+            oracle.build(ref=True)
+            sub = {k: v_ for k, v_ in leaves.items() if k <= min(args.taxa, 40)}
+            eng = OracleEngine(cm, nthreads=cores)
+            evc = T.Evaluator(eng, cm)
+            tc0 = time.perf_counter()
+            tp, _ = evc.wagner(sub)
+            evc.evaluate(tp, sub, keep=True)
+            dt = time.perf_counter() - tc0
+            cells = T.logged_cells(eng.log, True)
+            line["cpu_baseline"] = {"value": cells / dt * 1e-9, "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": f"Wagner build + evaluation of the first {len(sub)} taxa, Python driver over the compiled "
+                                              f"reference on {cores} threads, {dt:.1f} s"}
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bind_to_gpu_numa_node(local_rank: int) -> str:
     """Multi-rank runs: pin this process (and so its pinned host buffers, first touch) to the CPUs of the NUMA node its GPU
     hangs off, so the 8 ranks' host copies do not all cross one socket.  No-op where sysfs has no answer."""
@@ -556,7 +673,9 @@ def main():
     ap.add_argument("--taxa", type=int, default=150, help="tree workload: taxa")
     ap.add_argument("--bp", type=int, default=1500, help="tree workload: bases per taxon")
     ap.add_argument("--spr", type=int, default=400, help="tree workload: SPR neighbours evaluated exactly, in lockstep")
-    ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS),
+    ap.add_argument("--spr-rounds", type=int, default=4, help="cfg5 workload: accepted SPR moves at most")
+    ap.add_argument("--spr-window", type=int, default=16, help="cfg5 workload: candidates evaluated exactly per lockstep call")
+    ap.add_argument("--workload", default="affine500", choices=sorted(WORKLOADS) + ["cfg5"],
                     help="the headline line's workload (affine500 = BASELINE.json configs[1])")
     args = ap.parse_args()
 
@@ -567,6 +686,11 @@ def main():
 
     if args.workload == "tree":
         return bench_tree(args, rank, local_rank, world, cores)
+    if args.workload == "cfg5":
+        if args.impl == "reference":
+            args.workload = "tree"
+            return bench_tree(args, rank, local_rank, world, cores)
+        return bench_cfg5(args, rank, local_rank, world, cores)
 
     wl_desc, wl_mode, ops_per_cell, wl_kernel = WORKLOADS[args.workload]
 

@@ -132,8 +132,10 @@ typedef struct poyb200_config {
     int32_t timing;                    /* 1: CUDA events per chunk for poyb200_last_run_ms; default 1 */
     int32_t trace;                     /* stderr timeline of every one-shot call: 0 off, 1 host, 2 + downloads, 3 + device */
     int64_t dir_budget_bytes;          /* size limit of one direction buffer, 0 = a quarter of the free HBM, <= 40 GB */
-    int32_t use_ring;                  /* 1: ring kernels (fill + traceback in one kernel) for stripes without spare diagonals;
-                                          0: aff_fast_kernel / aff_stripe_kernel + the separate traceback kernel; default 1 */
+    int32_t use_ring;                  /* affine stripes without spare diagonals: 0 aff_fast_kernel / aff_stripe_kernel + the separate
+                                          traceback kernel; 1 ring kernels (fill + traceback in one kernel) for every pair;
+                                          2 aff_fast_kernel + traceback kernel for pairs without gap bits, the full ring instance
+                                          for the others (default: the fastest combination measured, profiles/README.md) */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 
@@ -217,6 +219,34 @@ int poyb200_stage(poyb200_ctx *ctx, int mode, const poyb200_batch *b); /* plan +
 int poyb200_run(poyb200_ctx *ctx);                                      /* kernels only, asynchronous */
 int poyb200_sync(poyb200_ctx *ctx);                                     /* wait for the context's stream */
 int poyb200_fetch(poyb200_ctx *ctx);                                    /* D2H into the staged batch's outputs */
+
+/* --- device-resident sequence store ---------------------------------------------------------------------------
+ * Sequences live in HBM; batches name their operands by store id and what they produce is appended to the store ON
+ * THE DEVICE, so a tree level (the medians of one downpass depth, the single assignments of one uppass depth) never
+ * crosses the host link with its sequences: per batch 56 bytes per pair go up, 12 come back.  This is what the tree
+ * driver (poyb200_tree.h) runs on.  Reference semantics folded in: the deltaw of Sequence.Align.cost_2
+ * (src/sequence.ml:691-714) is derived from the per-sequence gap counts the store keeps (seq_CAML_count,
+ * src/seq.c:570-582); poyb200_store_closest takes both early exits of Sequence.Align.closest (src/sequence.ml:975-1009).
+ * A store belongs to one context and its cost matrix; it is limited to 4 GiB. */
+typedef struct poyb200_store poyb200_store;
+int poyb200_store_create(poyb200_ctx *ctx, poyb200_store **out);
+void poyb200_store_destroy(poyb200_store *s);
+int32_t poyb200_store_size(const poyb200_store *s);   /* number of sequences */
+int64_t poyb200_store_bytes(const poyb200_store *s);  /* bytes of HBM in use */
+/* uploads n sequences (bytes + off[k], len[k] elements, leading gap included); ids first_id .. first_id + n - 1 */
+int poyb200_store_add(poyb200_store *s, const uint8_t *bytes, const int64_t *off, const int32_t *len, int32_t n, int32_t *first_id);
+int poyb200_store_info(const poyb200_store *s, int32_t id, int32_t *len, int32_t *empty, int32_t *gap_count);
+int poyb200_store_get(poyb200_store *s, int32_t id, uint8_t *out); /* len bytes to the host */
+/* SeqCS.DOS.median for n pairs of store ids (src/seqCS.ml:747-776; both operands non-empty -- the empty-operand rule,
+ * :748-752, needs no alignment and is the caller's): cost[p] and the id of the new median new_id[p] */
+int poyb200_store_median(poyb200_store *s, const int32_t *pairs, int32_t n, int32_t *cost, int32_t *new_id);
+/* SeqCS.DOS.distance / Sequence.Align.cost_2 (src/seqCS.ml:819-867): cost only.  hint[p] = the ?deltaw argument
+ * (DOS.distance passes max 8 |la - lb|), NULL = none; ignored for affine matrices. */
+int poyb200_store_distance(poyb200_store *s, const int32_t *pairs, int32_t n, const int32_t *hint, int32_t *cost);
+/* Sequence.Align.closest s1 s2 (src/sequence.ml:967-1033) for n pairs (s1, s2): new_id[p] = the closest sequence
+ * (s2 itself when it is empty) */
+int poyb200_store_closest(poyb200_store *s, const int32_t *pairs, int32_t n, int32_t *new_id);
+void poyb200_store_stats(const poyb200_store *s, int64_t *calls, int64_t *pairs, int64_t *cells);
 
 /* --- one batch over several GPUs of the node ----------------------------------------------------------------
  * BASELINE.json north_star: "batches shard across the 8 B200s by pair index, with results gathered on the host".

@@ -75,6 +75,9 @@ EXPORTS = [
     "poyb200_batch_align_3", "poyb200_cells_3d", "poyb200_batch_worst_2", "poyb200_batch_median_3",
     "poyb200_multi_create", "poyb200_multi_destroy", "poyb200_multi_last_error", "poyb200_multi_set_cm", "poyb200_multi_batch",
     "poyb200_multi_devices", "poyb200_multi_ctx", "poyb200_multi_launch_count", "poyb200_multi_shards",
+    "poyb200_store_create", "poyb200_store_destroy", "poyb200_store_size", "poyb200_store_bytes", "poyb200_store_add",
+    "poyb200_store_info", "poyb200_store_get", "poyb200_store_median", "poyb200_store_distance", "poyb200_store_closest",
+    "poyb200_store_stats",
 ]
 
 _lib = None
@@ -123,6 +126,20 @@ def lib() -> C.CDLL:
     L.poyb200_multi_launch_count.argtypes = [C.c_void_p]
     L.poyb200_multi_launch_count.restype = C.c_int64
     L.poyb200_multi_shards.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    L.poyb200_store_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.poyb200_store_destroy.argtypes = [C.c_void_p]
+    L.poyb200_store_destroy.restype = None
+    L.poyb200_store_size.argtypes = [C.c_void_p]
+    L.poyb200_store_bytes.argtypes = [C.c_void_p]
+    L.poyb200_store_bytes.restype = C.c_int64
+    L.poyb200_store_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+    L.poyb200_store_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.poyb200_store_get.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.poyb200_store_median.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.poyb200_store_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.poyb200_store_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.poyb200_store_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.poyb200_store_stats.restype = None
     L.poyb200_stage.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
     for f in ("poyb200_run", "poyb200_sync", "poyb200_fetch"):
         getattr(L, f).argtypes = [C.c_void_p]

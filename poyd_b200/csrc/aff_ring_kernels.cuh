@@ -40,7 +40,7 @@ constexpr int RING_PEND = 32;      // pairs a warp fills before its lanes walk t
 // tabR, tabC (int4, 64 classes each: code | prev-gap << 5), LUT of the ring blocks; LUT, prepend and gap tables of the
 // boundary phase; staging barriers; per-group scratch; per-warp pending lists
 constexpr int RING_TABLE_BYTES = 2 * 64 * 16 + 16 * RING_LUT_ROW + STRIPE_LUT_BYTES + 64 * 4 + STRIPE_WARPS * 4 * STAGE_BAR_BYTES +
-                                 STRIPE_WARPS * 4 * RING_SCR_INTS * 4 + STRIPE_WARPS * RING_PEND * 4;
+                                 STRIPE_WARPS * 4 * RING_SCR_INTS * 4 + STRIPE_WARPS * RING_PEND * 4 + 256;
 // The unchecked blocks read codes past an operand's end (rows up to Q G / 2 + D - 2 past it, columns up to G K + D - 1):
 // every staged operand gets that much private slack, so the stray reads never touch another warp's buffers.
 __host__ __device__ constexpr int ring_operand_pad(int K, int G) { return (K * G + 8 + 15) & ~15; }
@@ -392,13 +392,15 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, EBF ? RING_MIN_BLOCKS_EB : 
     StageBars *s_bar = reinterpret_cast<StageBars *>(s_get + 32);  // one staging ring per group (staging.cuh)
     int *s_scr = reinterpret_cast<int *>(s_bar + STRIPE_WARPS * 4);  // RING_SCR_INTS per group
     int *s_pend = s_scr + STRIPE_WARPS * 4 * RING_SCR_INTS;          // RING_PEND task indices per warp
-    uint8_t *s_win = reinterpret_cast<uint8_t *>(s_pend + STRIPE_WARPS * RING_PEND);  // per-thread band windows of the walk
+    uint8_t *s_med = reinterpret_cast<uint8_t *>(s_pend + STRIPE_WARPS * RING_PEND);  // 16 x 16 medians of 4-bit codes (the walk)
+    uint8_t *s_win = s_med + 256;                                                     // per-thread band windows of the walk
     uint8_t *s_seq = s_win + (BT ? STRIPE_WARPS * 32 * ring_walk_window_bytes<K, EBF>() : 0);
     if (threadIdx.x < STRIPE_WARPS * GPW) StageRing<G>::init_bars(&s_bar[threadIdx.x]);
     const int go4 = 4 * cm.gap_open;
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         const int c4 = 4 * __ldg(cm.cost + ((k >> 4) << cm.lcm) + (k & 15));
         s_lut[ring_lut_slot(k >> 4) * (RING_LUT_ROW / 4) + ring_lut_slot(k)] = c4;
+        s_med[k] = __ldg(cm.median + ((k >> 4) << cm.lcm) + (k & 15));
         *reinterpret_cast<int2 *>(s_lut2 + (k >> 4) * LUT_ROW_BYTES + (k & 15) * 8) = make_int2(c4, c4 - 2);
     }
     for (int k = threadIdx.x; k < 64; k += blockDim.x) {
@@ -447,7 +449,8 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, EBF ? RING_MIN_BLOCKS_EB : 
             band.dbase_d = t.dbase;
             band.tshift = t.tshift;
             band.sbuf = smem_u32(s_win + (size_t) threadIdx.x * ring_walk_window_bytes<K, EBF>());
-            aff_walk_pair(t, pool, band, cm, out);
+            aff_walk_pair(t, pool, band, MedianShared{smem_u32(s_med)}, cm, out);
+            if (out.walked) out.walked[t.pair] = 1;
         }
         __syncwarp();
         npend = 0;

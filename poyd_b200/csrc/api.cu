@@ -84,7 +84,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->force_generic = 0;
     cfg->allow_fast = 1;
     cfg->allow_noeb = 1;
-    cfg->use_ring = 1;
+    cfg->use_ring = 2;
     cfg->overlap_traceback = 1;
     cfg->dir_buffers = 3;
     cfg->traceback_threads_per_sm = 512;
@@ -181,6 +181,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->d_dir2.release();
     ctx->d_dir3.release();
     ctx->d_scratch.release();
+    ctx->d_walked.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -264,6 +265,10 @@ static int *next_counter(poyb200_ctx *ctx) {
     return ctx->d_counters.p + ctx->counter_next++;
 }
 static int reset_counters(poyb200_ctx *ctx) {
+    if (ctx->cfg.use_ring == 2 && ctx->staged && (ctx->mode == MODE_ALIGN_AFF)) {
+        CK(ctx->d_walked.reserve(ctx->tasks.size() + 16));
+        CK(cudaMemsetAsync(ctx->d_walked.p, 0, ctx->tasks.size() + 16, ctx->stream));
+    }
     CK(ctx->d_counters.reserve(MAX_COUNTERS));
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, MAX_COUNTERS * sizeof(int), ctx->stream));
     ctx->counter_next = 0;
@@ -272,7 +277,12 @@ static int reset_counters(poyb200_ctx *ctx) {
 
 // True when the pairs of this class are filled AND walked by the ring kernels (no separate traceback launch).
 static bool ring_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
-    return affine && ctx->cfg.use_ring && ring_has_shape(klass);
+    return affine && ctx->cfg.use_ring == 1 && ring_has_shape(klass);
+}
+// use_ring = 2: pairs WITHOUT gap bits take aff_fast_kernel + the traceback kernel, the batches it declines take the full
+// ring instance (fill + walk); the traceback kernel skips what the ring instance walked (OutPtrs::walked).
+static bool mixed_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
+    return affine && ctx->cfg.use_ring == 2 && ring_has_shape(klass) && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0;
 }
 
 static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, const OutPtrs &out) {
@@ -306,7 +316,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     if (klass != KLASS_GENERIC) {
         // pairs without gap bits take aff_fast_kernel; the batches it declines are listed for aff_stripe_kernel
         const int *list = nullptr, *count = nullptr;
-        if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {  // (use_ring = 0)
+        if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
@@ -315,6 +325,13 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             CK(e);
             list = ctx->d_slow_list.p;
             count = cnt;
+            if (mixed_class(ctx, klass, affine)) {
+                const size_t slot = std::max<size_t>(ctx->ring_slot_bytes, 128);
+                CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
+                               ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
+                ctx->launches++;
+                return POYB200_OK;
+            }
         }
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
                                       ctx->sm_count, ctx->stripe_seq_bytes, ctx->cfg.allow_noeb, next_counter(ctx), list, count, ctx->stream);
@@ -511,7 +528,8 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             const int W = t.dhi - t.dlo + 1;
             choose_class(t, affine, bt, W, dcm, allow_stripe);
             if (t.klass != KLASS_GENERIC) pt.max_stripe_len = std::max(pt.max_stripe_len, std::max(t.lr, t.lc));
-            if (bt && ring_class(ctx, t.klass, affine)) pt.ring_slot = std::max(pt.ring_slot, ((size_t) dir_bytes(t) + 127) & ~(size_t) 127);
+            if (bt && (ring_class(ctx, t.klass, affine) || mixed_class(ctx, t.klass, affine)))
+                pt.ring_slot = std::max(pt.ring_slot, ((size_t) dir_bytes(t) + 127) & ~(size_t) 127);
             else pt.maxW = std::max(pt.maxW, W);
             pt.maxcap = std::max<long long>(pt.maxcap, (long long) la + lb + 2);
             pt.klass_or |= t.klass;
@@ -727,7 +745,8 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     uint8_t *const bufs[3] = {ctx->d_dir.p, ctx->d_dir2.p, ctx->d_dir3.p};
     ctx->cur_dir = bufs[ci % nbuf];
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
-                ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride};
+                ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride,
+                (bt && affine && ctx->cfg.use_ring == 2) ? ctx->d_walked.p : nullptr};
     if (two && ci >= (size_t) nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - nbuf], 0));  // the buffer is free again
     if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk; the classes whose fill kernel does not walk its own pairs

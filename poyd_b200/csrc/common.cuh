@@ -92,6 +92,7 @@ struct OutPtrs {
     uint32_t want;
     uint8_t *bits_a, *bits_b, *bits_wg;  // POYB200_WANT_BITSETS rows
     long long bstride;                   // bytes per bitset row (multiple of 4)
+    uint8_t *walked;                     // per pair: 1 once a ring kernel has walked it (the traceback kernel skips it); may be null
 };
 
 __device__ __forceinline__ int cm_cost(const DevCM &c, int a, int b) { return __ldg(c.cost + (a << c.lcm) + b); }

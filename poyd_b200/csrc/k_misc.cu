@@ -45,6 +45,25 @@ cudaError_t median_3_launch(const uint8_t *median3, int lcm, const uint8_t *a, c
     return cudaGetLastError();
 }
 
+cudaError_t store_row_stats_launch(const uint8_t *rows, long long stride, const int *outlen4, int n, int gap, int *stats, cudaStream_t s) {
+    store_row_stats_kernel<<<(n + 3) / 4, 128, 0, s>>>(rows, stride, outlen4, n, gap, stats);
+    return cudaGetLastError();
+}
+cudaError_t store_append_launch(const uint8_t *rows, long long stride, const int *outlen4, const long long *newoff, int n, uint8_t *pool,
+                                cudaStream_t s) {
+    store_append_kernel<<<(n + 3) / 4, 128, 0, s>>>(rows, stride, outlen4, newoff, n, pool);
+    return cudaGetLastError();
+}
+cudaError_t store_equal_launch(const uint8_t *pool, const uint4 *jobs, int n, uint8_t *eq, cudaStream_t s) {
+    store_equal_kernel<<<(n + 3) / 4, 128, 0, s>>>(pool, jobs, n, eq);
+    return cudaGetLastError();
+}
+cudaError_t store_closest_same_launch(DevCM cm, const uint8_t *pool, const uint2 *jobs, int n, uint8_t *rows, long long stride,
+                                      int *outlen4, cudaStream_t s) {
+    store_closest_same_kernel<<<(n + 127) / 128, 128, 0, s>>>(cm, pool, jobs, n, rows, stride, outlen4);
+    return cudaGetLastError();
+}
+
 cudaError_t int32_peak_launch(int kind, int blocks, int threads, int *out, int seed, cudaStream_t stream) {
     if (kind == 0) int32_peak_kernel<0><<<blocks, threads, 0, stream>>>(out, seed);
     else if (kind == 1) int32_peak_kernel<1><<<blocks, threads, 0, stream>>>(out, seed);

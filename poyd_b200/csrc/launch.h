@@ -35,6 +35,13 @@ cudaError_t calc_aligned_2_launch(const int *matrix, DevCM cm, const uint8_t *a,
                                   int n, int *out, cudaStream_t stream);
 cudaError_t median_3_launch(const uint8_t *median3, int lcm, const uint8_t *a, const uint8_t *b, const uint8_t *c, long long in_stride,
                             const int *len, int n, uint8_t *out, long long out_stride, int *out_len, cudaStream_t stream);
+// device-resident sequence store (store.cu)
+cudaError_t store_row_stats_launch(const uint8_t *rows, long long stride, const int *outlen4, int n, int gap, int *stats, cudaStream_t s);
+cudaError_t store_append_launch(const uint8_t *rows, long long stride, const int *outlen4, const long long *newoff, int n, uint8_t *pool,
+                                cudaStream_t s);
+cudaError_t store_equal_launch(const uint8_t *pool, const uint4 *jobs, int n, uint8_t *eq, cudaStream_t s);
+cudaError_t store_closest_same_launch(DevCM cm, const uint8_t *pool, const uint2 *jobs, int n, uint8_t *rows, long long stride,
+                                      int *outlen4, cudaStream_t s);
 constexpr int PEAK_ITERS = 4096;
 constexpr int PEAK_CHAINS = 8;
 cudaError_t int32_peak_launch(int kind, int blocks, int threads, int *out, int seed, cudaStream_t stream);

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(128) aff_traceback_kernel(const Task *__restri
     const int ti = base + (threadIdx.x & 31);
     if ((int) (threadIdx.x & 31) < wpw && ti < ntasks) {
         const Task t = tasks[ti];
-        aff_walk_pair(t, pool, BandBytes(t, dir + t.dir_off), cm, out);
+        if (!(out.walked && out.walked[t.pair]))  // (a ring kernel may have walked the pair already)
+            aff_walk_pair(t, pool, BandBytes(t, dir + t.dir_off), MedianGlobal{cm.median, cm.lcm}, cm, out);
     }
     __syncwarp();
   }
@@ -219,6 +220,69 @@ __global__ void __launch_bounds__(128) median_3_kernel(const uint8_t *__restrict
     const int m = median3[((((size_t) a[o] << lcm) + b[o]) << lcm) + c[o]];
     uint8_t *row = out + (size_t) p * out_stride + (out_stride - L);
     for (int k = 0; k < L; k++) row[k] = (uint8_t) m;
+}
+
+// ---- device-resident sequence store (store.cu) --------------------------------------------------------------------------
+// Result rows of a batch (right aligned, stride bytes, length in outlen4[4 p]) -> per row {length, number of elements
+// carrying the gap bit (seq_CAML_count, src/seq.c:570-582)}.  One warp per row.
+__global__ void __launch_bounds__(128) store_row_stats_kernel(const uint8_t *__restrict__ rows, long long stride,
+                                                              const int *__restrict__ outlen4, int n, int gap, int *__restrict__ stats) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const int L = outlen4[4 * (size_t) p];
+    const uint8_t *src = rows + (size_t) p * stride + (stride - L);
+    int c = 0;
+    for (int k = lane; k < L; k += 32) c += (src[k] & gap) != 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) { stats[2 * p] = L; stats[2 * p + 1] = c; }
+}
+// Copies the result rows to their places in the store's pool.  One warp per row.
+__global__ void __launch_bounds__(128) store_append_kernel(const uint8_t *__restrict__ rows, long long stride,
+                                                           const int *__restrict__ outlen4, const long long *__restrict__ newoff, int n,
+                                                           uint8_t *__restrict__ pool) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const int L = outlen4[4 * (size_t) p];
+    const uint8_t *src = rows + (size_t) p * stride + (stride - L);
+    uint8_t *dst = pool + newoff[p];
+    for (int k = lane; k < L; k += 32) dst[k] = src[k];
+}
+// eq[p] = 1 when the two sequences of pair p have the same length and the same elements (`0 = compare s1 s2`).
+// jobs[p] = {offset a, offset b, length a, length b}.
+__global__ void __launch_bounds__(128) store_equal_kernel(const uint8_t *__restrict__ pool, const uint4 *__restrict__ jobs, int n,
+                                                          uint8_t *__restrict__ eq) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const uint4 jb = jobs[p];
+    int same = jb.z == jb.w;
+    if (same) {
+        const uint8_t *x = pool + jb.x, *y = pool + jb.y;
+        for (int k = lane; k < (int) jb.z; k += 32) same &= (x[k] == y[k]);
+    }
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) eq[p] = (uint8_t) same;
+}
+// Sequence.Align.closest s1 s2 when s1 = s2 (src/sequence.ml:1000-1009, combination alphabets): the gap bits past the
+// first element are cleared, every element x becomes get_closest x x, gaps are removed and one is prepended.  Writes a
+// right-aligned row of `stride` bytes and outlen4[4 p].  One thread per sequence.
+// jobs[p] = {offset, length}.
+__global__ void __launch_bounds__(128) store_closest_same_kernel(DevCM cm, const uint8_t *__restrict__ pool,
+                                                                 const uint2 *__restrict__ jobs, int n, uint8_t *rows, long long stride,
+                                                                 int *outlen4) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int L = (int) jobs[p].y, gap = cm.gap;
+    const uint8_t *s = pool + jobs[p].x;
+    uint8_t *row = rows + (size_t) p * stride;
+    int pos = (int) stride;
+    for (int k = L - 1; k >= 0; k--) {
+        int x = s[k];
+        if (k > 0) x &= ~gap;
+        const int sel = closest_elem(cm, x, x);
+        if (sel != gap) row[--pos] = (uint8_t) sel;
+    }
+    row[--pos] = (uint8_t) gap;
+    outlen4[4 * (size_t) p] = (int) stride - pos;
 }
 
 }  // namespace poyb200

@@ -79,11 +79,52 @@ struct BandBytes {
     }
 };
 
+// One operand read backwards, element by element: the walk consumes indices in descending order, one step at a time, so
+// the reader keeps the aligned 32-bit word that holds the current element and the word below it, and fetches the next word
+// a whole word (up to four steps) before it is needed -- the element itself never waits for a global load.
+struct SeqBack {
+    uintptr_t acur, lo;  // aligned address of `cur`; lowest address that may be read
+    uint32_t cur, nxt;
+    const uint8_t *base;
+    __device__ __forceinline__ void init(const uint8_t *pool, const uint8_t *seq, int i) {
+        base = seq;
+        lo = reinterpret_cast<uintptr_t>(pool) & ~(uintptr_t) 3;
+        acur = reinterpret_cast<uintptr_t>(seq + i) & ~(uintptr_t) 3;
+        cur = __ldg(reinterpret_cast<const uint32_t *>(acur));
+        nxt = (acur >= lo + 4) ? __ldg(reinterpret_cast<const uint32_t *>(acur - 4)) : 0u;
+    }
+    __device__ __forceinline__ int get(int i) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base + i);
+        if ((a & ~(uintptr_t) 3) != acur) {  // one word down
+            acur -= 4;
+            cur = nxt;
+            nxt = (acur >= lo + 4) ? __ldg(reinterpret_cast<const uint32_t *>(acur - 4)) : 0u;
+        }
+        return (int) ((cur >> (8 * (a & 3))) & 0xffu);
+    }
+};
+
+// cm_get_median for 4-bit codes from a 16 x 16 byte table in shared memory (the walk of a ring kernel) or from the matrix
+// in global memory.
+struct MedianGlobal {
+    const uint8_t *median;
+    int lcm;
+    __device__ __forceinline__ int get(int a, int b) const { return __ldg(median + (a << lcm) + b); }
+};
+struct MedianShared {
+    uint32_t tab;  // shared address of 256 bytes, index (a << 4) | b
+    __device__ __forceinline__ int get(int a, int b) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tab + ((a << 4) | b)));
+        return (int) v;
+    }
+};
+
 // dcap = device row stride (multiple of 16).
-template <class Band>
-__device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__restrict__ pool, Band band, const DevCM &cm,
-                                              const OutPtrs &out) {
-    const uint8_t *si = pool + t.off_r, *sj = pool + t.off_c;
+template <class Band, class Med>
+__device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__restrict__ pool, Band band, const Med med_lut,
+                                              const DevCM &cm, const OutPtrs &out) {
+    SeqBack si, sj;
     const int dcap = (int) out.stride;
     const size_t row = (size_t) t.pair * out.stride;
     const bool w_clo = out.want & 16;
@@ -103,7 +144,9 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
     ri.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
     rj.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
     int i = t.lr - 1, j = t.lc - 1;
-    int ic = si[i], jc = sj[j];
+    si.init(pool, pool + t.off_r, i);
+    sj.init(pool, pool + t.off_c, j);
+    int ic = si.get(i), jc = sj.get(j);
     if (i > 0 && j > 0) band.start(i, j);
     int nmed = 0, nwg = 0, nres = 0, med_first = -1, nclo = 0;
     // The reference's mode machine (m_todo / vertical / horizontal / diagonal / align, :2003-2075) and its two tails
@@ -127,7 +170,7 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
         const bool isH = eff == AM_H, isV = eff == AM_V, isA = eff == AM_A, isD = eff == AM_D;
         const int a_el = isH ? TMPGAP : ic, b_el = isV ? TMPGAP : jc;  // the column of resi / resj
         const int x = isV ? ic : jc;                                    // the element an indel column is built from
-        const int p = cm_median(cm, ic & 15, jc & 15);
+        const int p = med_lut.get(ic & 15, jc & 15);
         const int wgv = isA ? p : ((isD || (x & TMPGAP)) ? TMPGAP : (x | TMPGAP));
         const bool emit = isA || (!isD && !(x & TMPGAP));
         nres++;
@@ -150,8 +193,8 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
         mode = isA ? after_align : ((b & endbit) ? M_TODO : eff);
         i -= !isH;
         j -= !isV;
-        ic = si[i];
-        jc = sj[j];
+        ic = si.get(i);
+        jc = sj.get(j);
     }
     band.finish();
     // the leading column: (gap, gap), a gap in medianwg, and a gap in front of the median unless it starts with one

@@ -22,6 +22,13 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/poyb200.h but not exported"
     assert sorted(_lib.EXPORTS) == names, "poyd_b200/_lib.py EXPORTS out of sync with the header"
+    # the tree driver's header (include/poyb200_tree.h)
+    src = open(os.path.join(ROOT, "include", "poyb200_tree.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    tree_names = sorted(set(re.findall(r"\b(poyb200_tree_[a-z0-9_]+)\s*\(", src)))
+    assert len(tree_names) >= 9
+    for n in tree_names:
+        assert hasattr(L, n), f"{n} declared in include/poyb200_tree.h but not exported"
 
 
 def test_no_device_is_a_loud_error():

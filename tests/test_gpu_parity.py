@@ -219,7 +219,7 @@ def test_affine_every_stripe_shape(S, checker_factory, monkeypatch):
     o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
     oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
     # ring kernels (default), the legacy fast / stripe kernels + separate traceback, the generic kernels
-    for config in ({}, {"use_ring": 0}, {"use_ring": 0, "allow_fast": 0}, {"force_generic": 1}):
+    for config in ({}, {"use_ring": 1}, {"use_ring": 0}, {"use_ring": 0, "allow_fast": 0}, {"force_generic": 1}):
         al = S.Align(cm, config=config)
         g = al.align_affine_3(pool, pairs, ALL)
         assert_aligned_equal(g, o, label=f"affine shapes {config}")

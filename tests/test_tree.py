@@ -176,3 +176,57 @@ def test_read_fasta_follows_the_reference_parser(tmp_path):
     assert [f.tolist() for f in taxa[1][1]] == [[16, 1, 2, 4, 8], [16, 12, 31]]
     # trees: blanks or commas, annotations ignored, several trees per file
     assert T.parse_trees("(A (B C))[12.] (A,(B,C));") == [["A", ["B", "C"]], ["A", ["B", "C"]]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(REGIMES))
+def test_reference_tree_costs_native_driver(tmp_path, k):
+    """The same 52 reference goldens through the C++ driver (include/poyb200_tree.h) on the device-resident store."""
+    from poyd_b200 import tree_native as TN
+
+    cm = _cm(k)
+    for n in range(len(FILES)):
+        fa, tr, want = _case(tmp_path, k, n)
+        got = TN.tree_cost_native(cm, fa, tr)
+        assert got.adjusted == want, f"{FILES[n]} regime {k}: {got.adjusted} != {want}"
+
+
+@pytest.mark.gpu
+def test_native_driver_matches_python_driver_step_by_step():
+    """Wagner build (every step, the topology), evaluation (costs, root, every single assignment), lockstep evaluation of an
+    SPR neighbourhood, and the SPR search's invariants -- C++ driver on the store against tree.py over the CPU checker."""
+    from oracle import oracle
+    from oracle.tree_engine import OracleEngine
+    from poyd_b200 import synth, tree_native as TN
+
+    oracle.build(ref=True)
+    for cm, alphabet in ((CM.default_nucleotides(), "dna"), (CM.nucleotides(1, 2, 3), "dna"), (CM.default_aminoacids(), "protein")):
+        leaves = synth.taxa_on_random_tree(20, 300 if alphabet == "dna" else 120, seed=21, subst=0.05, indel=0.01, alphabet=alphabet)
+        ev = TN.NativeEvaluator(cm, leaves)
+        try:
+            tn, sn = ev.wagner()
+            cn = ev.evaluate(tn, keep=True)
+            evc = T.Evaluator(OracleEngine(cm, nthreads=8), cm)
+            tc, sc = evc.wagner(leaves)
+            cc = evc.evaluate(tc, leaves, keep=True)
+            assert [(s["taxon"], s["edge"], s["delta"]) for s in sn] == [(s["taxon"], s["edge"], s["delta"]) for s in sc]
+            assert tn.nodes == tc.nodes and tn.handle == tc.handle
+            assert (cn.adjusted, cn.unadjusted, cn.root) == (cc.adjusted, cc.unadjusted, cc.root)
+            for v in cc.singles:
+                for l, want in enumerate(cc.singles[v]):
+                    assert np.array_equal(ev.single(0, v, l), want), (v, l)
+            nbrs = T.spr_neighbours(tc, limit=16, seed=2)
+            many_n = ev.evaluate_many(nbrs, keep=True)
+            many_c = evc.evaluate_many(nbrs, leaves, keep=True)
+            assert [(a.adjusted, a.unadjusted, a.root) for a in many_n] == [(b.adjusted, b.unadjusted, b.root) for b in many_c]
+            # SPR search: never worse than the start, the final topology is a binary tree over the same taxa whose
+            # (independently evaluated) cost is the reported one
+            final, st = ev.spr(tn, max_rounds=3, window=8)
+            assert st["start_cost"] == cn.adjusted and st["final_cost"] <= st["start_cost"]
+            assert sorted(v for v in final.nodes if final.is_leaf(v)) == sorted(leaves)
+            assert all(u in final.nodes[v] for u in final.nodes for v in final.nodes[u])
+            cold = T.Evaluator(OracleEngine(cm, nthreads=8), cm).evaluate(final, leaves)
+            assert cold.adjusted == st["final_cost"]
+            assert st["joins_swept"] > 0 and st["breaks"] > 0
+        finally:
+            ev.close()

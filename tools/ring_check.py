@@ -39,7 +39,7 @@ def main():
         pool, pairs = synth.pair_batch(3000, 500, seed=5, min_len=450, **kw)
         o = chk.batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
         oc = chk.batch(2, pool.pool, pool.off, pool.len, pairs, nthreads=8)["cost"]
-        for cfg in ({}, {"use_ring": 0}):
+        for cfg in ({}, {"use_ring": 1}, {"use_ring": 0}):
             al = S.Align(cm, config=cfg)
             g = al.align_affine_3(pool, pairs, 7)
             ok &= compare(f"{name} {cfg}", g, o)
