@@ -113,6 +113,7 @@ struct poyb200_ctx {
     bool in_order = true;           // tasks[k].pair == k
     cudaStream_t s_in = nullptr, s_out = nullptr, s_tb = nullptr, s_len = nullptr;
     DevBuf<uint8_t> d_scratch;       // ring kernels: per-warp band slots (aff_ring_kernels.cuh)
+    DevBuf<uint8_t> d_walked;        // use_ring = 2: pairs the full ring instance walked
     size_t ring_slot_bytes = 0;      // largest band of a ring-class pair of the staged batch
     DevBuf<uint8_t> d_dir2, d_dir3;  // further direction buffers: the traceback of chunk k runs under the fills of chunks k+1, k+2
     uint8_t *cur_dir = nullptr;
