@@ -274,6 +274,11 @@ class Reference(_Base):
         n = self.L.ref_median_2(self.h, which, _p(a, _u8p), _p(b, _u8p), len(a), _p(out, _u8p))
         return out[:n].copy()
 
+    def worst_2(self, a, b):
+        """algn_worst_2 (src/algn.c:3373) of an aligned pair."""
+        a, b = _u8(a), _u8(b)
+        return int(self.L.ref_worst_2(self.h, _p(a, _u8p), _p(b, _u8p), len(a)))
+
     def align_affine_3(self, sa, sb, want_dir=False):
         sa, sb = _u8(sa), _u8(sb)
         cap = len(sa) + len(sb) + 2

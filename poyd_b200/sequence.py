@@ -345,6 +345,19 @@ class Align:
         """``Sequence.Align.median_2`` (src/sequence.ml:907-918)."""
         return self._median(2, a, b, lens)
 
+    def worst_2(self, a, b, lens, verify: bool = False) -> np.ndarray:
+        """``Sequence.Align.max_cost_2`` (``algn_CAML_worst_2``, src/algn.c:3382; verify=True: ``algn_CAML_verify_2``, :3395) on
+        rows of LEFT-aligned aligned sequences."""
+        a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        if a.shape != b.shape:
+            raise ValueError("The size of the sequences is not the same.")
+        n, stride = a.shape
+        out = np.zeros(n, np.int32)
+        self._check(self.L.poyb200_batch_worst_2(self.h, 1 if verify else 0, a.ctypes.data, b.ctypes.data, stride, lens.ctypes.data, n,
+                                                 out.ctypes.data))
+        return out
+
     def full_median_2(self, pool: SeqPool, pairs):
         """``Sequence.Align.full_median_2`` (src/sequence.ml:949-957): the affine median, or align_2 followed
         by median_2 (no gaps).  Returns (rows, lens), rows right aligned."""

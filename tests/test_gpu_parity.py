@@ -600,3 +600,63 @@ def test_multi_device_call_matches_single_device(S, checker_factory):
         assert cuts[0] == 0 and cuts[-1] == len(pairs) and np.all(np.diff(cuts) > 0), cuts
         ma.close()
         al.close()
+
+
+@pytest.mark.parametrize("affine", [False, True])
+def test_uppass_three_medians_and_union_distance(S, affine):
+    """SeqCS.DOS.median_3_no_union / median_3_union / distance and SeqCS.Union.distance_union (src/seqCS.ml:778-867,
+    1569-1616) as batches, against the same compositions of the compiled reference's own functions (align_2 /
+    align_affine_3, median_2, worst_2), vertex by vertex."""
+    from oracle import oracle
+    from poyd_b200 import cost_matrix as CM, seqcs, synth
+
+    oracle.build(ref=True)
+    cm = CM.nucleotides(1, 2, 3) if affine else CM.default_nucleotides()
+    chk = oracle.Reference(cm)
+    gap = cm.gap
+    pool, pairs = synth.ragged_batch(150, max_len=220, seed=71, gap_ambiguity=0.04 if affine else 0.0, min_len=5)
+    n = 100
+    parent, c1, c2 = pairs[:n, 0], pairs[:n, 1], pairs[50:50 + n, 1]
+    al = S.Align(cm)
+    dos = seqcs.DOS(al)
+
+    def ref_align(a, b):  # Sequence.Align.align_2: affine matrices are diverted to align_affine_3 (src/sequence.ml:851-858)
+        if affine:
+            c, _, _, ra, rb = chk.align_affine_3(a, b)
+            return ra, rb, c
+        c, ra, rb = chk.align_2(a, b, int(al.deltaw_for(S.SeqPool([a, b]), np.array([[0, 1]], np.int32))[0]))
+        return ra, rb, c
+
+    def ref_with_parent(p, c):
+        ra, rb, cost = ref_align(p, c)
+        return chk.median_2(2, ra, rb), cost, chk.worst_2(ra, rb)
+
+    seqs, cmin, cmax = dos.median_3_no_union(pool, parent, c1, c2)
+    for k in range(n):
+        m1, k1, w1 = ref_with_parent(pool.seq(int(parent[k])), pool.seq(int(c1[k])))
+        m2, k2, w2 = ref_with_parent(pool.seq(int(parent[k])), pool.seq(int(c2[k])))
+        m, c, w = (m1, k1, w1) if k1 < k2 else (m2, k2, w2)
+        if len(m) == 0 or m[0] != gap:
+            m = np.concatenate([[gap], m]).astype(np.uint8)
+        assert np.array_equal(seqs[k], m) and cmin[k] == c and cmax[k] == w, k
+    # median_3_union: the aligned children of a vertex = the aligned pair of (c1, c2)
+    al_a, al_b = [], []
+    for k in range(n):
+        ra, rb, _ = ref_align(pool.seq(int(c1[k])), pool.seq(int(c2[k])))
+        al_a.append(ra)
+        al_b.append(rb)
+    useqs, ucost, uworst = dos.median_3_union(pool, parent, al_a, al_b)
+    for k in range(n):
+        u = np.bitwise_or(al_a[k], al_b[k])
+        ra, rb, c = ref_align(pool.seq(int(parent[k])), u)
+        m = chk.median_2(2, ra, rb)
+        if len(m) == 0 or m[0] != gap:
+            m = np.concatenate([[gap], m]).astype(np.uint8)
+        assert np.array_equal(useqs[k], m) and ucost[k] == c and uworst[k] == chk.worst_2(ra, rb), k
+    # distances with the DOS.distance hint; Union.distance_union scales them
+    d = dos.distance(pool, pairs[:n])
+    la, lb = pool.len[pairs[:n, 0]].astype(np.int64), pool.len[pairs[:n, 1]].astype(np.int64)
+    want = al.cost_2(pool, pairs[:n], deltaw=np.maximum(np.abs(la - lb), 8))
+    assert np.array_equal(d, want)
+    assert np.allclose(seqcs.Union(al).distance_union(pool, pairs[:n]), (0.8 if affine else 1.0) * want)
+    al.close()
