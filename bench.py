@@ -828,10 +828,10 @@ def main():
                                     "rank 0, all_reduce of the shard cost totals; checked against the gathered costs"}
         alg.close()
         D.barrier()
-        # (2) inside one process: rank 0 alone runs ONE batch of world x pairs through poyb200_multi_batch over all GPUs
-        #     (host thread per device, results land in one set of pinned buffers); the other ranks wait
+        # (2) inside one process: rank 0 alone runs ONE batch (world x pairs, at most 2 M pairs) through poyb200_multi_batch
+        #     over all GPUs (host thread per device, results land in one set of pinned buffers); the other ranks wait
         if rank == 0:
-            cmm, poolm, pairsm, _ = workload(args.pairs * world, seed=91, name="affine500")
+            cmm, poolm, pairsm, _ = workload(min(args.pairs * world, 2_000_000), seed=91, name="affine500")
             cellsm = total_cells(poolm, pairsm, None)
             ma = S.MultiAlign(cmm, list(range(world)))
             batch, keep, info = pinned_batch(S, ma, poolm, pairsm, None, 0, torch)

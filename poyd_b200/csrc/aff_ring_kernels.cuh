@@ -50,6 +50,13 @@ __host__ __device__ constexpr int ring_operand_pad(int K, int G) { return (K * G
 #ifndef RING_MIN_BLOCKS_EB
 #define RING_MIN_BLOCKS_EB 2
 #endif
+// Double steps per unrolled block of the full (block-diagonal) instance with K = 5.  A whole ring turn (6) needs no register
+// moves but is 42 KB of code, and the kernel then waits for instructions more than for anything else (ncu: "no instruction"
+// 0.59 stalls per issue, profiles/README.md); half a turn (3) halves the code and rotates the windows by three slots -- 30
+// register moves per 30 cells -- at the end of the block.
+#ifndef RING_EB_UNROLL
+#define RING_EB_UNROLL 3
+#endif
 
 __device__ __forceinline__ int lds_s32(uint32_t a) {
     int v;
@@ -168,6 +175,7 @@ struct AffRing {
     static constexpr int Q = 2 * K, P = K + 1, BL = RingFmt<K, EBF>::BL;
     static constexpr bool DIR6 = RingFmt<K, EBF>::DIR6;
     static constexpr int NEB = EBF ? Q : 1, NW = EBF ? P : 1;
+    static constexpr int UN = (EBF && K == 5 && (P % RING_EB_UNROLL) == 0) ? RING_EB_UNROLL : P;  // double steps per block
 
     int cb[Q], ev[Q], eh[Q], eb[NEB];  // cb carries tag 0 here (4 * CB); ev, eh, eb their state tags
     // row window:  Rv = 4 * vertical extension, Rl = shared address of the LUT row;
@@ -298,11 +306,21 @@ struct AffRing {
         }
     }
 
-    // One block of P double steps starting at double step u (every lane at rows and columns >= 2), lane origin
+    template <class T, int N>
+    static __device__ __forceinline__ void rotate(T (&a)[N]) {  // a[s] <- a[(s + UN) % N]
+        if (N != P || UN == P) return;
+        T t[N];
+#pragma unroll
+        for (int s_ = 0; s_ < N; s_++) t[s_] = a[(s_ + UN) % N];
+#pragma unroll
+        for (int s_ = 0; s_ < N; s_++) a[s_] = t[s_];
+    }
+
+    // One block of UN double steps starting at double step u (every lane at rows and columns >= 2), lane origin
     // (i0, j0).  dptr = the address this lane's chunk of local step 0 has once the pair's tile origin is folded in.
     __device__ __forceinline__ void block(int u, int i0, int j0, uint8_t *dptr) {
 #pragma unroll
-        for (int p = 0; p < P; p++) {
+        for (int p = 0; p < UN; p++) {
             uint32_t de[2] = {0, 0}, dod[2] = {0, 0};
             int by[K];
             // ---- even step: q = 2m, cell (i0 + p - m, j0 + p + m)
@@ -361,6 +379,10 @@ struct AffRing {
             // ---- windows: row i0 + p + 1 and column j0 + p + K + 1 enter
             load_row((p + 1) % P, i0 + p + 1);
             load_col((p + K + 1) % P, j0 + p + K + 1);
+        }
+        if (UN != P) {  // the next block expects its rows / columns in the slots this one started with
+            rotate(Rv); rotate(Cv); rotate(Rl); rotate(Cl);
+            rotate(Rg); rotate(Rgop); rotate(Rgf); rotate(Cg); rotate(Cgop); rotate(Cgf);
         }
     }
 };
@@ -575,7 +597,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, EBF ? RING_MIN_BLOCKS_EB : 
             S.init_windows(i0, j0);
             // local step of (double step u, even half) is 2u - sbase: fold the per-pair part into the pointer
             uint8_t *dptr = dbase + (ptrdiff_t) lane * 8 * BL - (ptrdiff_t) (sbase >> 3) * (G * 8 * BL);
-            for (; u <= u_end; u += P, i0 += P, j0 += P) S.block(u, i0, j0, dptr);
+            for (; u <= u_end; u += S_t::UN, i0 += S_t::UN, j0 += S_t::UN) S.block(u, i0, j0, dptr);
         }
 
         if (valid && lane == lane_f) {

@@ -17,6 +17,9 @@
 // fragments and issued every later instruction once per fragment -- a measured 2x slowdown, profiles/README.md.)
 #pragma once
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -146,11 +149,26 @@ __device__ __forceinline__ int fetch_batch(int *work_counter, int nbatches, cons
 }
 
 // Shared-memory size and ring depth of a launch: two slots unless the second one costs a resident CTA (long operands) or
-// does not fit at all.  fixed = tables + barriers, ring1 = bytes of ONE slot for all groups of the CTA.
+// does not fit at all.  fixed = tables + barriers, ring1 = bytes of ONE slot for all groups of the CTA.  The answer depends
+// only on (kernel, device, sizes) and costs three driver calls, so it is remembered (small batches are launch-latency bound).
+struct StageCfg { size_t smem; int nslots, per_sm; };
 template <typename KernelT>
 static inline cudaError_t stage_ring_config(KernelT kern, size_t fixed, size_t ring1, int threads, size_t &smem, int &nslots,
                                             int &per_sm) {
     constexpr size_t SMEM_MAX = 227 * 1024;
+    static std::mutex mu;
+    static std::map<std::tuple<const void *, int, size_t, size_t>, StageCfg> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple((const void *) kern, dev, fixed, ring1);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            smem = it->second.smem; nslots = it->second.nslots; per_sm = it->second.per_sm;
+            return cudaSuccess;
+        }
+    }
     const size_t s1 = fixed + ring1, s2 = fixed + 2 * ring1;
     // always the architectural maximum: the attribute belongs to the (function, device), which several contexts and host
     // threads share -- a per-launch value would race between them
@@ -166,6 +184,8 @@ static inline cudaError_t stage_ring_config(KernelT kern, size_t fixed, size_t r
     nslots = (occ2 >= occ1 && occ2 >= 1) ? 2 : 1;
     smem = (nslots == 2) ? s2 : s1;
     per_sm = std::max(1, nslots == 2 ? occ2 : occ1);
+    std::lock_guard<std::mutex> g(mu);
+    cache[key] = StageCfg{smem, nslots, per_sm};
     return cudaSuccess;
 }
 

@@ -149,7 +149,10 @@ static int store_run(poyb200_store *s, int mode, uint32_t want, const int32_t *p
     }
     ctx->device_store = true;
     ctx->cur_pool = s->d_pool;
+    ctx->view = true;  // validate the operands pair by pair, not the whole (ever growing) store on every call
+    ctx->view_lo = 0;
     int rc = poyb200_stage_internal(ctx, mode, &b, false);
+    ctx->view = false;
     if (rc == POYB200_OK) {
         cudaError_t e = cudaMemcpyAsync(ctx->d_tasks.p, ctx->tasks.data(), (size_t) n * sizeof(Task), cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, POYB200_ECUDA, cudaGetErrorString(e));

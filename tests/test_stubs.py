@@ -111,6 +111,26 @@ def test_stub_library_exports_every_drop_in_symbol():
         assert hasattr(L, name), name
 
 
+def test_drop_in_link_has_one_definition_of_every_external():
+    """stubs/algn_b200.c + stubs/poyb200_stubs.c link into one library (what libpoycside would contain): the externals'
+    original names resolve (to the GPU stubs), the reference's renamed CPU versions and its untouched externals are there."""
+    import subprocess
+
+    from oracle import oracle
+
+    oracle.build(ref=True)
+    so = os.path.join(ROOT, "oracle", "_ref", "libpoydropin.so")
+    if not os.path.exists(so):
+        pytest.skip("libpoydropin.so not built")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout.split("\n")
+    names = [ln.split()[-1] for ln in syms if ln.strip()]
+    for n in DROP_IN:
+        assert names.count(n) == 1, n
+        assert names.count(n + "_cpu") == 1, n + "_cpu"
+    for n in ("algn_CAML_union", "algn_CAML_myers", "algn_CAML_limit_2", "algn_CAML_create_backtrack", "cm_CAML_create", "seq_CAML_create"):
+        assert names.count(n) == 1, n
+
+
 def _ref_cm(ref: Side, cm):
     """(handle keep-alive, value block) of a cost matrix made by the reference's own cm_set_val (ref_driver.c)."""
     from oracle import oracle
