@@ -724,8 +724,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: no binding"
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # barriers that must not occupy a GPU (see sharded_call below)
     D = Dist(world)
 
     from poyd_b200 import build as _build, sequence as S
@@ -828,6 +830,8 @@ def main():
                                     "rank 0, all_reduce of the shard cost totals; checked against the gathered costs"}
         alg.close()
         D.barrier()
+        # While rank 0 drives every GPU from one process, the other ranks must not hold a kernel on theirs: an NCCL barrier
+        # is a spinning kernel, and two processes on one GPU time-slice.  They wait on the host (gloo) instead.
         # (2) inside one process: rank 0 alone runs ONE batch (world x pairs, at most 2 M pairs) through poyb200_multi_batch
         #     over all GPUs (host thread per device, results land in one set of pinned buffers); the other ranks wait
         if rank == 0:
@@ -850,7 +854,8 @@ def main():
                              "what": "one poyb200_multi_batch call (csrc/multi.cu) on one batch of N x pairs, DOS.median payload, "
                                      "pinned host buffers in and out: the north_star's shard-by-pair-index + host gather"}
             ma.close()
-        D.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
 
     if rank != 0:
         if world > 1:

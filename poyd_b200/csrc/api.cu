@@ -285,7 +285,8 @@ static bool mixed_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
     return affine && ctx->cfg.use_ring == 2 && ring_has_shape(klass) && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0;
 }
 
-static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, const OutPtrs &out) {
+static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, const OutPtrs &out,
+                       int seq_bytes) {
     if (n <= 0) return POYB200_OK;
     if (ring_class(ctx, klass, affine)) {
         // pairs without gap bits take the instance without the block-diagonal state, which lists the batches it declines
@@ -296,19 +297,19 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             CK(ctx->d_slow_list.reserve((size_t) n + 8));
             int *cnt = next_counter(ctx);
             CK(ring_launch(klass, bt, false, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
-                           ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), nullptr, nullptr, ctx->d_slow_list.p, cnt, ctx->stream));
+                           ctx->sm_count, seq_bytes, next_counter(ctx), nullptr, nullptr, ctx->d_slow_list.p, cnt, ctx->stream));
             ctx->launches++;
             list = ctx->d_slow_list.p;
             count = cnt;
         }
         CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
-                       ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
+                       ctx->sm_count, seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
         ctx->launches++;
         return POYB200_OK;
     }
     if (klass >= KLASS_LIN_BASE) {
         cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
-                                          ctx->sm_count, ctx->stripe_seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
+                                          ctx->sm_count, seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -320,7 +321,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
-                                        ctx->stripe_seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt, ctx->stream);
+                                        seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt, ctx->stream);
             ctx->launches++;
             CK(e);
             list = ctx->d_slow_list.p;
@@ -328,13 +329,13 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             if (mixed_class(ctx, klass, affine)) {
                 const size_t slot = std::max<size_t>(ctx->ring_slot_bytes, 128);
                 CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
-                               ctx->sm_count, ctx->stripe_seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
+                               ctx->sm_count, seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
                 ctx->launches++;
                 return POYB200_OK;
             }
         }
         cudaError_t e = stripe_launch(klass, affine, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
-                                      ctx->sm_count, ctx->stripe_seq_bytes, ctx->cfg.allow_noeb, next_counter(ctx), list, count, ctx->stream);
+                                      ctx->sm_count, seq_bytes, ctx->cfg.allow_noeb, next_counter(ctx), list, count, ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
@@ -758,7 +759,11 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
         size_t e = k;
         const uint32_t klass = ctx->tasks[k].klass;
         while (e < ch.end && ctx->tasks[e].klass == klass) e++;
-        int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k), out);
+        // shared memory per staged operand: the longest sequence of THIS class group (a few long pairs of another class must
+        // not cost the short ones their occupancy)
+        int longest = 16;
+        for (size_t q = k; q < e; q++) longest = std::max(longest, std::max(ctx->tasks[q].lr, ctx->tasks[q].lc));
+        int rc = launch_fill(ctx, klass, affine, bt, ctx->d_tasks.p + k, (int) (e - k), out, (longest + 15) & ~15);
         if (rc) return rc;
         if (bt && !ring_class(ctx, klass, affine)) {
             if (!walk_groups.empty() && walk_groups.back().end == k) walk_groups.back().end = e;

@@ -1,6 +1,8 @@
 // Kernel classes: which fill kernel a pair takes and how its direction band is addressed.  Host-side planner logic shared
 // by api.cu and the kernel translation units; no device code.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace poyb200 {
@@ -14,7 +16,11 @@ struct StripeShape {
 constexpr StripeShape AFF_SHAPES[] = {{5, 8}, {6, 8}, {4, 16}, {6, 16}, {4, 32}, {6, 32}, {8, 32}};
 constexpr int N_AFF_SHAPES = sizeof(AFF_SHAPES) / sizeof(AFF_SHAPES[0]);
 constexpr uint32_t KLASS_AFF_SPARE = 17;
-constexpr int STRIPE_MAX_SEQ_BYTES = 2048;  // per operand, staged in shared memory
+// Longest operand a stripe kernel stages whole in shared memory: 4 warps x (32 / G) pairs x 2 operands must fit next to
+// the tables, the walk windows and the staging barriers (one ring slot; ~170 KB of the 227 KB are left for operands).
+// Past 2048 elements a CTA's operands cost resident CTAs -- occupancy falls with the length -- but every pair up to these
+// caps still runs in a register kernel instead of the generic one (state in global memory, an order of magnitude slower).
+__host__ __device__ constexpr int stripe_max_seq_bytes(int G) { return G >= 32 ? 16384 : (G >= 16 ? 10240 : 5120); }
 
 struct LinShape {
     int K, G;
@@ -28,10 +34,10 @@ constexpr int LIN_MAX_LCM = 6;
 static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
     if (!affine) return false;
     if (cm.lcm != 5 || cm.gap != 16) return false;  // aff_cell_dna assumes the nucleotide encoding
-    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
     for (int s = 0; s < N_AFF_SHAPES; s++) {
         const int K = AFF_SHAPES[s].K, G = AFF_SHAPES[s].G;
         if (2 * K * G >= W + 1) {
+            if (std::max(t.lr, t.lc) > stripe_max_seq_bytes(G)) continue;  // a wider group stages fewer pairs per CTA
             t.G = G;
             t.twoK = 2 * K;
             t.BL = (K <= 4) ? 4 : 8;
@@ -61,10 +67,10 @@ static inline bool fast_has_shape(uint32_t klass) { return ring_has_shape(klass)
 
 static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
     if (cm.lcm > LIN_MAX_LCM) return false;
-    if (t.lr > STRIPE_MAX_SEQ_BYTES || t.lc > STRIPE_MAX_SEQ_BYTES) return false;
     for (int s = 0; s < N_LIN_SHAPES; s++) {
         const int K = LIN_SHAPES[s].K, G = LIN_SHAPES[s].G;
         if (2 * K * G >= W) {
+            if (std::max(t.lr, t.lc) > stripe_max_seq_bytes(G)) continue;
             const int d0 = t.dhi + 1 - 2 * K * G;
             t.klass = KLASS_LIN_BASE + s;
             t.G = G;

@@ -23,6 +23,11 @@ struct Topo {
     std::vector<int> ids;  // present vertices, ascending
     int handle = -1;
     bool is_leaf(int v) const { return deg[v] == 1; }
+    // index of the directional node (a looking away from b) in a flat per-tree table of 3 * nb.size() entries
+    size_t dix(int a, int b) const {
+        const auto &n = nb[a];
+        return (size_t) 3 * a + (n[0] == b ? 0 : (n[1] == b ? 1 : 2));
+    }
     void other_two(int nbr, int v, int &x, int &y) const {  // src/tree.ml:989-1010
         const auto &n = nb[v];
         if (nbr == n[0]) { x = n[1]; y = n[2]; }
@@ -83,6 +88,9 @@ void topo_write(const Topo &t, int32_t *ids, int32_t *nbr, int32_t *n_nodes, int
     if (handle) *handle = t.handle;
 }
 
+// signature of every directional node of one tree, by Topo::dix; -1 = not known yet
+using SigMap = std::vector<int>;
+
 struct NodeInfo {
     std::vector<int> idx;  // store id per locus
     int64_t cost = 0;      // total cost of the subtree
@@ -132,6 +140,7 @@ struct poyb200_tree {
     }
     void reset() {
         sig_.clear(); node_.clear(); fresh_.clear(); edge_.clear(); leafsig_.clear(); clo_.clear(); dist_.clear();
+        sig_.reserve(1 << 18); edge_.reserve(1 << 18); dist_.reserve(1 << 18); clo_.reserve(1 << 14);
         n_medians = 0;
     }
     // The store only grows (every median ever computed stays, which is what makes the cache work); a long search trims it:
@@ -198,31 +207,32 @@ struct poyb200_tree {
     }
 
     // Signature of every directional node (u, v) = u looking away from v; missing medians are only registered.
-    int collect(const Topo &t, std::unordered_map<Key, int> &sig) {
+    int collect(const Topo &t, SigMap &sig) {
+        sig.assign(3 * t.nb.size(), -1);
         std::vector<std::pair<int, int>> stack;
         for (int u : t.ids) {
             for (int q = 0; q < t.deg[u]; q++) {
                 stack.push_back({u, t.nb[u][q]});
                 while (!stack.empty()) {
                     auto [a, b] = stack.back();
-                    if (sig.count(key2(a, b))) { stack.pop_back(); continue; }
+                    if (sig[t.dix(a, b)] >= 0) { stack.pop_back(); continue; }
                     if (t.is_leaf(a)) {
                         int s;
                         int rc = leaf(a, s);
                         if (rc) return rc;
-                        sig[key2(a, b)] = s;
+                        sig[t.dix(a, b)] = s;
                         stack.pop_back();
                         continue;
                     }
                     int x, y;
                     t.other_two(b, a, x, y);
-                    const bool hx = sig.count(key2(x, a)), hy = sig.count(key2(y, a));
+                    const bool hx = sig[t.dix(x, a)] >= 0, hy = sig[t.dix(y, a)] >= 0;
                     if (!hx || !hy) {
                         if (!hx) stack.push_back({x, a});
                         if (!hy) stack.push_back({y, a});
                         continue;
                     }
-                    int sx = sig[key2(x, a)], sy = sig[key2(y, a)];
+                    int sx = sig[t.dix(x, a)], sy = sig[t.dix(y, a)];
                     // Node.cs_median: the operand with the smaller min_child_code first (src/node.ml:343-348)
                     if (!(minc(sx) < minc(sy))) std::swap(sx, sy);
                     auto it = sig_.find(key2(sx, sy));
@@ -235,7 +245,7 @@ struct poyb200_tree {
                     } else {
                         s = it->second;
                     }
-                    sig[key2(a, b)] = s;
+                    sig[t.dix(a, b)] = s;
                     stack.pop_back();
                 }
             }
@@ -276,14 +286,14 @@ struct poyb200_tree {
     }
 
     // refresh_all_edges (src/allDirChar.ml:672-700) for several trees: the median across every edge and its root cost
-    int edge_medians_many(const std::vector<const std::unordered_map<Key, int> *> &sigs,
+    int edge_medians_many(const std::vector<const SigMap *> &sigs, const std::vector<const Topo *> &topos,
                           const std::vector<std::vector<std::pair<int, int>>> &edges_all, std::vector<std::vector<Key>> &keys) {
         std::vector<std::pair<int, int>> jobs, res;
         std::vector<Key> todo;
         keys.assign(sigs.size(), {});
         for (size_t ti = 0; ti < sigs.size(); ti++) {
             for (auto [a, b] : edges_all[ti]) {
-                int sa = sigs[ti]->at(key2(a, b)), sb = sigs[ti]->at(key2(b, a));
+                int sa = (*sigs[ti])[topos[ti]->dix(a, b)], sb = (*sigs[ti])[topos[ti]->dix(b, a)];
                 if (!(node_[sa].minc < node_[sb].minc)) std::swap(sa, sb);
                 const Key k = key2(sa, sb);
                 keys[ti].push_back(k);
@@ -361,7 +371,7 @@ struct poyb200_tree {
         if (!keep) reset();
         fresh_.clear();
         const size_t nt = topos.size();
-        std::vector<std::unordered_map<Key, int>> sigs(nt);
+        std::vector<SigMap> sigs(nt);
         for (size_t ti = 0; ti < nt; ti++) {
             int rc = collect(topos[ti], sigs[ti]);
             if (rc) return rc;
@@ -369,10 +379,11 @@ struct poyb200_tree {
         int rc = flush();
         if (rc) return rc;
         std::vector<std::vector<std::pair<int, int>>> edges_all(nt);
-        std::vector<const std::unordered_map<Key, int> *> sp(nt);
-        for (size_t ti = 0; ti < nt; ti++) { edges_all[ti] = topos[ti].pre_order_edges(); sp[ti] = &sigs[ti]; }
+        std::vector<const SigMap *> sp(nt);
+        std::vector<const Topo *> tp(nt);
+        for (size_t ti = 0; ti < nt; ti++) { edges_all[ti] = topos[ti].pre_order_edges(); sp[ti] = &sigs[ti]; tp[ti] = &topos[ti]; }
         std::vector<std::vector<Key>> ekeys;
-        rc = edge_medians_many(sp, edges_all, ekeys);
+        rc = edge_medians_many(sp, tp, edges_all, ekeys);
         if (rc) return rc;
         // general_pick_best_root with blindly_trust_downpass, tree by tree
         out.assign(nt, poyb200_tree_cost{});
@@ -409,7 +420,7 @@ struct poyb200_tree {
             for (size_t ti = 0; ti < nt; ti++) {
                 const int a = out[ti].root_a, b = out[ti].root_b;
                 const EdgeInfo &E = edge_[ekeys[ti][root_pos[ti]]];
-                const NodeInfo &mine = node_[sigs[ti][key2(a, b)]];
+                const NodeInfo &mine = node_[sigs[ti][topos[ti].dix(a, b)]];
                 for (int l = 0; l < n_loci; l++) jobs.push_back({nonempty_parent(E.idx[l], mine.idx[l]), mine.idx[l]});
             }
             std::vector<int> rs;
@@ -424,7 +435,7 @@ struct poyb200_tree {
         while (!frontier.empty()) {
             std::vector<std::pair<int, int>> jobs;
             for (auto &f : frontier) {
-                const NodeInfo &mine = node_[sigs[f.ti][key2(f.cur, f.parent)]];
+                const NodeInfo &mine = node_[sigs[f.ti][topos[f.ti].dix(f.cur, f.parent)]];
                 for (int l = 0; l < n_loci; l++) jobs.push_back({nonempty_parent(f.ps[l], mine.idx[l]), mine.idx[l]});
             }
             std::vector<int> res;
@@ -535,14 +546,14 @@ extern "C" int poyb200_tree_wagner(poyb200_tree *t, const int32_t *order, int32_
     next_id++;
     for (int s = 2; s < n; s++) {
         const int c = order[s];
-        std::unordered_map<Key, int> sig;
+        SigMap sig;
         int rc = t->collect(topo, sig);
         if (rc) return rc;
         rc = t->flush();
         if (rc) return rc;
         auto edges = topo.pre_order_edges();
         std::vector<std::vector<Key>> ekeys;
-        rc = t->edge_medians_many({&sig}, {edges}, ekeys);
+        rc = t->edge_medians_many({&sig}, {&topo}, {edges}, ekeys);
         if (rc) return rc;
         int csig;
         rc = t->leaf(c, csig);
@@ -596,14 +607,14 @@ static int spr_round(poyb200_tree *t, const Topo &cur, int64_t best, int shard, 
         if (rc0) return rc0;
     }
     // ---- the current tree's directional medians and edge medians (cached: free after the first round)
-    std::unordered_map<Key, int> sig;
+    SigMap sig;
     int rc = t->collect(cur, sig);
     if (rc) return rc;
     rc = t->flush();
     if (rc) return rc;
     auto cur_edges = cur.pre_order_edges();
     std::vector<std::vector<Key>> ck;
-    rc = t->edge_medians_many({&sig}, {cur_edges}, ck);
+    rc = t->edge_medians_many({&sig}, {&cur}, {cur_edges}, ck);
     if (rc) return rc;
     std::unordered_map<Key, Key> edge_key;  // (a, b) either orientation -> edge_ key
     for (size_t q = 0; q < cur_edges.size(); q++) {
@@ -650,7 +661,7 @@ static int spr_round(poyb200_tree *t, const Topo &cur, int64_t best, int shard, 
     }
     res->breaks += (int64_t) breaks.size();
     // ---- medians of the broken trees, all breaks at once
-    std::vector<std::unordered_map<Key, int>> bsig(breaks.size());
+    std::vector<SigMap> bsig(breaks.size());
     for (size_t k = 0; k < breaks.size(); k++) {
         rc = t->collect(breaks[k].rest, bsig[k]);
         if (rc) return rc;
@@ -658,15 +669,16 @@ static int spr_round(poyb200_tree *t, const Topo &cur, int64_t best, int shard, 
     rc = t->flush();
     if (rc) return rc;
     std::vector<std::vector<std::pair<int, int>>> bedges(breaks.size());
-    std::vector<const std::unordered_map<Key, int> *> bsp(breaks.size());
-    for (size_t k = 0; k < breaks.size(); k++) { bedges[k] = breaks[k].rest.pre_order_edges(); bsp[k] = &bsig[k]; }
+    std::vector<const SigMap *> bsp(breaks.size());
+    std::vector<const Topo *> btp(breaks.size());
+    for (size_t k = 0; k < breaks.size(); k++) { bedges[k] = breaks[k].rest.pre_order_edges(); bsp[k] = &bsig[k]; btp[k] = &breaks[k].rest; }
     std::vector<std::vector<Key>> bkeys;
-    rc = t->edge_medians_many(bsp, bedges, bkeys);
+    rc = t->edge_medians_many(bsp, btp, bedges, bkeys);
     if (rc) return rc;
     // ---- the whole sweep: cost_fn = distance(clade root, median across the join edge), every break x every edge
     std::vector<std::pair<int, int>> jobs;
     for (size_t k = 0; k < breaks.size(); k++) {
-        const NodeInfo &clade = t->node_[sig[key2(breaks[k].c, breaks[k].p)]];
+        const NodeInfo &clade = t->node_[sig[cur.dix(breaks[k].c, breaks[k].p)]];
         for (size_t e = 0; e < bedges[k].size(); e++) {
             const EdgeInfo &E = t->edge_[bkeys[k][e]];
             for (int l = 0; l < L; l++) jobs.push_back({clade.idx[l], E.idx[l]});
@@ -682,8 +694,8 @@ static int spr_round(poyb200_tree *t, const Topo &cur, int64_t best, int shard, 
     for (size_t k = 0; k < breaks.size(); k++) {
         const Break &b = breaks[k];
         // break delta: what the median across the broken edge cost (prev root cost - the two sides' own costs)
-        const int64_t b_delta = t->edge_[edge_key[key2(b.p, b.c)]].cost - t->node_[sig[key2(b.c, b.p)]].cost -
-                                t->node_[sig[key2(b.p, b.c)]].cost;
+        const int64_t b_delta = t->edge_[edge_key[key2(b.p, b.c)]].cost - t->node_[sig[cur.dix(b.c, b.p)]].cost -
+                                t->node_[sig[cur.dix(b.p, b.c)]].cost;
         for (size_t e = 0; e < bedges[k].size(); e++) {
             int64_t cc = 0;
             for (int l = 0; l < L; l++, q++) cc += t->dist_[key2(jobs[q].first, jobs[q].second)];
