@@ -703,8 +703,10 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     for (auto &c : ctx->chunks) maxdir = std::max(maxdir, c.dir_bytes);
     if (bt && ctx->ring_slot_bytes) {
         // as many slots per warp as the ring kernels can use, within the direction budget (they run with fewer if need be)
-        const size_t want = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
-        CK(ctx->d_scratch.reserve(std::min(want, std::max(ctx->dir_budget, want / 8))));
+        // never more than one slot group per batch of the call: small calls (a tree level) and long pairs stay cheap
+        const size_t full = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
+        const size_t by_pairs = ((size_t) n / 4 + 1) * 32 * ctx->ring_slot_bytes;
+        CK(ctx->d_scratch.reserve(std::min(std::min(full, by_pairs), ctx->dir_budget)));
     }
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));
@@ -1298,8 +1300,10 @@ extern "C" int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b) 
     CK(ctx->d_ring.reserve(max_ring * (size_t) grid_max));
     if (bt && ctx->ring_slot_bytes) {
         // as many slots per warp as the ring kernels can use, within the direction budget (they run with fewer if need be)
-        const size_t want = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
-        CK(ctx->d_scratch.reserve(std::min(want, std::max(ctx->dir_budget, want / 8))));
+        // never more than one slot group per batch of the call: small calls (a tree level) and long pairs stay cheap
+        const size_t full = ring_scratch_bytes(ctx->sm_count, ctx->ring_slot_bytes);
+        const size_t by_pairs = ((size_t) n / 4 + 1) * 32 * ctx->ring_slot_bytes;
+        CK(ctx->d_scratch.reserve(std::min(std::min(full, by_pairs), ctx->dir_budget)));
     }
     if (bt) {
         CK(ctx->d_dir.reserve(maxdir));

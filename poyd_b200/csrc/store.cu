@@ -9,6 +9,7 @@
 // (src/sequence.ml:975-1009) are taken inside poyb200_store_closest.
 #include <algorithm>
 #include <cstring>
+#include <unordered_map>
 
 #include "ctx.h"
 
@@ -26,6 +27,7 @@ struct poyb200_store {
     std::vector<int32_t> h_stats, h_cost, dw;
     std::vector<long long> h_newoff;
     int64_t pairs_done = 0, calls = 0, cells = 0;
+    std::unordered_map<uint64_t, int64_t> cells_memo;  // DP cells by (len a, len b[, deltaw]): the formulas walk the rows
 };
 
 static int store_reserve(poyb200_store *s, size_t need) {
@@ -165,7 +167,13 @@ static int store_run(poyb200_store *s, int mode, uint32_t want, const int32_t *p
     s->calls++;
     for (int p = 0; p < n; p++) {
         const int la = s->len[pairs[2 * p]], lb = s->len[pairs[2 * p + 1]];
-        s->cells += affine ? poyb200_cells_affine(la, lb) : poyb200_cells_linear(std::max(la, lb), std::min(la, lb), s->dw[p]);
+        const uint64_t key = ((uint64_t) (uint32_t) std::max(la, lb) << 40) | ((uint64_t) (uint32_t) std::min(la, lb) << 20) |
+                             (uint64_t) (affine ? 0 : (s->dw[p] & 0xfffff));
+        auto it = s->cells_memo.find(key);
+        if (it == s->cells_memo.end())
+            it = s->cells_memo.emplace(key, affine ? poyb200_cells_affine(la, lb)
+                                                   : poyb200_cells_linear(std::max(la, lb), std::min(la, lb), s->dw[p])).first;
+        s->cells += it->second;
     }
     return POYB200_OK;
 }
