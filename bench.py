@@ -42,7 +42,7 @@ UNIT = "GCUPS"
 WORKLOADS = {
     # name: (description, mode, reference ops per cell, dominant kernel)
     "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
-                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_ring_kernel<5,8,true,false>"),
+                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_fast_kernel<5,8,true>"),
     "affine500_medianlike": ("configs[1], median-like operands: as affine500 plus 0.5% IUPAC ambiguities and 10% of positions "
                              "carrying the gap bit (what internal-node medians look like; exercises the block-diagonal "
                              "state)", 3, 50, "aff_ring_kernel<5,8,true,true>"),
@@ -752,9 +752,9 @@ def main():
     add_g, mm_g, mix_g = al.int32_peak()
     f_ms = head["phase_ms"]["fill"]
     fill_s = f_ms * 1e-3
-    # launches per chunk: affine = two ring instances (without / with the block-diagonal state; each fills AND walks its
-    # pairs); linear = fill + traceback
-    fill_launches = max(1, head["launches_per_step"] // 2)
+    # launches per chunk: affine = aff_fast_kernel + the full ring instance over the declined list + traceback kernel;
+    # linear = fill + traceback
+    fill_launches = max(1, head["launches_per_step"] // (3 if wl_mode == 3 else 2))
     km = kernel_metrics().get(wl_kernel, {})
     clocks = head.pop("clocks", None)
     sm_hz = ((clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))) * 1e6
@@ -776,9 +776,9 @@ def main():
             "note": "ops_per_cell is the REFERENCE's operation count per cell (SURVEY.md 8d), i.e. algorithmic work; the kernel "
                     "executes fewer instructions than that, so frac can exceed 1; executed_frac = executed warp instructions "
                     "per second / issue slots per second is the utilisation"}
-    # HBM view: both operands in, one direction code per band cell out and in again (the ring kernel walks its own band),
-    # counted as one byte per cell each way
-    alg_bytes = float(cells) + float(pool.len[pairs[:, 0]].astype(np.int64).sum() + pool.len[pairs[:, 1]].astype(np.int64).sum()) + float(cells)
+    # HBM view of the fill kernel: both operands in, one direction byte per band cell out (the band is re-read by the
+    # traceback kernel, not by this one)
+    alg_bytes = float(pool.len[pairs[:, 0]].astype(np.int64).sum() + pool.len[pairs[:, 1]].astype(np.int64).sum()) + float(cells)
     roof_hbm = {"bound": "hbm", "achieved": alg_bytes / fill_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / fill_s * 1e-9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes / fill_launches,
                 "traffic": roof["traffic"], "peak_source": hbm_src, "note": "not the bound: integer min-plus work is ALU-bound"}
