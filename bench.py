@@ -49,7 +49,7 @@ WORKLOADS = {
     "linear500": ("cfg 2-lin: DNA pairs 500 bp, linear gaps (subst 1, indel 2), deltaw as Sequence.Align.cost_2 computes it, "
                   "align_2 + ancestor_2 + median_2_with_gaps", 1, 10, "lin_stripe_kernel<K,G,true>"),
     "protein300": ("configs[2] (3a): protein pairs 300 aa, 22x22 matrix 1/2, deltaw as the product computes it "
-                   "(full matrix, SURVEY.md A15), align_2 + medians", 1, 10, "lin_stripe_kernel<K,G,true>"),
+                   "(full matrix, SURVEY.md A15), align_2 + medians", 1, 10, "lin_rows_kernel<10,32,true>"),
     "protein300_band16": ("configs[2] (3b): protein pairs 300 aa, explicit deltaw 16, align_2 + medians", 1, 10,
                           "lin_stripe_kernel<K,G,true>"),
     "tree": ("configs[4]-style host-driver workload (one GPU per tree): Wagner build with batched candidate-edge sweeps, "

@@ -136,6 +136,7 @@ typedef struct poyb200_config {
                                           traceback kernel; 1 ring kernels (fill + traceback in one kernel) for every pair;
                                           2 aff_fast_kernel + traceback kernel for pairs without gap bits, the full ring instance
                                           for the others (default: the fastest combination measured, profiles/README.md) */
+    int32_t allow_rows;                /* 0: full linear matrices take the diagonal-stripe kernels too (no lin_rows_kernel); default 1 */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 

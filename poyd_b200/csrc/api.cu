@@ -95,6 +95,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->timing = 1;
     cfg->trace = 0;
     cfg->dir_budget_bytes = 0;
+    cfg->allow_rows = 1;
 }
 
 extern "C" int poyb200_create_ex(int device, const poyb200_config *user, poyb200_ctx **out) {
@@ -238,9 +239,10 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
 static inline uint32_t round16(uint32_t v) { return (v + 15u) & ~15u; }
 
 // Picks the fill kernel for one pair and fixes the layout of its direction band.
-static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, bool allow_stripe) {
+static void choose_class(Task &t, bool affine, bool bt, int W, const DevCM &cm, bool allow_stripe, bool allow_rows) {
     (void) bt;
     if (allow_stripe && affine && stripe_choose(t, affine, W, cm)) return;
+    if (allow_stripe && allow_rows && !affine && lin_rows_choose(t, cm)) return;
     if (allow_stripe && !affine && lin_stripe_choose(t, W, cm)) return;
     t.klass = KLASS_GENERIC;
     t.dbase = t.dlo;
@@ -305,6 +307,13 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         CK(ring_launch(klass, bt, true, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->d_scratch.p, ctx->d_scratch.cap, slot, out,
                        ctx->sm_count, seq_bytes, next_counter(ctx), list, count, nullptr, nullptr, ctx->stream));
         ctx->launches++;
+        return POYB200_OK;
+    }
+    if (klass >= KLASS_LINROW_BASE) {
+        cudaError_t e = lin_rows_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
+                                        seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
+        ctx->launches++;
+        CK(e);
         return POYB200_OK;
     }
     if (klass >= KLASS_LIN_BASE) {
@@ -480,6 +489,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
     if (!ctx->tasks.resize((size_t) b->n_pairs)) return fail(ctx, POYB200_ENOMEM, "pinned allocation of the task array failed");
     const DevCM dcm = ctx->dcm;
     const bool allow_stripe = (!ctx->cfg.force_generic);
+    const bool allow_rows = ctx->cfg.allow_rows != 0;
     parallel_for(NT, (size_t) b->n_pairs, [&](size_t lo, size_t hi, int slot) {
         Part pt;  // thread-local: the parts[] entries share cache lines
         struct Commit {
@@ -527,7 +537,7 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
                 if (sw) t.flags |= TF_SWAPED;
             }
             const int W = t.dhi - t.dlo + 1;
-            choose_class(t, affine, bt, W, dcm, allow_stripe);
+            choose_class(t, affine, bt, W, dcm, allow_stripe, allow_rows);
             if (t.klass != KLASS_GENERIC) pt.max_stripe_len = std::max(pt.max_stripe_len, std::max(t.lr, t.lc));
             if (bt && (ring_class(ctx, t.klass, affine) || mixed_class(ctx, t.klass, affine)))
                 pt.ring_slot = std::max(pt.ring_slot, ((size_t) dir_bytes(t) + 127) & ~(size_t) 127);

@@ -29,6 +29,13 @@ constexpr LinShape LIN_SHAPES[] = {{8, 8}, {10, 8}, {12, 8}, {8, 16}, {12, 16}, 
 constexpr int N_LIN_SHAPES = sizeof(LIN_SHAPES) / sizeof(LIN_SHAPES[0]);
 constexpr uint32_t KLASS_LIN_BASE = 32;  // klass = KLASS_LIN_BASE + shape index
 constexpr int LIN_MAX_LCM = 6;
+// Column-striped kernel for full linear matrices (lin_rows_kernels.cuh): a group of G lanes, C columns per lane.
+struct LinRowShape {
+    int C, G;
+};
+constexpr LinRowShape LIN_ROW_SHAPES[] = {{8, 8}, {12, 8}, {16, 8}, {10, 16}, {12, 16}, {16, 16}, {10, 32}, {12, 32}, {16, 32}};
+constexpr int N_LIN_ROW_SHAPES = sizeof(LIN_ROW_SHAPES) / sizeof(LIN_ROW_SHAPES[0]);
+constexpr uint32_t KLASS_LINROW_BASE = 48;  // klass = KLASS_LINROW_BASE + shape index (classes stay below 64)
 
 // Chooses a stripe shape for an affine pair; returns false when the pair must take the generic kernel.
 static inline bool stripe_choose(Task &t, bool affine, int W, const DevCM &cm) {
@@ -64,6 +71,24 @@ static inline bool ring_has_shape(uint32_t klass) {
 }
 // True when the class has a fast kernel (aff_fast_kernel, the ring kernels' predecessor).
 static inline bool fast_has_shape(uint32_t klass) { return ring_has_shape(klass); }
+
+// Full matrices whose shorter operand (the columns) fits one group: the narrowest shape that covers the columns.
+static inline bool lin_rows_choose(Task &t, const DevCM &cm) {
+    if (!(t.flags & TF_FULL) || cm.lcm > LIN_MAX_LCM) return false;
+    for (int s = 0; s < N_LIN_ROW_SHAPES; s++) {
+        const int C = LIN_ROW_SHAPES[s].C, G = LIN_ROW_SHAPES[s].G;
+        if (C * G < t.lc) continue;
+        if (std::max(t.lr, t.lc) > stripe_max_seq_bytes(G)) continue;
+        t.klass = KLASS_LINROW_BASE + s;
+        t.G = G;
+        t.twoK = C;
+        t.BL = 4;
+        t.dbase = 0;
+        t.flags |= TF_DIR2 | TF_ROWMAJ;
+        return true;
+    }
+    return false;
+}
 
 static inline bool lin_stripe_choose(Task &t, int W, const DevCM &cm) {
     if (cm.lcm > LIN_MAX_LCM) return false;

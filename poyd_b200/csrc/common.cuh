@@ -35,6 +35,7 @@ constexpr uint32_t TF_ROWS_ARE_B = 1;  // operand b sits on the rows: swap the a
 constexpr uint32_t TF_FULL = 2;        // linear: full matrix (algn_fill_plane), no edge rules
 constexpr uint32_t TF_SWAPED = 4;      // linear traceback tie flag (backtrack_2d `swaped`)
 constexpr uint32_t TF_DIR2 = 8;        // direction band holds 2-bit resolved moves (linear stripe kernels)
+constexpr uint32_t TF_ROWMAJ = 16;     // direction band in row-major tiles: lane = j / twoK owns twoK columns (lin_rows_kernels.cuh)
 
 struct Task {
     uint32_t off_r, off_c;  // pool offsets of the row / column sequence
@@ -64,6 +65,11 @@ __host__ __device__ __forceinline__ uint64_t dir_index(const Task &t, int i, int
 }
 // Direction code of cell (i, j): a byte, or a 2-bit field of a 32-bit chunk (TF_DIR2).
 __device__ __forceinline__ int dir_fetch(const Task &t, const uint8_t *dbase, int i, int j) {
+    if (t.flags & TF_ROWMAJ) {  // one 32-bit word of 2-bit moves per lane and row, rows tiled by 8
+        const uint32_t lane = (uint32_t) j / t.twoK, m = (uint32_t) j - lane * t.twoK;
+        const uint64_t chunk = ((((uint64_t) ((uint32_t) i >> 3) * t.G + lane) << 3) + ((uint32_t) i & 7)) * 4;
+        return (__ldg(dbase + chunk + (m >> 2)) >> ((m & 3) * 2)) & 3;
+    }
     const uint32_t dd = (uint32_t) ((j - i) - t.dbase), T = (uint32_t) (i + j - t.tshift);
     const uint32_t lane = dd / t.twoK, m = (dd - lane * t.twoK) >> 1;
     const uint64_t chunk = ((((uint64_t) (T >> 3) * t.G + lane) << 3) + (T & 7)) * t.BL;
@@ -72,6 +78,7 @@ __device__ __forceinline__ int dir_fetch(const Task &t, const uint8_t *dbase, in
 }
 // Bytes of one pair's direction band (steps 0 .. lr + lc - 2 - tshift).
 __host__ __device__ __forceinline__ uint64_t dir_bytes(const Task &t) {
+    if (t.flags & TF_ROWMAJ) return (uint64_t) ((t.lr + 7) >> 3) * 8 * t.G * 4;
     return (uint64_t) ((t.lr + t.lc - 1 - t.tshift + 7) >> 3) * 8 * t.G * t.BL;
 }
 

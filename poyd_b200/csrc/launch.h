@@ -22,6 +22,9 @@ cudaError_t ring_launch(uint32_t klass, bool bt, bool ebf, const Task *d_tasks, 
 // ---- linear fills (k_lin_stripe.cu) -----------------------------------------------------------------------------------
 cudaError_t lin_stripe_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                               int *cost, int sm_count, int seq_bytes, int custom_tail, int *work_counter, cudaStream_t stream);
+// full matrices, column-striped (k_lin_rows.cu)
+cudaError_t lin_rows_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
+                            int sm_count, int seq_bytes, int custom_tail, int *work_counter, cudaStream_t stream);
 // ---- generic fills, tracebacks, medians, INT32 probe (k_misc.cu) -------------------------------------------------------
 cudaError_t aff_generic_launch(bool bt, int blocks, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, int4 *state,
                                int state_stride, uint8_t *dir, int *cost, cudaStream_t stream);

@@ -307,6 +307,45 @@ def test_linear_custom_tail_and_prepend_costs(S, checker_factory, monkeypatch):
         al.close()
 
 
+def test_linear_full_matrix_rows_kernel(S, checker_factory):
+    """Full matrices (algn_fill_plane: cases 1 and 3a of algn_fill_plane_2, src/algn.c:893, :936) take the column-striped
+    lin_rows_kernel: every shape of it (columns 1 .. 512), both tie orders, custom tail / prepend costs, against the
+    checker and against the diagonal-stripe kernels (allow_rows = 0)."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    tail_cm = CM.default_nucleotides().clone()
+    rng = np.random.default_rng(21)
+    tail_cm.tail_cost[1:32] = rng.integers(0, 4, size=31)
+    tail_cm.prepend_cost[1:32] = rng.integers(0, 4, size=31)
+    cases = [("dna", CM.default_nucleotides(), "dna"), ("dna_3_1", CM.nucleotides(3, 1), "dna"),
+             ("protein", CM.default_aminoacids(), "protein"), ("dna_custom_tail", tail_cm, "dna")]
+    for name, cm, alph in cases:
+        chk = checker_factory(cm)
+        batches = [synth.ragged_batch(300, max_len=130, seed=31, alphabet=alph, gap_ambiguity=0.02 if alph == "dna" else 0),
+                   synth.pair_batch(64, 500, seed=32, alphabet=alph, min_len=380, indel=0.05),
+                   synth.pair_batch(96, 250, seed=33, alphabet=alph, min_len=100, indel=0.1)]
+        al, al0 = S.Align(cm), S.Align(cm, config={"allow_rows": 0})
+        for bi, (pool, pairs) in enumerate(batches):
+            dw = np.full(len(pairs), 600, np.int32)  # 8 >= l1 - height: the full matrix whatever the lengths
+            o = chk.batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=8)
+            g = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
+            assert_aligned_equal(g, o, label=f"rows kernel {name} batch {bi}")
+            g0 = al0.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True)
+            assert_aligned_equal(g0, o, label=f"stripe kernels on full matrices {name} batch {bi}")
+            assert np.array_equal(al.cost_2(pool, pairs, deltaw=dw, raw_deltaw=True), o["cost"]), f"cost-only rows kernel {name} {bi}"
+            for flag in (0, 1):
+                sw = np.full(len(pairs), flag, np.uint8)
+                ga = al.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True, swaped=sw)
+                gb = al0.align_2(pool, pairs, ALL, deltaw=dw, raw_deltaw=True, swaped=sw)
+                assert np.array_equal(ga.cost, gb.cost) and np.array_equal(ga.lens, gb.lens), f"swaped={flag} {name} batch {bi}"
+                for k, attr in enumerate(("median", "medianwg", "aligned_a", "aligned_b")):
+                    x, y = getattr(ga, attr), getattr(gb, attr)
+                    live = np.arange(x.shape[1])[None, :] >= x.shape[1] - ga.lens[:, k][:, None]
+                    assert np.array_equal(np.where(live, x, 0), np.where(live, y, 0)), f"swaped={flag} {name} batch {bi}: {attr}"
+        al.close()
+        al0.close()
+
+
 def test_linear_generic_matches_stripe(S, checker_factory, monkeypatch):
     from poyd_b200 import cost_matrix as CM, synth
 
