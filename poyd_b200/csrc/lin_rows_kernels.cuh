@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_ROWS_MIN_BLOCKS) lin_ro
                 const int c_al = *reinterpret_cast<const int *>(rowp + colp[c]);
                 int v = min(diag + c_al, min(left + cins[c], up + cdel));  // :381-431, ties resolved by the tags
                 if (ENDP) {
-                    if (j_first + c == nc) v = min(v, up + ctail);
+                    if (j_first + c == nc && nc > 0) v = min(v, up + ctail);  // `if (l > 0)` :551: not on a lone column 0
                 }
                 if (BND) {
                     if (i == 0) {
