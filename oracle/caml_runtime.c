@@ -155,3 +155,22 @@ int camlrt_array_len(value arr) { return (int) Wosize_val(arr); }
 value camlrt_val_int(int x) { return Val_int(x); }
 int camlrt_int_val(value v) { return Int_val(v); }
 void camlrt_bytes_read(value str, unsigned char *out, int n) { memcpy(out, (const void *) str, (size_t) n); }
+
+/* ---- Powell's 3-D aligner in one C call (tests only): powell_3D_align (src/ukkCommon.c:110-145) on fresh blocks.
+ * Sequences with the leading gap; r1..r3 need l1 + l2 + l3 bytes.  Returns the cost, -1 if the stub raised. */
+extern value powell_3D_align(value, value, value, value, value, value, value, value, value);
+int camlrt_powell(const unsigned char *s1, int l1, const unsigned char *s2, int l2, const unsigned char *s3, int l3, int mm, int go,
+                  int ge, unsigned char *r1, unsigned char *r2, unsigned char *r3, int *rlen) {
+    const int cap = l1 + l2 + l3;
+    value a[9];
+    int failed = 0;
+    a[0] = camlrt_seq(s1, l1, l1); a[1] = camlrt_seq(s2, l2, l2); a[2] = camlrt_seq(s3, l3, l3);
+    a[3] = camlrt_seq(NULL, 0, cap); a[4] = camlrt_seq(NULL, 0, cap); a[5] = camlrt_seq(NULL, 0, cap);
+    a[6] = Val_int(mm); a[7] = Val_int(go); a[8] = Val_int(ge);
+    value res = camlrt_call((void *) powell_3D_align, 9, a, &failed);
+    if (failed) return -1;
+    *rlen = camlrt_seq_read(a[3], r1);
+    camlrt_seq_read(a[4], r2);
+    camlrt_seq_read(a[5], r3);
+    return Int_val(res);
+}
