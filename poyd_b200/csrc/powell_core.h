@@ -1,0 +1,562 @@
+// Powell's three-sequence affine-gap aligner (Ukkonen furthest-reaching formulation with check-pointing):
+// src/ukk.checkp.c + src/ukkCommon.c of the reference, the aligner behind Sequence.Align.readjust_3d
+// (src/sequence.ml:1075-1139).  Level-synchronous restatement: one cooperating group of threads per triple.
+//
+// The reference is a memoised recursion: U(ab, ac, d, s) = furthest position on sequence A reachable on diagonal
+// (ab, ac) = (i - j, i - k) with cost d ending in state s (16 states over {match, delete, insert}^3, setup() :247-350),
+// demanded top-down from (final diagonal, d, MMM) for d = 0, 1, 2, ... (doUkk :113-214), then the alignment is recovered by
+// re-running the same computation between check-points (doUkkInLimits / getSplitRecurse :216-367) down to base cases
+// that keep complete `from` pointers (traceBack :370-444).  Every U value and `from` record is a pure function of the
+// pass parameters, so the order of evaluation is free -- except for one thing: the check-point of the FIRST pass is placed
+// by `furthestReached`, the largest U over the cells the recursion happened to have computed so far (:174-180, :597), and a
+// different check-point can give a different (equally optimal) alignment.  So this restatement reproduces exactly WHICH
+// cells the recursion computes at every top-level cost T:
+//   * the demand edges of calcUkk (:608-784) are data-independent: (x, d) asks for (y, d - transCost - contCost) on the
+//     neighbour diagonal for all 16 from-states, for (x, d - 1), and MMM asks for the other states of its own cell;
+//     a demand stops at cells outside withinMatrix (:545-576) and at memoised cells;
+//   * hence the cells computed for a diagonal/state x are a contiguous range of costs lower(x) .. top(x), and top() is the
+//     least fixpoint of  top(y) >= top(x) - w(x -> y)  over the demand edges, seeded with top(root) = T.  Going from T - 1
+//     to T every active top grows by at least one; a relaxation sweep finds what else changed (relax());
+//   * the new cells of a top level are computed in order of their cost (they depend on lower costs, MMM also on the other
+//     states of its own cell), each exactly as calcUkk does (calc()).
+// U lives in a window of Wd costs per (diagonal, state) (the reference keeps 2 maxSingleStep planes and recomputes what it
+// lost, :136-141); every read checks the cost tag, a miss is reported as PW_EWINDOW, never papered over.
+//
+// The same source is compiled for the device (powell_kernel.cuh: PW_TID / PW_NT / PW_SYNC map to a CTA) and, single-threaded,
+// for the host-side test harness (tests/powell_host.cpp) that checks it against the compiled reference without a GPU.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define PW_HD __host__ __device__ __forceinline__
+#else
+#define PW_HD inline
+#endif
+
+namespace poyb200 {
+namespace powell {
+
+constexpr int NS = 16;          // states with at least one match and at most one insert (setup() :264-273)
+constexpr int PW_INF = 5000;    // INFINITY = MAXINT / 2, MAXINT = 10000 (ukkCommon.h:41, ukk.checkp.c:31)
+constexpr int NEGBIG = -(1 << 28);
+enum { PW_OK = 0, PW_EBOX = 1, PW_EWINDOW = 2, PW_ELIST = 3, PW_ESTACK = 4, PW_EINPUT = 5, PW_ECAP = 6 };
+
+struct Tables {
+    int mis, go, ge, maxSingleStep;
+    int da[NS], db[NS], dc[NS];   // which sequences the state's step consumes (neighbours[] + step(), :207-217, :282-293)
+    int cont[NS], second[NS];     // contCost, secondCost (:296-313)
+    int trans[NS][NS];            // transCost[from][to] (:320-337)
+};
+
+// setup() of ukkCommon.c for (misCost, startInsert = startDelete, continueInsert = continueDelete).
+inline void make_tables(Tables &t, int mm, int go, int ge) {
+    memset(&t, 0, sizeof t);
+    t.mis = mm; t.go = go; t.ge = ge;
+    int st[NS][3], ns = 0;
+    for (int s = 0; s < 27; s++) {
+        const int tr[3] = {s % 3, (s / 3) % 3, (s / 9) % 3};  // 0 match, 1 del, 2 ins
+        int nm = 0, nd = 0, ni = 0;
+        for (int i = 0; i < 3; i++) { nm += tr[i] == 0; nd += tr[i] == 1; ni += tr[i] == 2; }
+        if (nm == 0 || ni > 1) continue;
+        for (int i = 0; i < 3; i++) st[ns][i] = tr[i];
+        const int sel = ni == 0 ? 0 : 2;  // no insert: the matching sequences move; else only the inserted one
+        t.da[ns] = tr[0] == sel; t.db[ns] = tr[1] == sel; t.dc[ns] = tr[2] == sel;
+        if (ni > 0) { t.cont[ns] = ge; t.second[ns] = 0; }
+        else if (nm == 3) { t.cont[ns] = mm; t.second[ns] = 1; }
+        else if (nd == 1) { t.cont[ns] = ge; t.second[ns] = 1; }
+        else { t.cont[ns] = 2 * ge; t.second[ns] = 0; }
+        ns++;
+    }
+    int maxc = 0;
+    for (int s1 = 0; s1 < NS; s1++)
+        for (int s2 = 0; s2 < NS; s2++) {
+            int c = 0, nm = 0;
+            for (int i = 0; i < 3; i++) {
+                if (st[s2][i] != 0 && st[s2][i] != st[s1][i]) c += go;
+                nm += st[s2][i] == 0;
+            }
+            t.trans[s1][s2] = c;
+            const int step = c + t.cont[s2] + mm * (nm - 1);
+            if (step > maxc) maxc = step;
+        }
+    t.maxSingleStep = maxc;
+}
+
+struct Entry {  // one U cell (U_cell_type :44) + the distance of its check-point cell (CP(...)->dist, :342)
+    int32_t tag;                 // d + costOffset ("computed")
+    int16_t dist, fdist;
+    int16_t fab, fac, fcost, fstate;
+};
+
+struct Task {  // one doUkkInLimits call
+    int sab, sac, sCost, sState, sDist, fab, fac, fCost, fState, fDist;
+};
+
+// Per-triple workspace (global memory on the device).  Box: diagonals |ab - cab| <= R, |ac - cac| <= R.
+struct Work {
+    const uint8_t *A, *B, *C;    // 0-based characters (any code; equal codes match)
+    int Alen, Blen, Clen;
+    int R, D, cab, cac, Wd;      // D = 2 R + 1; Wd a power of two
+    Entry *U;                    // D * D * NS * Wd
+    int *top, *prev;             // D * D * NS: newest computed cost of the cell (NEGBIG: none), and the same one level earlier
+    int *keycnt;                 // 2 * (maxlevels + 1) + 1
+    int *list;                   // 2 ints per new cell: x, cost
+    int listcap, maxlevels;
+    uint8_t *resA, *resB, *resC; // alignment in reverse order ('-' = 0xff), capacity rescap
+    int rescap;
+    Task *stack;                 // capacity stackcap
+    int stackcap;
+    // --- scalars shared by the group (written by thread 0 between barriers, or by atomics)
+    int status, nres, nstack;
+    int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist;
+    long long costOffset;
+    long long ncalc;             // cells computed (statistics)
+};
+
+#ifndef PW_TRACE
+#define PW_TRACE(...) ((void) 0)
+#endif
+#ifndef PW_TID
+#define PW_TID 0
+#define PW_NT 1
+#define PW_SYNC() ((void) 0)
+#define PW_ATOMIC_MAX(p, v) do { if (*(p) < (v)) *(p) = (v); } while (0)
+#define PW_ATOMIC_MIN(p, v) do { if (*(p) > (v)) *(p) = (v); } while (0)
+#define PW_ATOMIC_ADD(p, v) pw_host_fetch_add((p), (v))
+inline int pw_host_fetch_add(int *p, int v) { const int o = *p; *p += v; return o; }
+#endif
+
+struct Engine {
+    Work *w;
+    const Tables *tb;
+    // pass parameters (the globals of ukk.checkp.c :86-107)
+    int sab, sac, sCost, sState;      // sabG, sacG, sCostG, sStateG
+    int endA, endB, endC;
+    int CPcost, CPwidth, completeFromInfo;
+    int startx;                       // box index of the pass's start cell
+
+    PW_HD bool in_box(int ab, int ac) const {
+        return ab >= w->cab - w->R && ab <= w->cab + w->R && ac >= w->cac - w->R && ac <= w->cac + w->R;
+    }
+    PW_HD int xi(int ab, int ac, int s) const { return ((ab - w->cab + w->R) * w->D + (ac - w->cac + w->R)) * NS + s; }
+    PW_HD Entry &cell(int x, int d) const { return w->U[(size_t) x * w->Wd + (d & (w->Wd - 1))]; }
+    PW_HD static int iabs(int v) { return v < 0 ? -v : v; }
+
+    // smallest cost at which withinMatrix(ab, ac, .) holds (:545-576)
+    PW_HD int lower(int ab, int ac) const {
+        int a0 = iabs(sab - ab), a1 = iabs(sac - ac), a2 = iabs((sac - sab) - (ac - ab));
+        // g, h = the two smallest
+        int g = a0 < a1 ? a0 : a1, mx = a0 < a1 ? a1 : a0;
+        int h = mx < a2 ? mx : a2;
+        if (a2 < g) { h = g; g = a2; }
+        int cheapest;
+        if (sState == 0) cheapest = (g == 0 ? 0 : tb->go + g * tb->ge) + (h == 0 ? 0 : tb->go + h * tb->ge);
+        else cheapest = (g == 0 ? 0 : g * tb->ge) + (h == 0 ? 0 : h * tb->ge);
+        const int lo = cheapest + sCost;
+        return lo < 0 ? 0 : lo;
+    }
+    PW_HD bool within(int ab, int ac, int d) const { return d >= 0 && d >= lower(ab, ac); }
+    PW_HD bool diag_ok(int ab, int ac) const { return ab >= -endB && ab <= endA && ac >= -endC && ac <= endA; }  // :644
+    PW_HD static bool ok_index(int a, int da, int end) {  // okIndex, ukkCommon.c:187-193
+        if (a < 0) return false;
+        return da ? a < end : a <= end;
+    }
+
+    // Ukk(ab, ac, d, s) as a READ: the relaxation has made sure the cell exists whenever the reference would compute it.
+    PW_HD int U(int ab, int ac, int d, int s) const {
+        if (!within(ab, ac, d)) return -PW_INF;
+        if (!in_box(ab, ac)) { w->status = PW_EBOX; return -PW_INF; }
+        const Entry &e = cell(xi(ab, ac, s), d);
+        if (e.tag != (int32_t) (d + w->costOffset)) { w->status = PW_EWINDOW; return -PW_INF; }
+        return e.dist;
+    }
+    PW_HD void inherit(Entry &dst, int ab, int ac, int d, int s) const {  // from = U(ab, ac, d, s)->from
+        const Entry &e = cell(xi(ab, ac, s), d);
+        dst.fab = e.fab; dst.fac = e.fac; dst.fcost = e.fcost; dst.fstate = e.fstate; dst.fdist = e.fdist;
+    }
+
+    // calcUkk (:608-784) for cell x = (ab, ac, toState) at cost d.
+    PW_HD void calc(int ab, int ac, int d, int toState) const {
+        const uint8_t *A = w->A, *B = w->B, *C = w->C;
+        Entry out;
+        out.fab = 0; out.fac = 0; out.fcost = -1; out.fstate = 0; out.fdist = 0;
+        int bestDist = -PW_INF;
+        const bool cpwin = d >= CPcost && d < CPcost + CPwidth;
+        const bool cpinherit = !completeFromInfo && d >= CPcost + CPwidth;
+        if (cpwin) { out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) d; out.fstate = (int16_t) toState; }
+        const int da = tb->da[toState], db = tb->db[toState], dc = tb->dc[toState];
+        const int ab1 = ab - da + db, ac1 = ac - da + dc;
+        if (diag_ok(ab1, ac1)) {
+            for (int fromState = 0; fromState < NS; fromState++) {
+                const int cost = d - tb->trans[fromState][toState] - tb->cont[toState];
+                int fromCost = -PW_INF, dist = -PW_INF;
+                const int a1 = U(ab1, ac1, cost, fromState);
+                bool first = false;
+                if (ok_index(a1, da, endA) && ok_index(a1 - ab1, db, endB) && ok_index(a1 - ac1, dc, endC)) {
+                    // whichCharCost(...) == 1 (ukkCommon.c:155-184): not all three equal, but two of them are
+                    const int ca = da ? A[a1] : 256, cb = db ? B[a1 - ab1] : 256, cc = dc ? C[a1 - ac1] : 256;
+                    first = !(ca == cb && ca == cc) && (ca == cb || ca == cc || cb == cc);
+                }
+                if (first) {
+                    fromCost = cost;
+                    dist = a1 + da;
+                } else {
+                    if (!tb->second[toState]) continue;
+                    const int a2 = U(ab1, ac1, cost - tb->mis, fromState);
+                    if (ok_index(a2, da, endA) && ok_index(a2 - ab1, db, endB) && ok_index(a2 - ac1, dc, endC)) {
+                        fromCost = cost - tb->mis;
+                        dist = a2 + da;
+                    }
+                }
+                if (bestDist < dist) {
+                    bestDist = dist;
+                    if (completeFromInfo) {
+                        out.fab = (int16_t) ab1; out.fac = (int16_t) ac1; out.fcost = (int16_t) fromCost; out.fstate = (int16_t) fromState;
+                    } else if (cpinherit) {
+                        inherit(out, ab1, ac1, fromCost, fromState);
+                    }
+                }
+            }
+        }
+        {   // what can be reached for AT MOST cost d (:693-711)
+            const int dist = U(ab, ac, d - 1, toState);
+            if (ok_index(dist, 0, endA) && ok_index(dist - ab, 0, endB) && ok_index(dist - ac, 0, endC) && bestDist < dist) {
+                bestDist = dist;
+                if (completeFromInfo) {
+                    out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) (d - 1); out.fstate = (int16_t) toState;
+                } else if (cpinherit) {
+                    inherit(out, ab, ac, d - 1, toState);
+                }
+            }
+        }
+        if (toState == 0) {  // extend along a run of matches from the furthest state of this cell (:713-764)
+            int dist = -PW_INF, from_state = -1;
+            for (int s = 0; s < NS; s++) {
+                const int thisdist = (s == 0) ? bestDist : U(ab, ac, d, s);
+                if (thisdist > dist) { dist = thisdist; from_state = s; }
+            }
+            while (ok_index(dist, 1, endA) && ok_index(dist - ab, 1, endB) && ok_index(dist - ac, 1, endC) && A[dist] == B[dist - ab] &&
+                   A[dist] == C[dist - ac])
+                dist++;
+            if (dist > bestDist) {
+                bestDist = dist;
+                if (from_state != 0) {
+                    if (completeFromInfo) {
+                        out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) d; out.fstate = (int16_t) from_state;
+                    } else if (cpinherit) {
+                        inherit(out, ab, ac, d, from_state);
+                    }
+                }
+            }
+        }
+        out.dist = (int16_t) bestDist;
+        if (cpwin && out.fab == ab && out.fac == ac && out.fcost == d && out.fstate == toState) out.fdist = (int16_t) bestDist;  // CP(...)->dist (:592-595)
+        out.tag = (int32_t) (d + w->costOffset);
+        cell(xi(ab, ac, toState), d) = out;
+        if (bestDist > w->fr) PW_ATOMIC_MAX(&w->fr, bestDist);  // furthestReached (:597)
+    }
+
+    PW_HD void decode(int x, int &ab, int &ac, int &st) const {
+        st = x % NS;
+        const int q = x / NS;
+        ab = q / w->D - w->R + w->cab;
+        ac = q % w->D - w->R + w->cac;
+    }
+    // top of x as a source of demands: the preset start cell is a memo hit, never expanded (:242-243, :582)
+    PW_HD int src_top(int x) const {
+        const int t = w->top[x];
+        return (x == startx && t <= sCost) ? NEGBIG : t;
+    }
+
+    // Top level T - 1 -> T, step 1: every cell that was demanded keeps being demanded one cost higher (the same path).
+    PW_HD void bump() const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int x = xi(lo_ab + q / nac, lo_ac + q % nac, st);
+            const int t = w->top[x];
+            w->prev[x] = t;
+            if (t != NEGBIG && !(x == startx && t <= sCost)) w->top[x] = t + 1;
+        }
+    }
+    // Step 2, repeated until nothing changes: one pull sweep of the demand closure over the bounding box of the active cells
+    // (+ 1 diagonal); r0 / r1 = the cells the top level asks for directly (box indices, -1 = none).  In place: the closure is
+    // a monotone fixpoint, the order of the updates does not matter.
+    PW_HD void sweep(int T, int r0, int r1) const {
+        const int lo_ab = w->lo_ab - 1, hi_ab = w->hi_ab + 1, lo_ac = w->lo_ac - 1, hi_ac = w->hi_ac + 1;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int ab = lo_ab + q / nac, ac = lo_ac + q % nac;
+            if (!in_box(ab, ac)) continue;
+            const int y = xi(ab, ac, st);
+            const int cur = w->top[y];
+            int cand = NEGBIG;
+            if (y == r0 || y == r1) cand = T;
+            if (diag_ok(ab, ac)) {
+                for (int ts = 0; ts < NS; ts++) {  // the cells whose neighbour diagonal this is
+                    const int xab = ab + tb->da[ts] - tb->db[ts], xac = ac + tb->da[ts] - tb->dc[ts];
+                    if (!in_box(xab, xac)) continue;
+                    const int tx = src_top(xi(xab, xac, ts));
+                    if (tx == NEGBIG) continue;
+                    const int c = tx - (tb->trans[st][ts] + tb->cont[ts]);
+                    if (c > cand) cand = c;
+                }
+            }
+            if (st != 0) {  // MMM asks for the other states of its own cell (:732-739)
+                const int tx = src_top(xi(ab, ac, 0));
+                if (tx > cand) cand = tx;
+            }
+            if (cand == NEGBIG || cand <= cur) continue;
+            if (cur == NEGBIG && cand < lower(ab, ac)) continue;  // outside the matrix: the demand returns -INFINITY (:581)
+            w->top[y] = cand;
+            w->changed = 1;
+            if (ab - w->cab == -w->R || ab - w->cab == w->R || ac - w->cac == -w->R || ac - w->cac == w->R) w->status = PW_EBOX;
+            PW_ATOMIC_MIN(&w->lo_ab, ab); PW_ATOMIC_MAX(&w->hi_ab, ab);
+            PW_ATOMIC_MIN(&w->lo_ac, ac); PW_ATOMIC_MAX(&w->hi_ac, ac);
+        }
+    }
+    // The cells that became demanded at this top level, as (x, cost) sorted by (cost, MMM last).  count = false: scatter.
+    PW_HD void collect(bool scatter) const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int ab = lo_ab + q / nac, ac = lo_ac + q % nac;
+            const int x = xi(ab, ac, st);
+            const int hi = w->top[x];
+            if (hi == NEGBIG) continue;
+            const int pv = w->prev[x];
+            int lo = (pv == NEGBIG) ? lower(ab, ac) : pv + 1;
+            for (int c = lo; c <= hi; c++) {
+                const int key = 2 * (c - sCost) + (st == 0 ? 1 : 0);
+                const int pos = PW_ATOMIC_ADD(&w->keycnt[key], 1);
+                if (scatter && pos < w->listcap) { w->list[2 * pos] = x; w->list[2 * pos + 1] = c; }
+            }
+        }
+    }
+
+    // All cells the reference computes for the top-level calls Ukk(root, T, .): relax, list, compute in cost order.
+    PW_HD void top_level(int T, int r0, int r1) const {
+        if (T - sCost >= w->maxlevels) { if (PW_TID == 0) w->status = PW_ECAP; PW_SYNC(); return; }
+        bump();
+        PW_SYNC();
+        for (;;) {
+            if (PW_TID == 0) w->changed = 0;
+            PW_SYNC();
+            sweep(T, r0, r1);
+            PW_SYNC();
+            if (!w->changed || w->status) break;
+            PW_SYNC();
+        }
+        if (w->status) return;
+        const int nkeys = 2 * (T - sCost + 1);
+        for (int k = PW_TID; k < nkeys; k += PW_NT) w->keycnt[k] = 0;
+        PW_SYNC();
+        collect(false);
+        PW_SYNC();
+        if (PW_TID == 0) {
+            int run = 0;
+            for (int k = 0; k < nkeys; k++) { const int c = w->keycnt[k]; w->keycnt[k] = run; run += c; }
+            w->nlist = run;
+            if (run > w->listcap) w->status = PW_ELIST;
+        }
+        PW_SYNC();
+        if (w->status) return;
+        collect(true);
+        PW_SYNC();
+        // keycnt[k] is now the END of key k
+        for (int k = 0; k < nkeys; k++) {
+            const int begin = k == 0 ? 0 : w->keycnt[k - 1], end = w->keycnt[k];
+            if (end == begin) continue;
+            for (int i = begin + PW_TID; i < end; i += PW_NT) {
+                int ab, ac, st;
+                decode(w->list[2 * i], ab, ac, st);
+                calc(ab, ac, w->list[2 * i + 1], st);
+            }
+            PW_SYNC();
+        }
+    }
+
+    // Start of a pass: the preset start cell and an empty demand state.  Thread 0, between barriers.
+    PW_HD void begin_pass(const Task &t) {
+        sab = t.sab; sac = t.sac; sCost = t.sCost; sState = t.sState;
+        startx = xi(sab, sac, sState);
+        if (PW_TID == 0) {
+            const int R1 = w->R - 1;  // strictly inside: a cell on the border cannot see its outer neighbours
+            if (iabs(sab - w->cab) > R1 || iabs(sac - w->cac) > R1 || iabs(t.fab - w->cab) > R1 || iabs(t.fac - w->cac) > R1) w->status = PW_EBOX;
+            else {
+                Entry &e = cell(startx, sCost);
+                e.dist = (int16_t) t.sDist;
+                e.tag = (int32_t) (sCost + w->costOffset);
+                w->top[startx] = sCost;
+                w->prev[startx] = sCost;
+                // sweep region: hull of the start and the final diagonal (the roots must be inside it to be asked at all)
+                w->lo_ab = sab < t.fab ? sab : t.fab; w->hi_ab = sab < t.fab ? t.fab : sab;
+                w->lo_ac = sac < t.fac ? sac : t.fac; w->hi_ac = sac < t.fac ? t.fac : sac;
+            }
+        }
+        PW_SYNC();
+    }
+    // End of a pass: forget the demand state of the region it touched.
+    PW_HD void end_pass() const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        PW_SYNC();
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int x = xi(lo_ab + q / nac, lo_ac + q % nac, st);
+            w->top[x] = NEGBIG;
+            w->prev[x] = NEGBIG;
+        }
+        PW_SYNC();
+    }
+    PW_HD bool computed(int ab, int ac, int d, int st) const {
+        return in_box(ab, ac) && cell(xi(ab, ac, st), d).tag == (int32_t) (d + w->costOffset);
+    }
+    // best() :508-527
+    PW_HD int best(int ab, int ac, int d, bool wantState) const {
+        int bst = -PW_INF, bs = -1;
+        for (int st = 0; st < NS; st++)
+            if (computed(ab, ac, d, st) && cell(xi(ab, ac, st), d).dist > bst) { bst = cell(xi(ab, ac, st), d).dist; bs = st; }
+        return wantState ? bs : bst;
+    }
+    PW_HD void push_res(int a, int b, int c) const {
+        if (w->nres >= w->rescap) { w->status = PW_ECAP; return; }
+        w->resA[w->nres] = (uint8_t) a; w->resB[w->nres] = (uint8_t) b; w->resC[w->nres] = (uint8_t) c;
+        w->nres++;
+    }
+    // traceBack :370-444 (thread 0)
+    PW_HD void trace_back(const Task &t) const {
+        int ab = t.fab, ac = t.fac, d = t.fCost, st = t.fState;
+        int guard = 0;
+        while (ab != t.sab || ac != t.sac || d != t.sCost || st != t.sState) {
+            if (!computed(ab, ac, d, st) || ++guard > 4 * w->rescap + 64) { w->status = PW_EWINDOW; return; }
+            const Entry e = cell(xi(ab, ac, st), d);
+            int a = e.dist;
+            const int nab = e.fab, nac = e.fac, nd = e.fcost, ns = e.fstate;
+            if (nd < 0 || ns < 0 || !computed(nab, nac, nd, ns)) { w->status = PW_EWINDOW; return; }
+            int b = a - ab, c = a - ac;
+            const int a1 = cell(xi(nab, nac, ns), nd).dist;
+            const int b1 = a1 - nab, c1 = a1 - nac;
+            while (a > a1 && b > b1 && c > c1) {  // run of matches
+                a--; b--; c--;
+                push_res(w->A[a], w->B[b], w->C[c]);
+            }
+            if (a != a1 || b != b1 || c != c1) {  // the step (nab, nac, nd, ns) -> (ab, ac, d, st)
+                const int ra = a > a1 ? w->A[--a] : 0xff, rb = b > b1 ? w->B[--b] : 0xff, rc = c > c1 ? w->C[--c] : 0xff;
+                push_res(ra, rb, rc);
+            }
+            if (w->status) return;
+            ab = nab; ac = nac; d = nd; st = ns;
+        }
+    }
+    PW_HD void push_task(const Task &t) const {
+        if (w->nstack >= w->stackcap) { w->status = PW_ESTACK; return; }
+        w->stack[w->nstack++] = t;
+    }
+    // getSplitRecurse :324-367: second half first (popped first), then the first half
+    PW_HD void split(const Task &t) const {
+        const Entry e = cell(xi(t.fab, t.fac, t.fState), t.fCost);
+        if (e.fcost < 0) { w->status = PW_EWINDOW; return; }
+        Task first = t, second = t;
+        first.fab = e.fab; first.fac = e.fac; first.fCost = e.fcost; first.fState = e.fstate; first.fDist = e.fdist;
+        second.sab = e.fab; second.sac = e.fac; second.sCost = e.fcost; second.sState = e.fstate; second.sDist = e.fdist;
+        push_task(first);
+        push_task(second);
+    }
+
+    // doUkkInLimits :216-322
+    PW_HD void in_limits(Task t, int finalCost) {
+        endA = t.fDist; endB = t.fDist - t.fab; endC = t.fDist - t.fac;
+        completeFromInfo = 0;
+        if (PW_TID == 0) w->costOffset += finalCost + 1;
+        PW_SYNC();
+        begin_pass(t);
+        PW_TRACE("in_limits s=(%d,%d,c%d,s%d,d%d) f=(%d,%d,c%d,s%d,d%d) status %d\n", t.sab, t.sac, t.sCost, t.sState, t.sDist, t.fab, t.fac,
+                 t.fCost, t.fState, t.fDist, w->status);
+        if (w->status) return;
+        const bool base = t.fCost - t.sCost <= CPwidth;
+        if (base) completeFromInfo = 1;
+        else CPcost = (t.fCost + t.sCost - CPwidth + 1) / 2;
+        const int rf = xi(t.fab, t.fac, t.fState), r0 = base ? -1 : xi(t.fab, t.fac, 0);
+        int T = t.sCost - 1, dist;
+        do {
+            T++;
+            top_level(T, r0, rf);
+            if (w->status) return;
+            dist = U(t.fab, t.fac, T, t.fState);
+            PW_TRACE("  T=%d dist=%d nlist=%d status=%d\n", T, dist, w->nlist, w->status);
+        } while (dist < t.fDist && !w->status);
+        if (w->status) return;
+        t.fCost = T;  // `if (i != fCost) ... fCost = i` (:267-271, :312-316)
+        if (PW_TID == 0) {
+            if (base) trace_back(t);
+            else split(t);
+        }
+        end_pass();
+    }
+
+    // doUkk :113-214.  Returns the cost; the alignment is left reversed in resA / resB / resC ('-' = 0xff).
+    PW_HD int run() {
+        const int Alen = w->Alen, Blen = w->Blen, Clen = w->Clen;
+        CPwidth = tb->maxSingleStep;
+        CPcost = 0;
+        completeFromInfo = 0;
+        int startDist = 0;
+        while (startDist < Alen && startDist < Blen && startDist < Clen && w->A[startDist] == w->B[startDist] &&
+               w->A[startDist] == w->C[startDist])
+            startDist++;
+        // (the reference compares against the terminating 0 of the shorter strings: same stop)
+        const int finalab = Alen - Blen, finalac = Alen - Clen;
+        endA = Alen; endB = Blen; endC = Clen;
+        if (PW_TID == 0) { w->costOffset = 1; w->fr = -1; w->nres = 0; w->nstack = 0; }
+        PW_SYNC();
+        Task t0{0, 0, 0, 0, startDist, finalab, finalac, 0, 0, Alen};
+        begin_pass(t0);
+        if (w->status) return -1;
+        if (PW_TID == 0) {  // fresh `from` of the very first cell: calloc'ed zeros (:152-153)
+            Entry &e = cell(startx, 0);
+            e.fab = e.fac = e.fcost = e.fstate = e.fdist = 0;
+        }
+        PW_SYNC();
+        bool CPonDist = true;
+        CPcost = PW_INF;
+        const int rf = xi(finalab, finalac, 0);
+        int d = -1;
+        do {
+            d++;
+            top_level(d, rf, -1);
+            if (w->status) return -1;
+            if (CPonDist && w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
+            PW_TRACE("pass1 d=%d fr=%d best=%d nlist=%d CPcost=%d\n", d, w->fr, best(finalab, finalac, d, false), w->nlist, CPcost);
+        } while (best(finalab, finalac, d, false) < Alen);
+        const int finalCost = d;
+        const int fState = best(finalab, finalac, finalCost, true);
+        Task whole{0, 0, 0, 0, startDist, finalab, finalac, finalCost, fState, Alen};
+        const bool redo = cell(xi(finalab, finalac, fState), finalCost).fcost <= 0;  // check-pointed too late (:195-200)
+        PW_SYNC();
+        if (PW_TID == 0) {
+            if (redo) push_task(whole);
+            else split(whole);
+        }
+        end_pass();
+        while (!w->status && w->nstack > 0) {
+            const Task t = w->stack[w->nstack - 1];
+            PW_SYNC();
+            if (PW_TID == 0) w->nstack--;
+            PW_SYNC();
+            in_limits(t, finalCost);
+        }
+        if (w->status) return -1;
+        if (PW_TID == 0)  // printTraceBack :456-475: the first run of matches, in reverse order like the rest
+            for (int i = startDist - 1; i >= 0; i--) push_res(w->A[i], w->B[i], w->C[i]);
+        PW_SYNC();
+        return w->status ? -1 : finalCost;
+    }
+};
+
+}  // namespace powell
+}  // namespace poyb200
