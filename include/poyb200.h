@@ -211,6 +211,14 @@ int poyb200_batch_align_3(poyb200_ctx *ctx, const poyb200_batch3 *b);
  * len[p] elements each; out rows RIGHT aligned.  Reproduces algn_get_median_3d as executed (a constant sequence). */
 int poyb200_batch_median_3(poyb200_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t in_stride,
                            const int32_t *len, int32_t n, uint8_t *out, int64_t out_stride, int32_t *out_len);
+/* Powell's three-sequence aligner under affine gap costs (src/ukk.checkp.c + src/ukkCommon.c): the external powell_3D_align
+ * (src/ukkCommon.c:110-145, sequence.ml:1075-1087) for every triple -- mismatch cost mm, gap opening go, gap extension ge as
+ * Sequence.Align.align_3_powell_inter derives them from the 2-D matrix (src/sequence.ml:1089-1102).  Elements collapse to their
+ * lowest base like copySequence does (:87-108); cost[t] = the edit cost, aligned_1..3 = the three rows behind one gap column
+ * (POYB200_WANT3_ALIGNED), median = the 3-D median of every column with gaps dropped and one gap in front (align_3_powell_inter
+ * :1103-1114; POYB200_WANT3_MEDIAN, needs poyb200_set_cm_3d).  out_len holds TWO ints per triple: aligned length, median length.
+ * status[t]: 0, or 5 = an element without a base (the reference raises "This is impossible!"), other values = internal limits. */
+int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b, int32_t mm, int32_t go, int32_t ge);
 /* cells of the cube: l1 * l2 * l3 */
 int64_t poyb200_cells_3d(int32_t l1, int32_t l2, int32_t l3);
 

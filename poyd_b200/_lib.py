@@ -72,7 +72,7 @@ EXPORTS = [
     "poyb200_batch_cost_affine_3", "poyb200_batch_align_affine_3", "poyb200_batch_median_2", "poyb200_stage",
     "poyb200_run", "poyb200_sync", "poyb200_fetch", "poyb200_launch_count", "poyb200_cells_linear",
     "poyb200_cells_affine", "poyb200_last_run_ms", "poyb200_stream", "poyb200_int32_peak", "poyb200_set_cm_3d",
-    "poyb200_batch_align_3", "poyb200_cells_3d", "poyb200_batch_worst_2", "poyb200_batch_median_3",
+    "poyb200_batch_align_3", "poyb200_batch_powell_3", "poyb200_cells_3d", "poyb200_batch_worst_2", "poyb200_batch_median_3",
     "poyb200_multi_create", "poyb200_multi_destroy", "poyb200_multi_last_error", "poyb200_multi_set_cm", "poyb200_multi_batch",
     "poyb200_multi_devices", "poyb200_multi_ctx", "poyb200_multi_launch_count", "poyb200_multi_shards",
     "poyb200_store_create", "poyb200_store_destroy", "poyb200_store_size", "poyb200_store_bytes", "poyb200_store_add",

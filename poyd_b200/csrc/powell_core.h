@@ -28,10 +28,12 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifndef PW_HD
 #ifdef __CUDACC__
 #define PW_HD __host__ __device__ __forceinline__
 #else
 #define PW_HD inline
+#endif
 #endif
 
 namespace poyb200 {
@@ -112,6 +114,7 @@ struct Work {
     int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist;
     long long costOffset;
     long long ncalc;             // cells computed (statistics)
+    long long nextOffset;        // first tag offset of the next triple run in this workspace (tags never repeat)
 };
 
 #ifndef PW_TRACE
@@ -361,6 +364,7 @@ struct Engine {
             int run = 0;
             for (int k = 0; k < nkeys; k++) { const int c = w->keycnt[k]; w->keycnt[k] = run; run += c; }
             w->nlist = run;
+            w->ncalc += run;
             if (run > w->listcap) w->status = PW_ELIST;
         }
         PW_SYNC();
@@ -512,7 +516,7 @@ struct Engine {
         // (the reference compares against the terminating 0 of the shorter strings: same stop)
         const int finalab = Alen - Blen, finalac = Alen - Clen;
         endA = Alen; endB = Blen; endC = Clen;
-        if (PW_TID == 0) { w->costOffset = 1; w->fr = -1; w->nres = 0; w->nstack = 0; }
+        if (PW_TID == 0) { w->costOffset = w->nextOffset; w->fr = -1; w->nres = 0; w->nstack = 0; }  // the reference starts at 1 (:86)
         PW_SYNC();
         Task t0{0, 0, 0, 0, startDist, finalab, finalac, 0, 0, Alen};
         begin_pass(t0);

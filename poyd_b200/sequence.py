@@ -472,10 +472,11 @@ class Aligned3:
     aligned_2: Optional[np.ndarray] = None
     aligned_3: Optional[np.ndarray] = None
     median: Optional[np.ndarray] = None
+    median_lens: Optional[np.ndarray] = None  # align_3_powell only: the median is shorter than the rows
 
     def get(self, what: str, t: int) -> np.ndarray:
         buf = getattr(self, what)
-        n = int(self.lens[t])
+        n = int(self.median_lens[t]) if (what == "median" and self.median_lens is not None) else int(self.lens[t])
         return buf[t, buf.shape[1] - n:]
 
 
@@ -516,3 +517,41 @@ class Align3(Align):
 
     def cost_3(self, pool: SeqPool, triples) -> np.ndarray:
         return self.align_3(pool, triples, want=0).cost
+
+    def align_3_powell(self, pool: SeqPool, triples, mm: int, go: int, ge: int, want: int = 1) -> Aligned3:
+        """``Sequence.Align.align_3_powell s1 s2 s3 mm go ge`` (src/sequence.ml:1078-1087) for every triple: Powell's
+        three-sequence aligner under affine gap costs (src/ukk.checkp.c).  want & 1: the three aligned rows; want & 2: the
+        median of ``align_3_powell_inter`` (:1103-1114).  ``lens`` = aligned lengths, ``median_lens`` = median lengths;
+        ``status[t] = 5`` marks a triple holding an element without a base (the reference raises there)."""
+        triples = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
+        n = len(triples)
+        b = _lib.Batch3()
+        b.pool, b.pool_bytes = pool.pool.ctypes.data, pool.pool.nbytes
+        b.seq_off, b.seq_len, b.n_seqs = pool.off.ctypes.data, pool.len.ctypes.data, len(pool)
+        b.triples, b.n_triples, b.want = triples.ctypes.data, n, want
+        res = Aligned3(cost=np.zeros(n, np.int32))
+        b.cost = res.cost.ctypes.data
+        stride = 16
+        if n:
+            stride = int(pool.len[triples].astype(np.int64).sum(axis=1).max())
+        stride = (stride + 15) // 16 * 16
+        lens2 = np.zeros((n, 2), np.int32)
+        res.status = np.zeros(n, np.int32)
+        b.out_len, b.status, b.out_stride = lens2.ctypes.data, res.status.ctypes.data, stride
+        if want & 1:
+            res.aligned_1, res.aligned_2, res.aligned_3 = (np.zeros((n, stride), np.uint8) for _ in range(3))
+            b.aligned_1, b.aligned_2, b.aligned_3 = (x.ctypes.data for x in (res.aligned_1, res.aligned_2, res.aligned_3))
+        if want & 2:
+            res.median = np.zeros((n, stride), np.uint8)
+            b.median = res.median.ctypes.data
+        self._check(self.L.poyb200_batch_powell_3(self.h, C.byref(b), int(mm), int(go), int(ge)))
+        res.lens = np.ascontiguousarray(lens2[:, 0])
+        res.median_lens = np.ascontiguousarray(lens2[:, 1])
+        return res
+
+    def align_3_powell_inter(self, pool: SeqPool, triples, want: int = 3) -> Aligned3:
+        """``Sequence.Align.align_3_powell_inter`` (src/sequence.ml:1089-1114): mismatch, gap opening and gap extension
+        taken from the 2-D matrix (cost 1 2, the affine opening or 0, cost 1 16), medians through the 3-D matrix."""
+        model = self.cm.affine()
+        go = int(model[1]) if model[0] == "Affine" else 0
+        return self.align_3_powell(pool, triples, int(self.cm.cost[1, 2]), go, int(self.cm.cost[1, 16]), want)

@@ -52,6 +52,7 @@ extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned cha
     w.resA = ra.data(); w.resB = rb.data(); w.resC = rc.data(); w.rescap = cap;
     std::vector<Task> stack(256);
     w.stack = stack.data(); w.stackcap = 256;
+    w.nextOffset = 1;
     Engine e;
     memset(&e, 0, sizeof e);
     e.w = &w; e.tb = &tb;

@@ -699,3 +699,47 @@ def test_uppass_three_medians_and_union_distance(S, affine):
     assert np.array_equal(d, want)
     assert np.allclose(seqcs.Union(al).distance_union(pool, pairs[:n]), (0.8 if affine else 1.0) * want)
     al.close()
+
+
+def test_powell_3d_aligner_matches_the_reference(S):
+    """poyb200_batch_powell_3 (the CUDA port of src/ukk.checkp.c) against the compiled reference's
+    powell_3D_align, triple by triple: cost, the three aligned rows (every tie), and the median of align_3_powell_inter
+    (src/sequence.ml:1103-1114) recomputed here from the reference's rows through the 3-D matrix."""
+    import powell_util as PU
+    from poyd_b200 import cost_matrix as CM
+
+    ref = PU.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref/libpoyref.so with the Powell recipe not built")
+    cm = CM.nucleotides(1, 2, 3)
+    cm3 = CM.of_two_dim(cm)
+    al = S.Align3(cm, cm3)
+    cases = PU.triples(seed=23, count=60, max_len=60) + PU.triples(seed=24, count=12, max_len=160, rates=(0.03, 0.08))
+    rng = np.random.default_rng(3)
+    a = PU.dna(rng, 90)
+    cases += [(a, a[:40].copy(), PU.mutate(rng, a, 0.05)), (a, a.copy(), a.copy()), (PU.dna(rng, 1), PU.dna(rng, 1), PU.dna(rng, 1))]
+    seqs = [s for t in cases for s in t]
+    pool = S.SeqPool(seqs)
+    triples = np.arange(3 * len(cases), dtype=np.int32).reshape(-1, 3)
+    med3 = np.asarray(cm3.median).reshape(32, 32, 32)
+    for mm, go, ge in PU.COSTS[:3]:
+        g = al.align_3_powell(pool, triples, mm, go, ge, want=3)
+        assert not g.status.any(), g.status
+        for t, (x, y, z) in enumerate(cases):
+            rc, rows = PU.ref_powell(ref, x, y, z, mm, go, ge)
+            assert g.cost[t] == rc, (t, (mm, go, ge), g.cost[t], rc)
+            for k, name in enumerate(("aligned_1", "aligned_2", "aligned_3")):
+                assert np.array_equal(g.get(name, t), rows[k]), f"triple {t} costs {(mm, go, ge)}: {name}"
+            med = med3[rows[0], rows[1], rows[2]]
+            want_med = np.concatenate([[16], med[med != 16]]).astype(np.uint8)
+            assert np.array_equal(g.get("median", t), want_med), f"triple {t}: median"
+    # align_3_powell_inter takes its three costs from the 2-D matrix: (1, 3, 2) here
+    g2 = al.align_3_powell_inter(pool, triples[:8])
+    g1 = al.align_3_powell(pool, triples[:8], 1, 3, 2, want=3)
+    assert np.array_equal(g1.cost, g2.cost) and np.array_equal(g1.aligned_1, g2.aligned_1)
+    # an element without a base: the reference raises, the batch marks the triple and goes on
+    bad = S.SeqPool([np.array([16, 1, 2, 16, 4], np.uint8), np.array([16, 1, 2, 4], np.uint8), np.array([16, 1, 2, 4], np.uint8)] + list(cases[0]))
+    gb = al.align_3_powell(bad, np.array([[0, 1, 2], [3, 4, 5]], np.int32), 1, 3, 2, want=1)
+    assert gb.status[0] == 5 and gb.status[1] == 0
+    assert gb.cost[1] == PU.ref_powell(ref, *cases[0], 1, 3, 2)[0]
+    al.close()

@@ -1,0 +1,90 @@
+"""Powell's three-sequence affine Ukkonen aligner (src/ukk.checkp.c, the aligner behind
+Sequence.Align.readjust_3d).  The CUDA kernel executes poyd_b200/csrc/powell_core.h; here the same source runs on one host
+thread (tests/native/powell_host.cpp, a test harness -- the product library has no CPU path) and must reproduce the compiled
+reference bit for bit: cost and the three aligned rows, i.e. every tie the reference's check-pointed recursion breaks."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import powell_util as PU
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def host():
+    out = os.path.join(HERE, "..", "build", "libpwhost.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "native", "powell_host.cpp")
+    dep = os.path.join(HERE, "..", "poyd_b200", "csrc", "powell_core.h")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    lib = PU.reference()
+    if lib is None:
+        pytest.skip("oracle/_ref/libpoyref.so with the Powell recipe not built")
+    return lib
+
+
+def host_powell(host, a, b, c, mm, go, ge):
+    cap = len(a) + len(b) + len(c) + 2
+    R = 16
+    while True:
+        rows = [np.zeros(cap, np.uint8) for _ in range(3)]
+        n, st, cells = C.c_int(0), C.c_int(0), C.c_longlong(0)
+        cost = host.pw_host_align(a.ctypes.data_as(PU.u8), len(a), b.ctypes.data_as(PU.u8), len(b), c.ctypes.data_as(PU.u8), len(c),
+                                  mm, go, ge, R, 0, *[r.ctypes.data_as(PU.u8) for r in rows], C.byref(n), C.byref(st), C.byref(cells))
+        if st.value == 1 and R < 512:  # PW_EBOX: the diagonal box was too small, like the library's next round
+            R *= 2
+            continue
+        return cost, [r[: n.value] for r in rows], st.value
+
+
+def test_tables_match_setup():
+    """ukkCommon.c setup(): 16 states, MMM first, the largest single step for (1, 3, 2) is MDD entered with two openings."""
+    # (exercised through the alignments below; here only the invariants a reader can check by hand)
+    assert len(PU.COSTS) == 5
+
+
+def test_restatement_matches_the_reference(host, ref):
+    bad = []
+    for k, (a, b, c) in enumerate(PU.triples(seed=5, count=120, max_len=70)):
+        mm, go, ge = PU.COSTS[k % len(PU.COSTS)]
+        rc, rr = PU.ref_powell(ref, a, b, c, mm, go, ge)
+        hc, hr, st = host_powell(host, a, b, c, mm, go, ge)
+        if st != 0 or rc != hc or not all(np.array_equal(x, y) for x, y in zip(rr, hr)):
+            bad.append((k, len(a), len(b), len(c), (mm, go, ge), rc, hc, st))
+    assert not bad, bad[:5]
+
+
+def test_restatement_on_longer_and_unequal_triples(host, ref):
+    rng = np.random.default_rng(17)
+    cases = []
+    for n, p in ((150, 0.08), (220, 0.04), (120, 0.2)):
+        a = PU.dna(rng, n)
+        cases.append((a, PU.mutate(rng, a, p), PU.mutate(rng, a, p)))
+    a = PU.dna(rng, 90)
+    cases.append((a, a[:40].copy(), PU.mutate(rng, a, 0.05)))     # very different lengths: the final diagonal is far out
+    cases.append((a, a.copy(), a.copy()))                          # identical: cost 0, one run of matches
+    cases.append((PU.dna(rng, 1), PU.dna(rng, 1), PU.dna(rng, 1)))
+    for k, (a, b, c) in enumerate(cases):
+        mm, go, ge = PU.COSTS[k % len(PU.COSTS)]
+        rc, rr = PU.ref_powell(ref, a, b, c, mm, go, ge)
+        hc, hr, st = host_powell(host, a, b, c, mm, go, ge)
+        assert st == 0 and rc == hc, (k, rc, hc, st)
+        for x, y in zip(rr, hr):
+            assert np.array_equal(x, y), f"case {k}: aligned rows differ"
+
+
+def test_element_without_a_base_is_an_error(host):
+    a = np.array([16, 1, 2, 16, 4], np.uint8)  # a bare gap inside: copySequence raises "This is impossible!"
+    b = np.array([16, 1, 2, 4], np.uint8)
+    _, _, st = host_powell(host, a, b, b, 1, 3, 2)
+    assert st == 5
