@@ -4,7 +4,7 @@
  *     externals -- algn_CAML_simple_2, algn_CAML_backtrack_2d(_bc), algn_CAML_align_2d(_bc), algn_CAML_cost_affine_3,
  *     algn_CAML_align_affine_3(_bc), algn_CAML_median_2_no_gaps, algn_CAML_median_2_with_gaps, algn_CAML_ancestor_2,
  *     algn_CAML_worst_2, algn_CAML_verify_2, algn_CAML_simple_3(_bc), algn_CAML_backtrack_3d(_bc),
- *     algn_CAML_align_3d(_bc), algn_CAML_median_3 -- with the same argument lists and results, each running on the GPU
+ *     algn_CAML_align_3d(_bc), algn_CAML_median_3, and powell_3D_align(_bc) of src/ukkCommon.c -- with the same argument lists and results, each running on the GPU
  *     as a batch of one.  No OCaml source changes: src/algn_b200.c renames the originals
  *     out of the way and this file takes their place at link time.
  * (2) BATCHED EXTERNALS (poyb200_CAML_batch_*) for the batching layer in seqCS.ml / allDirChar.ml
@@ -455,6 +455,52 @@ value algn_CAML_median_3(value s1, value s2, value s3, value m, value sm) {
     free(buf);
     if (rc != POYB200_OK) fail_with_ctx("poyb200_batch_median_3");
     CAMLreturn(Val_unit);
+}
+
+/* powell_3D_align (src/ukkCommon.c:110-145; the external behind Sequence.Align.align_3_powell, src/sequence.ml:1075-1087):
+ * this symbol replaces ukkCommon.o + ukk.checkp.o at link time.  ra / rb / rc arrive empty with capacity |sa| + |sb| + |sc|. */
+value powell_3D_align(value sa, value sb, value sc, value ra, value rb, value rc, value mm, value go, value ge) {
+    CAMLparam5(sa, sb, sc, mm, go);
+    CAMLxparam4(ge, ra, rb, rc);
+    seqt s[3], r[3];
+    Seq_custom_val(s[0], sa);
+    Seq_custom_val(s[1], sb);
+    Seq_custom_val(s[2], sc);
+    Seq_custom_val(r[0], ra);
+    Seq_custom_val(r[1], rb);
+    Seq_custom_val(r[2], rc);
+    poyb200_ctx *ctx = the_ctx();
+    int64_t off[3];
+    int32_t len[3], tri[3] = {0, 1, 2}, cost = 0, olen[2] = {0, 0}, status = 0;
+    size_t total = 0;
+    for (int k = 0; k < 3; k++) {
+        off[k] = (int64_t) total;
+        len[k] = s[k]->len;
+        total += ((size_t) s[k]->len + 15) & ~(size_t) 15;
+    }
+    const int64_t stride = ((int64_t) len[0] + len[1] + len[2] + 15) & ~15ll;
+    uint8_t *buf = (uint8_t *) xmalloc(total + 32 + 3 * (size_t) stride);
+    uint8_t *pool = buf + 3 * (size_t) stride;
+    for (int k = 0; k < 3; k++) memcpy(pool + off[k], s[k]->begin, (size_t) s[k]->len);
+    poyb200_batch3 bt;
+    memset(&bt, 0, sizeof bt);
+    bt.pool = pool; bt.pool_bytes = total; bt.seq_off = off; bt.seq_len = len; bt.n_seqs = 3;
+    bt.triples = tri; bt.n_triples = 1; bt.cost = &cost;
+    bt.want = POYB200_WANT3_ALIGNED;
+    bt.aligned_1 = buf; bt.aligned_2 = buf + stride; bt.aligned_3 = buf + 2 * stride;
+    bt.out_stride = stride; bt.out_len = olen; bt.status = &status;
+    const int rc3 = poyb200_batch_powell_3(ctx, &bt, Int_val(mm), Int_val(go), Int_val(ge));
+    if (rc3 == POYB200_OK && status == 0)
+        for (int k = 0; k < 3; k++) fill_seq(r[k], buf + (size_t) (k + 1) * stride, olen[0]);
+    free(buf);
+    if (rc3 != POYB200_OK) fail_with_ctx("poyb200_batch_powell_3");
+    if (status == 5) failwith("This is impossible!"); /* copySequence's own message (:104) */
+    if (status != 0) failwith("poyb200_batch_powell_3: internal limit reached");
+    CAMLreturn(Val_int(cost));
+}
+value powell_3D_align_bc(value *argv, int argn) {
+    (void) argn;
+    return powell_3D_align(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6], argv[7], argv[8]);
 }
 
 /* ---- (2) batched externals ---------------------------------------------------------------------------------------------- */
