@@ -23,7 +23,8 @@
 namespace poyb200 {
 namespace powell {
 
-constexpr int PW_THREADS = 256;
+constexpr int PW_THREADS = 128;   // a cost level of one triple rarely holds more cells than this
+constexpr int PW_CTAS_PER_SM = 4;  // the work of a level is a chain of dependent loads: several triples per SM overlap them
 
 struct Job {
     uint32_t off[3];
@@ -40,16 +41,17 @@ struct OutP {
     int lcm3, gap;
 };
 
-__global__ void __launch_bounds__(PW_THREADS) powell_kernel(const Job *__restrict__ jobs, int njobs, const uint8_t *__restrict__ pool,
+__global__ void __launch_bounds__(PW_THREADS, PW_CTAS_PER_SM) powell_kernel(const Job *__restrict__ jobs, int njobs, const uint8_t *__restrict__ pool,
                                                            const Tables *__restrict__ tables, Work *works, uint8_t *seqbuf,
-                                                           int seqcap, OutP out, int *counter) {
+                                                           int seqcap, int seq_shared, OutP out, int *counter) {
+    extern __shared__ __align__(16) uint8_t s_seq[];  // the three sequences of the triple, when they fit (seq_shared)
     __shared__ Tables s_tb;
     __shared__ int s_job;
     for (int k = threadIdx.x; k < (int) (sizeof(Tables) / sizeof(int)); k += blockDim.x)
         reinterpret_cast<int *>(&s_tb)[k] = reinterpret_cast<const int *>(tables)[k];
     Work *w = &works[blockIdx.x];
     uint8_t *sq[3];
-    for (int k = 0; k < 3; k++) sq[k] = seqbuf + ((size_t) blockIdx.x * 3 + k) * seqcap;
+    for (int k = 0; k < 3; k++) sq[k] = seq_shared ? s_seq + (size_t) k * seqcap : seqbuf + ((size_t) blockIdx.x * 3 + k) * seqcap;
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) s_job = atomicAdd(counter, 1);
@@ -151,7 +153,7 @@ static Layout make_layout(int R, int Wd, int maxlevels, int rescap) {
     l.u = off; off += align_up(l.nx * Wd * sizeof(Entry), 256);
     l.top = off; off += align_up(l.nx * sizeof(int), 256);
     l.prev = off; off += align_up(l.nx * sizeof(int), 256);
-    l.keycnt = off; off += align_up((2 * ((size_t) maxlevels + 1) + 1) * sizeof(int), 256);
+    l.keycnt = off; off += align_up((2 * ((size_t) maxlevels + 1) + 1 + 1024) * sizeof(int), 256);
     l.list = off; off += align_up((size_t) l.listcap * 2 * sizeof(int), 256);
     l.res = off; off += align_up(3 * (size_t) rescap, 256);
     l.stack = off; off += align_up(256 * sizeof(poyb200::powell::Task), 256);
@@ -252,7 +254,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         if (round_jobs.empty()) { pending.swap(later); continue; }
         const Layout lay = make_layout(R, Wd, maxlevels, rescap);
         const size_t per_cta = lay.total + 3 * (size_t) seqcap + 256;
-        int grid = (int) std::min<size_t>(std::min<size_t>(round_jobs.size(), (size_t) ctx->sm_count * 2), std::max<size_t>(1, budget / per_cta));
+        int grid = (int) std::min<size_t>(std::min<size_t>(round_jobs.size(), (size_t) ctx->sm_count * PW_CTAS_PER_SM), std::max<size_t>(1, budget / per_cta));
         if (per_cta > budget) return fail(ctx, POYB200_ENOMEM, "Powell kernel: one workspace exceeds the memory budget");
         uint8_t *arena = nullptr, *seqbuf = nullptr;
         Work *d_works = nullptr;
@@ -273,7 +275,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
             w.prev = reinterpret_cast<int *>(base + lay.prev);
             w.keycnt = reinterpret_cast<int *>(base + lay.keycnt);
             w.list = reinterpret_cast<int *>(base + lay.list);
-            w.listcap = lay.listcap; w.maxlevels = maxlevels;
+            w.listcap = lay.listcap; w.maxlevels = maxlevels; w.keycap = 2 * (maxlevels + 1) + 1;
             w.resA = base + lay.res; w.resB = w.resA + rescap; w.resC = w.resB + rescap; w.rescap = rescap;
             w.stack = reinterpret_cast<poyb200::powell::Task *>(base + lay.stack); w.stackcap = 256;
             w.nextOffset = 1;
@@ -282,8 +284,10 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         CK(cudaMemsetAsync(arena, 0xff, lay.total * (size_t) grid, ctx->stream));  // every tag = -1: nothing computed
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(int), ctx->stream));
         CK(cudaMemcpyAsync(d_jobs, round_jobs.data(), round_jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
-        powell_kernel<<<grid, PW_THREADS, 0, ctx->stream>>>(d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb, d_works, seqbuf, seqcap, out,
-                                                            ctx->d_counters.p);
+        const int seq_shared = 3 * (size_t) seqcap <= 40 * 1024;  // within the default dynamic shared memory limit, 4 CTAs per SM
+        powell_kernel<<<grid, PW_THREADS, seq_shared ? 3 * (size_t) seqcap : 0, ctx->stream>>>(d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb,
+                                                                                             d_works, seqbuf, seqcap, seq_shared, out,
+                                                                                             ctx->d_counters.p);
         CK(cudaGetLastError());
         ctx->launches++;
         CK(cudaMemcpyAsync(status.data(), ctx->d_status.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

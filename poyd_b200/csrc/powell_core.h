@@ -102,7 +102,8 @@ struct Work {
     int R, D, cab, cac, Wd;      // D = 2 R + 1; Wd a power of two
     Entry *U;                    // D * D * NS * Wd
     int *top, *prev;             // D * D * NS: newest computed cost of the cell (NEGBIG: none), and the same one level earlier
-    int *keycnt;                 // 2 * (maxlevels + 1) + 1
+    int *keycnt;                 // keycap = 2 * (maxlevels + 1) + 1 key counters, then one partial sum per thread (<= 1024)
+    int keycap;
     int *list;                   // 2 ints per new cell: x, cost
     int listcap, maxlevels;
     uint8_t *resA, *resB, *resC; // alignment in reverse order ('-' = 0xff), capacity rescap
@@ -114,6 +115,7 @@ struct Work {
     int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist;
     long long costOffset;
     long long ncalc;             // cells computed (statistics)
+    long long st_sweeps, st_sweep_cells, st_levels, st_tops;  // statistics (thread 0)
     long long nextOffset;        // first tag offset of the next triple run in this workspace (tags never repeat)
 };
 
@@ -179,85 +181,121 @@ struct Engine {
         dst.fab = e.fab; dst.fac = e.fac; dst.fcost = e.fcost; dst.fstate = e.fstate; dst.fdist = e.fdist;
     }
 
-    // calcUkk (:608-784) for cell x = (ab, ac, toState) at cost d.
+    // Ukk(.., d, state) as a read of cell x (box index, valid when `inb`) whose diagonal enters the matrix at cost `lo`.  Errors
+    // are collected in `err` and stored once per calc(): a store between the loads would serialise them.
+    PW_HD int read(int x, int d, int lo, bool inb, int &err) const {
+        if (d < lo) return -PW_INF;  // !withinMatrix (lo >= 0)
+        if (!inb) { err |= 1 << PW_EBOX; return -PW_INF; }
+        const Entry &e = cell(x, d);
+        if (e.tag != (int32_t) (d + w->costOffset)) { err |= 1 << PW_EWINDOW; return -PW_INF; }
+        return e.dist;
+    }
+
+    // calcUkk (:608-784) for cell x = (ab, ac, toState) at cost d.  The 16 from-states are independent of each other until
+    // the final "first strict improvement wins" scan, so their reads are issued together (three rounds of loads instead of
+    // sixteen chains of three).
     PW_HD void calc(int ab, int ac, int d, int toState) const {
         const uint8_t *A = w->A, *B = w->B, *C = w->C;
         Entry out;
         out.fab = 0; out.fac = 0; out.fcost = -1; out.fstate = 0; out.fdist = 0;
-        int bestDist = -PW_INF;
+        int bestDist = -PW_INF, err = 0;
         const bool cpwin = d >= CPcost && d < CPcost + CPwidth;
         const bool cpinherit = !completeFromInfo && d >= CPcost + CPwidth;
         if (cpwin) { out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) d; out.fstate = (int16_t) toState; }
         const int da = tb->da[toState], db = tb->db[toState], dc = tb->dc[toState];
         const int ab1 = ab - da + db, ac1 = ac - da + dc;
+        int from_ab = 0, from_ac = 0, from_cost = 0, from_state = -1;  // the predecessor chosen so far (from_state < 0: none)
         if (diag_ok(ab1, ac1)) {
-            for (int fromState = 0; fromState < NS; fromState++) {
-                const int cost = d - tb->trans[fromState][toState] - tb->cont[toState];
-                int fromCost = -PW_INF, dist = -PW_INF;
-                const int a1 = U(ab1, ac1, cost, fromState);
-                bool first = false;
+            const bool inb = in_box(ab1, ac1);
+            const int lo1 = lower(ab1, ac1), xb = inb ? xi(ab1, ac1, 0) : 0;
+            const int base = d - tb->cont[toState], mis = tb->mis;
+            const bool second = tb->second[toState] != 0;
+            int a1v[NS], a2v[NS];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int fs = 0; fs < NS; fs++) {
+                const int cost = base - tb->trans[fs][toState];
+                a1v[fs] = read(xb + fs, cost, lo1, inb, err);
+                a2v[fs] = second ? read(xb + fs, cost - mis, lo1, inb, err) : -PW_INF;
+            }
+            unsigned firstmask = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int fs = 0; fs < NS; fs++) {
+                const int a1 = a1v[fs];
                 if (ok_index(a1, da, endA) && ok_index(a1 - ab1, db, endB) && ok_index(a1 - ac1, dc, endC)) {
                     // whichCharCost(...) == 1 (ukkCommon.c:155-184): not all three equal, but two of them are
                     const int ca = da ? A[a1] : 256, cb = db ? B[a1 - ab1] : 256, cc = dc ? C[a1 - ac1] : 256;
-                    first = !(ca == cb && ca == cc) && (ca == cb || ca == cc || cb == cc);
+                    if (!(ca == cb && ca == cc) && (ca == cb || ca == cc || cb == cc)) firstmask |= 1u << fs;
                 }
-                if (first) {
+            }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int fs = 0; fs < NS; fs++) {  // in the reference's order: the first strict improvement wins (:679)
+                const int cost = base - tb->trans[fs][toState];
+                int fromCost = -PW_INF, dist = -PW_INF;
+                if ((firstmask >> fs) & 1) {
                     fromCost = cost;
-                    dist = a1 + da;
-                } else {
-                    if (!tb->second[toState]) continue;
-                    const int a2 = U(ab1, ac1, cost - tb->mis, fromState);
+                    dist = a1v[fs] + da;
+                } else if (second) {
+                    const int a2 = a2v[fs];
                     if (ok_index(a2, da, endA) && ok_index(a2 - ab1, db, endB) && ok_index(a2 - ac1, dc, endC)) {
-                        fromCost = cost - tb->mis;
+                        fromCost = cost - mis;
                         dist = a2 + da;
                     }
                 }
                 if (bestDist < dist) {
                     bestDist = dist;
-                    if (completeFromInfo) {
-                        out.fab = (int16_t) ab1; out.fac = (int16_t) ac1; out.fcost = (int16_t) fromCost; out.fstate = (int16_t) fromState;
-                    } else if (cpinherit) {
-                        inherit(out, ab1, ac1, fromCost, fromState);
-                    }
+                    from_ab = ab1; from_ac = ac1; from_cost = fromCost; from_state = fs;
                 }
             }
         }
+        const bool inb0 = in_box(ab, ac);  // true: the cell itself is in the box
+        const int lo0 = lower(ab, ac), x0 = xi(ab, ac, 0);
         {   // what can be reached for AT MOST cost d (:693-711)
-            const int dist = U(ab, ac, d - 1, toState);
+            const int dist = read(x0 + toState, d - 1, lo0, inb0, err);
             if (ok_index(dist, 0, endA) && ok_index(dist - ab, 0, endB) && ok_index(dist - ac, 0, endC) && bestDist < dist) {
                 bestDist = dist;
-                if (completeFromInfo) {
-                    out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) (d - 1); out.fstate = (int16_t) toState;
-                } else if (cpinherit) {
-                    inherit(out, ab, ac, d - 1, toState);
-                }
+                from_ab = ab; from_ac = ac; from_cost = d - 1; from_state = toState;
             }
         }
         if (toState == 0) {  // extend along a run of matches from the furthest state of this cell (:713-764)
-            int dist = -PW_INF, from_state = -1;
-            for (int s = 0; s < NS; s++) {
-                const int thisdist = (s == 0) ? bestDist : U(ab, ac, d, s);
-                if (thisdist > dist) { dist = thisdist; from_state = s; }
-            }
+            int sv[NS];
+            sv[0] = bestDist;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int st = 1; st < NS; st++) sv[st] = read(x0 + st, d, lo0, inb0, err);
+            int dist = -PW_INF, best_state = -1;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int st = 0; st < NS; st++)
+                if (sv[st] > dist) { dist = sv[st]; best_state = st; }
             while (ok_index(dist, 1, endA) && ok_index(dist - ab, 1, endB) && ok_index(dist - ac, 1, endC) && A[dist] == B[dist - ab] &&
                    A[dist] == C[dist - ac])
                 dist++;
             if (dist > bestDist) {
                 bestDist = dist;
-                if (from_state != 0) {
-                    if (completeFromInfo) {
-                        out.fab = (int16_t) ab; out.fac = (int16_t) ac; out.fcost = (int16_t) d; out.fstate = (int16_t) from_state;
-                    } else if (cpinherit) {
-                        inherit(out, ab, ac, d, from_state);
-                    }
-                }
+                if (best_state != 0) { from_ab = ab; from_ac = ac; from_cost = d; from_state = best_state; }
+            }
+        }
+        if (from_state >= 0) {
+            if (completeFromInfo) {
+                out.fab = (int16_t) from_ab; out.fac = (int16_t) from_ac; out.fcost = (int16_t) from_cost; out.fstate = (int16_t) from_state;
+            } else if (cpinherit) {
+                inherit(out, from_ab, from_ac, from_cost, from_state);
             }
         }
         out.dist = (int16_t) bestDist;
         if (cpwin && out.fab == ab && out.fac == ac && out.fcost == d && out.fstate == toState) out.fdist = (int16_t) bestDist;  // CP(...)->dist (:592-595)
         out.tag = (int32_t) (d + w->costOffset);
-        cell(xi(ab, ac, toState), d) = out;
+        cell(x0 + toState, d) = out;
         if (bestDist > w->fr) PW_ATOMIC_MAX(&w->fr, bestDist);  // furthestReached (:597)
+        if (err) w->status = (err & (1 << PW_EBOX)) ? PW_EBOX : PW_EWINDOW;
     }
 
     PW_HD void decode(int x, int &ab, int &ac, int &st) const {
@@ -344,10 +382,15 @@ struct Engine {
     // All cells the reference computes for the top-level calls Ukk(root, T, .): relax, list, compute in cost order.
     PW_HD void top_level(int T, int r0, int r1) const {
         if (T - sCost >= w->maxlevels) { if (PW_TID == 0) w->status = PW_ECAP; PW_SYNC(); return; }
+        if (PW_TID == 0) w->st_tops++;
         bump();
         PW_SYNC();
         for (;;) {
-            if (PW_TID == 0) w->changed = 0;
+            if (PW_TID == 0) {
+                w->changed = 0;
+                w->st_sweeps++;
+                w->st_sweep_cells += (long long) (w->hi_ab - w->lo_ab + 3) * (w->hi_ac - w->lo_ac + 3) * NS;
+            }
             PW_SYNC();
             sweep(T, r0, r1);
             PW_SYNC();
@@ -360,12 +403,22 @@ struct Engine {
         PW_SYNC();
         collect(false);
         PW_SYNC();
-        if (PW_TID == 0) {
-            int run = 0;
-            for (int k = 0; k < nkeys; k++) { const int c = w->keycnt[k]; w->keycnt[k] = run; run += c; }
-            w->nlist = run;
-            w->ncalc += run;
-            if (run > w->listcap) w->status = PW_ELIST;
+        {   // exclusive prefix over the keys, all threads: a contiguous chunk each, partial sums behind the keys
+            int *part = w->keycnt + w->keycap;
+            const int chunk = (nkeys + PW_NT - 1) / PW_NT;
+            const int klo = PW_TID * chunk < nkeys ? PW_TID * chunk : nkeys, khi = klo + chunk < nkeys ? klo + chunk : nkeys;
+            int sum = 0;
+            for (int k = klo; k < khi; k++) sum += w->keycnt[k];
+            part[PW_TID] = sum;
+            PW_SYNC();
+            int base = 0, total = 0;
+            for (int u = 0; u < PW_NT; u++) { const int v = part[u]; if (u < PW_TID) base += v; total += v; }
+            for (int k = klo; k < khi; k++) { const int c = w->keycnt[k]; w->keycnt[k] = base; base += c; }
+            if (PW_TID == 0) {
+                w->nlist = total;
+                w->ncalc += total;
+                if (total > w->listcap) w->status = PW_ELIST;
+            }
         }
         PW_SYNC();
         if (w->status) return;
@@ -375,6 +428,7 @@ struct Engine {
         for (int k = 0; k < nkeys; k++) {
             const int begin = k == 0 ? 0 : w->keycnt[k - 1], end = w->keycnt[k];
             if (end == begin) continue;
+            if (PW_TID == 0) w->st_levels++;
             for (int i = begin + PW_TID; i < end; i += PW_NT) {
                 int ab, ac, st;
                 decode(w->list[2 * i], ab, ac, st);

@@ -23,7 +23,7 @@ static int collapse(const unsigned char *s, int n, std::vector<uint8_t> &out) { 
 
 extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned char *s2, int l2, const unsigned char *s3, int l3, int mm,
                              int go, int ge, int R, int Wd, unsigned char *r1, unsigned char *r2, unsigned char *r3, int *rlen, int *status,
-                             long long *cells) {
+                             long long *cells /* 5 statistics, may be NULL */) {
     std::vector<uint8_t> A, B, C;
     *status = PW_EINPUT;
     *rlen = 0;
@@ -44,7 +44,8 @@ extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned cha
     memset(U.data(), 0xff, U.size() * sizeof(Entry));
     std::vector<int> top(nx, NEGBIG), prev(nx, NEGBIG);
     w.maxlevels = 2 * (w.Alen + w.Blen + w.Clen) * (ge > mm ? ge : mm) + 6 * go + 16;
-    std::vector<int> keycnt(2 * (w.maxlevels + 1) + 1), list(4 * nx);
+    std::vector<int> keycnt(2 * (w.maxlevels + 1) + 1 + 1024), list(4 * nx);
+    w.keycap = 2 * (w.maxlevels + 1) + 1;
     w.U = U.data(); w.top = top.data(); w.prev = prev.data(); w.keycnt = keycnt.data(); w.list = list.data();
     w.listcap = (int) (2 * nx);
     const int cap = w.Alen + w.Blen + w.Clen + 1;
@@ -58,7 +59,7 @@ extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned cha
     e.w = &w; e.tb = &tb;
     const int cost = e.run();
     *status = w.status;
-    if (cells) *cells = w.ncalc;
+    if (cells) { cells[0] = w.ncalc; cells[1] = w.st_sweeps; cells[2] = w.st_sweep_cells; cells[3] = w.st_levels; cells[4] = w.st_tops; }
     if (w.status) return -1;
     // printTraceBack :477-495: the rows, forward, behind one gap
     r1[0] = r2[0] = r3[0] = 16;

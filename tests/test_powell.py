@@ -38,9 +38,9 @@ def host_powell(host, a, b, c, mm, go, ge):
     R = 16
     while True:
         rows = [np.zeros(cap, np.uint8) for _ in range(3)]
-        n, st, cells = C.c_int(0), C.c_int(0), C.c_longlong(0)
+        n, st = C.c_int(0), C.c_int(0)
         cost = host.pw_host_align(a.ctypes.data_as(PU.u8), len(a), b.ctypes.data_as(PU.u8), len(b), c.ctypes.data_as(PU.u8), len(c),
-                                  mm, go, ge, R, 0, *[r.ctypes.data_as(PU.u8) for r in rows], C.byref(n), C.byref(st), C.byref(cells))
+                                  mm, go, ge, R, 0, *[r.ctypes.data_as(PU.u8) for r in rows], C.byref(n), C.byref(st), None)
         if st.value == 1 and R < 512:  # PW_EBOX: the diagonal box was too small, like the library's next round
             R *= 2
             continue
