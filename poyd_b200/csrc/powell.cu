@@ -23,8 +23,14 @@
 namespace poyb200 {
 namespace powell {
 
-constexpr int PW_THREADS = 128;   // a cost level of one triple rarely holds more cells than this
-constexpr int PW_CTAS_PER_SM = 4;  // the work of a level is a chain of dependent loads: several triples per SM overlap them
+#ifndef POYB200_PW_THREADS
+#define POYB200_PW_THREADS 256
+#endif
+#ifndef POYB200_PW_CTAS
+#define POYB200_PW_CTAS 2
+#endif
+constexpr int PW_THREADS = POYB200_PW_THREADS;  // a cost level of one triple rarely holds more cells than this
+constexpr int PW_CTAS_PER_SM = POYB200_PW_CTAS; // the work of a level is a chain of dependent loads: several triples per SM overlap them
 
 struct Job {
     uint32_t off[3];
@@ -284,7 +290,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         CK(cudaMemsetAsync(arena, 0xff, lay.total * (size_t) grid, ctx->stream));  // every tag = -1: nothing computed
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(int), ctx->stream));
         CK(cudaMemcpyAsync(d_jobs, round_jobs.data(), round_jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
-        const int seq_shared = 3 * (size_t) seqcap <= 40 * 1024;  // within the default dynamic shared memory limit, 4 CTAs per SM
+        const int seq_shared = 3 * (size_t) seqcap <= 40 * 1024;  // within the default dynamic shared memory limit
         powell_kernel<<<grid, PW_THREADS, seq_shared ? 3 * (size_t) seqcap : 0, ctx->stream>>>(d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb,
                                                                                              d_works, seqbuf, seqcap, seq_shared, out,
                                                                                              ctx->d_counters.p);

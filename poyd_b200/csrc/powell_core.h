@@ -42,6 +42,7 @@ namespace powell {
 constexpr int NS = 16;          // states with at least one match and at most one insert (setup() :264-273)
 constexpr int PW_INF = 5000;    // INFINITY = MAXINT / 2, MAXINT = 10000 (ukkCommon.h:41, ukk.checkp.c:31)
 constexpr int NEGBIG = -(1 << 28);
+constexpr int PW_STRIDE = 8;    // top levels advanced per closure once the check-point of the first pass is placed
 enum { PW_OK = 0, PW_EBOX = 1, PW_EWINDOW = 2, PW_ELIST = 3, PW_ESTACK = 4, PW_EINPUT = 5, PW_ECAP = 6 };
 
 struct Tables {
@@ -112,7 +113,7 @@ struct Work {
     int stackcap;
     // --- scalars shared by the group (written by thread 0 between barriers, or by atomics)
     int status, nres, nstack;
-    int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist;
+    int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist, win_k1, win_base;
     long long costOffset;
     long long ncalc;             // cells computed (statistics)
     long long st_sweeps, st_sweep_cells, st_levels, st_tops;  // statistics (thread 0)
@@ -311,7 +312,7 @@ struct Engine {
     }
 
     // Top level T - 1 -> T, step 1: every cell that was demanded keeps being demanded one cost higher (the same path).
-    PW_HD void bump() const {
+    PW_HD void bump(int inc) const {
         const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
         const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
         for (int k = PW_TID; k < total; k += PW_NT) {
@@ -319,7 +320,7 @@ struct Engine {
             const int x = xi(lo_ab + q / nac, lo_ac + q % nac, st);
             const int t = w->top[x];
             w->prev[x] = t;
-            if (t != NEGBIG && !(x == startx && t <= sCost)) w->top[x] = t + 1;
+            if (t != NEGBIG && !(x == startx && t <= sCost)) w->top[x] = t + inc;
         }
     }
     // Step 2, repeated until nothing changes: one pull sweep of the demand closure over the bounding box of the active cells
@@ -360,7 +361,7 @@ struct Engine {
         }
     }
     // The cells that became demanded at this top level, as (x, cost) sorted by (cost, MMM last).  count = false: scatter.
-    PW_HD void collect(bool scatter) const {
+    PW_HD void collect(bool scatter, int k0, int k1, int base) const {
         const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
         const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
         for (int k = PW_TID; k < total; k += PW_NT) {
@@ -373,17 +374,18 @@ struct Engine {
             int lo = (pv == NEGBIG) ? lower(ab, ac) : pv + 1;
             for (int c = lo; c <= hi; c++) {
                 const int key = 2 * (c - sCost) + (st == 0 ? 1 : 0);
-                const int pos = PW_ATOMIC_ADD(&w->keycnt[key], 1);
-                if (scatter && pos < w->listcap) { w->list[2 * pos] = x; w->list[2 * pos + 1] = c; }
+                if (key < k0 || key >= k1) continue;
+                const int pos = PW_ATOMIC_ADD(&w->keycnt[key], 1) - base;
+                if (scatter) { w->list[2 * pos] = x; w->list[2 * pos + 1] = c; }
             }
         }
     }
 
     // All cells the reference computes for the top-level calls Ukk(root, T, .): relax, list, compute in cost order.
-    PW_HD void top_level(int T, int r0, int r1) const {
+    PW_HD void top_level(int T, int r0, int r1, int inc) const {
         if (T - sCost >= w->maxlevels) { if (PW_TID == 0) w->status = PW_ECAP; PW_SYNC(); return; }
         if (PW_TID == 0) w->st_tops++;
-        bump();
+        bump(inc);
         PW_SYNC();
         for (;;) {
             if (PW_TID == 0) {
@@ -401,7 +403,7 @@ struct Engine {
         const int nkeys = 2 * (T - sCost + 1);
         for (int k = PW_TID; k < nkeys; k += PW_NT) w->keycnt[k] = 0;
         PW_SYNC();
-        collect(false);
+        collect(false, 0, nkeys, 0);
         PW_SYNC();
         {   // exclusive prefix over the keys, all threads: a contiguous chunk each, partial sums behind the keys
             int *part = w->keycnt + w->keycap;
@@ -417,24 +419,39 @@ struct Engine {
             if (PW_TID == 0) {
                 w->nlist = total;
                 w->ncalc += total;
-                if (total > w->listcap) w->status = PW_ELIST;
             }
         }
         PW_SYNC();
-        if (w->status) return;
-        collect(true);
-        PW_SYNC();
-        // keycnt[k] is now the END of key k
-        for (int k = 0; k < nkeys; k++) {
-            const int begin = k == 0 ? 0 : w->keycnt[k - 1], end = w->keycnt[k];
-            if (end == begin) continue;
-            if (PW_TID == 0) w->st_levels++;
-            for (int i = begin + PW_TID; i < end; i += PW_NT) {
-                int ab, ac, st;
-                decode(w->list[2 * i], ab, ac, st);
-                calc(ab, ac, w->list[2 * i + 1], st);
+        // The list holds listcap cells: the keys are taken in windows [k0, k1) that fit (one window when the top levels are
+        // stepped one by one; a pass computed in one go needs several).
+        for (int k0 = 0; k0 < nkeys && !w->status;) {
+            if (PW_TID == 0) {
+                const int base = w->keycnt[k0];  // exclusive offset of k0 (keys >= k0 still hold their start offsets)
+                int k1 = k0 + 1;  // start(k) = keycnt[k] for k < nkeys, the total for k = nkeys
+                if ((k1 < nkeys ? w->keycnt[k1] : w->nlist) - base > w->listcap) w->status = PW_ELIST;
+                else
+                    while (k1 < nkeys && (k1 + 1 < nkeys ? w->keycnt[k1 + 1] : w->nlist) - base <= w->listcap) k1++;
+                w->win_k1 = k1;
+                w->win_base = base;
             }
             PW_SYNC();
+            const int k1 = w->win_k1, base = w->win_base;
+            if (w->status) break;
+            collect(true, k0, k1, base);
+            PW_SYNC();
+            // keycnt[k] is now the END of key k for k0 <= k < k1 (and for every earlier key)
+            for (int k = k0; k < k1; k++) {
+                const int begin = (k == 0 ? 0 : w->keycnt[k - 1]) - base, end = w->keycnt[k] - base;
+                if (end == begin) continue;
+                if (PW_TID == 0) w->st_levels++;
+                for (int i = begin + PW_TID; i < end; i += PW_NT) {
+                    int ab, ac, st;
+                    decode(w->list[2 * i], ab, ac, st);
+                    calc(ab, ac, w->list[2 * i + 1], st);
+                }
+                PW_SYNC();
+            }
+            k0 = k1;
         }
     }
 
@@ -540,16 +557,29 @@ struct Engine {
         if (base) completeFromInfo = 1;
         else CPcost = (t.fCost + t.sCost - CPwidth + 1) / 2;
         const int rf = xi(t.fab, t.fac, t.fState), r0 = base ? -1 : xi(t.fab, t.fac, 0);
-        int T = t.sCost - 1, dist;
-        do {
-            T++;
-            top_level(T, r0, rf);
-            if (w->status) return;
-            dist = U(t.fab, t.fac, T, t.fState);
-            PW_TRACE("  T=%d dist=%d nlist=%d status=%d\n", T, dist, w->nlist, w->status);
-        } while (dist < t.fDist && !w->status);
+        // The reference steps i = sCost, sCost + 1, ... until Ukk(f, i, fState) reaches fDist, which happens at i = fCost
+        // (:261-271, :305-316).  The cells it has computed by then are those of the last step alone (top() only grows), and
+        // their values do not depend on the stepping, so the closure is taken once, at fCost, and the cells are computed in
+        // one sweep over the cost levels: 2 (fCost - sCost) block-wide levels instead of one set of levels per step.
+        int T = t.fCost;
+        top_level(T, r0, rf, T - t.sCost);
         if (w->status) return;
-        t.fCost = T;  // `if (i != fCost) ... fCost = i` (:267-271, :312-316)
+        int reach = -1;
+        {
+            int c = T - w->Wd / 2;
+            if (c < t.sCost) c = t.sCost;
+            for (; c <= T; c++)
+                if (U(t.fab, t.fac, c, t.fState) >= t.fDist) { reach = c; break; }
+        }
+        while (reach < 0 && !w->status) {  // not reached at fCost: go on like the reference would
+            T++;
+            top_level(T, r0, rf, 1);
+            if (w->status) return;
+            if (U(t.fab, t.fac, T, t.fState) >= t.fDist) reach = T;
+        }
+        if (w->status) return;
+        PW_TRACE("  reached at %d (expected %d)\n", reach, t.fCost);
+        t.fCost = reach;  // `if (i != fCost) ... fCost = i` (:267-271, :312-316)
         if (PW_TID == 0) {
             if (base) trace_back(t);
             else split(t);
@@ -583,14 +613,28 @@ struct Engine {
         bool CPonDist = true;
         CPcost = PW_INF;
         const int rf = xi(finalab, finalac, 0);
+        // Until the check-point is placed the top levels are stepped one by one: furthestReached must be what the recursion
+        // would have seen after each of them.  Afterwards only "which cost reaches the end first" matters, the values do not
+        // depend on the stepping, and the closure is advanced PW_STRIDE costs at a time (a few cells past the final cost get
+        // computed that the reference never asks for; nothing reads them).
         int d = -1;
-        do {
-            d++;
-            top_level(d, rf, -1);
-            if (w->status) return -1;
-            if (CPonDist && w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
-            PW_TRACE("pass1 d=%d fr=%d best=%d nlist=%d CPcost=%d\n", d, w->fr, best(finalab, finalac, d, false), w->nlist, CPcost);
-        } while (best(finalab, finalac, d, false) < Alen);
+        for (bool done = false; !done;) {
+            if (CPonDist) {
+                d++;
+                top_level(d, rf, -1, 1);
+                if (w->status) return -1;
+                if (w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
+                PW_TRACE("pass1 d=%d fr=%d best=%d nlist=%d CPcost=%d\n", d, w->fr, best(finalab, finalac, d, false), w->nlist, CPcost);
+                done = best(finalab, finalac, d, false) >= Alen;
+            } else {
+                const int dn = d + PW_STRIDE;
+                top_level(dn, rf, -1, PW_STRIDE);
+                if (w->status) return -1;
+                for (int c = d + 1; c <= dn && !done; c++)
+                    if (best(finalab, finalac, c, false) >= Alen) { d = c; done = true; }
+                if (!done) d = dn;
+            }
+        }
         const int finalCost = d;
         const int fState = best(finalab, finalac, finalCost, true);
         Task whole{0, 0, 0, 0, startDist, finalab, finalac, finalCost, fState, Alen};

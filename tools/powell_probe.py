@@ -16,7 +16,10 @@ def main():
     ref = PU.reference()
     cm = CM.nucleotides(1, 2, 3)
     al = S.Align3(cm, CM.of_two_dim(cm))
-    for n, p, count in ((100, 0.05, 592), (300, 0.03, 592), (300, 0.10, 148), (500, 0.05, 148)):
+    configs = ((100, 0.05, 592), (300, 0.03, 592), (300, 0.10, 148), (500, 0.05, 148))
+    if len(sys.argv) > 1:  # "n,p,count" triples on the command line
+        configs = tuple((int(a.split(",")[0]), float(a.split(",")[1]), int(a.split(",")[2])) for a in sys.argv[1:])
+    for n, p, count in configs:
         rng = np.random.default_rng(n)
         cases = []
         for _ in range(count):
@@ -29,7 +32,7 @@ def main():
         g = al.align_3_powell(pool, triples, 1, 3, 2, want=3)
         dt = time.perf_counter() - t0
         line = f"n={n} p={p} triples={count}: {dt:.3f} s = {count / dt:.1f} triples/s, mean cost {g.cost.mean():.1f}, status {np.bincount(g.status)}"
-        if ref is not None:
+        if ref is not None and not os.environ.get("PROBE_NO_REF"):
             k = 4 if n >= 300 else 12
             t0 = time.perf_counter()
             ok = True
