@@ -23,14 +23,11 @@
 namespace poyb200 {
 namespace powell {
 
-#ifndef POYB200_PW_THREADS
-#define POYB200_PW_THREADS 256
-#endif
-#ifndef POYB200_PW_CTAS
-#define POYB200_PW_CTAS 2
-#endif
-constexpr int PW_THREADS = POYB200_PW_THREADS;  // a cost level of one triple rarely holds more cells than this
-constexpr int PW_CTAS_PER_SM = POYB200_PW_CTAS; // the work of a level is a chain of dependent loads: several triples per SM overlap them
+// Launch shapes (measured, profiles/r02_powell_probe.txt): a cost level is a chain of dependent loads, so the triples of an SM
+// overlap each other's latency -- 256 threads x 2 CTAs per SM is the best throughput when there are more triples than SMs;
+// a small batch of heavy triples finishes sooner with 512 threads on each (128 x 4 was 2 - 3 x slower than either).
+constexpr int PW_THREADS_MANY = 256, PW_CTAS_MANY = 2;
+constexpr int PW_THREADS_FEW = 512, PW_CTAS_FEW = 1;
 
 struct Job {
     uint32_t off[3];
@@ -47,7 +44,8 @@ struct OutP {
     int lcm3, gap;
 };
 
-__global__ void __launch_bounds__(PW_THREADS, PW_CTAS_PER_SM) powell_kernel(const Job *__restrict__ jobs, int njobs, const uint8_t *__restrict__ pool,
+template <int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) powell_kernel(const Job *__restrict__ jobs, int njobs, const uint8_t *__restrict__ pool,
                                                            const Tables *__restrict__ tables, Work *works, uint8_t *seqbuf,
                                                            int seqcap, int seq_shared, OutP out, int *counter) {
     extern __shared__ __align__(16) uint8_t s_seq[];  // the three sequences of the triple, when they fit (seq_shared)
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(PW_THREADS, PW_CTAS_PER_SM) powell_kernel(cons
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-    size_t nx, u, top, prev, keycnt, list, res, stack, total;
+    size_t nx, u, top, prev, snap, keycnt, list, res, stack, total;
     int Wd, maxlevels, rescap, listcap;
 };
 static Layout make_layout(int R, int Wd, int maxlevels, int rescap) {
@@ -159,6 +157,7 @@ static Layout make_layout(int R, int Wd, int maxlevels, int rescap) {
     l.u = off; off += align_up(l.nx * Wd * sizeof(Entry), 256);
     l.top = off; off += align_up(l.nx * sizeof(int), 256);
     l.prev = off; off += align_up(l.nx * sizeof(int), 256);
+    l.snap = off; off += align_up(l.nx * sizeof(int), 256);
     l.keycnt = off; off += align_up((2 * ((size_t) maxlevels + 1) + 1 + 1024) * sizeof(int), 256);
     l.list = off; off += align_up((size_t) l.listcap * 2 * sizeof(int), 256);
     l.res = off; off += align_up(3 * (size_t) rescap, 256);
@@ -260,7 +259,9 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         if (round_jobs.empty()) { pending.swap(later); continue; }
         const Layout lay = make_layout(R, Wd, maxlevels, rescap);
         const size_t per_cta = lay.total + 3 * (size_t) seqcap + 256;
-        int grid = (int) std::min<size_t>(std::min<size_t>(round_jobs.size(), (size_t) ctx->sm_count * PW_CTAS_PER_SM), std::max<size_t>(1, budget / per_cta));
+        const bool many = round_jobs.size() > (size_t) ctx->sm_count;
+        const int ctas = many ? PW_CTAS_MANY : PW_CTAS_FEW;
+        int grid = (int) std::min<size_t>(std::min<size_t>(round_jobs.size(), (size_t) ctx->sm_count * ctas), std::max<size_t>(1, budget / per_cta));
         if (per_cta > budget) return fail(ctx, POYB200_ENOMEM, "Powell kernel: one workspace exceeds the memory budget");
         uint8_t *arena = nullptr, *seqbuf = nullptr;
         Work *d_works = nullptr;
@@ -279,6 +280,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
             w.U = reinterpret_cast<Entry *>(base + lay.u);
             w.top = reinterpret_cast<int *>(base + lay.top);
             w.prev = reinterpret_cast<int *>(base + lay.prev);
+            w.snap = reinterpret_cast<int *>(base + lay.snap);
             w.keycnt = reinterpret_cast<int *>(base + lay.keycnt);
             w.list = reinterpret_cast<int *>(base + lay.list);
             w.listcap = lay.listcap; w.maxlevels = maxlevels; w.keycap = 2 * (maxlevels + 1) + 1;
@@ -291,9 +293,13 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(int), ctx->stream));
         CK(cudaMemcpyAsync(d_jobs, round_jobs.data(), round_jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
         const int seq_shared = 3 * (size_t) seqcap <= 40 * 1024;  // within the default dynamic shared memory limit
-        powell_kernel<<<grid, PW_THREADS, seq_shared ? 3 * (size_t) seqcap : 0, ctx->stream>>>(d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb,
-                                                                                             d_works, seqbuf, seqcap, seq_shared, out,
-                                                                                             ctx->d_counters.p);
+        const size_t smem = seq_shared ? 3 * (size_t) seqcap : 0;
+        if (many)
+            powell_kernel<PW_THREADS_MANY, PW_CTAS_MANY><<<grid, PW_THREADS_MANY, smem, ctx->stream>>>(
+                d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb, d_works, seqbuf, seqcap, seq_shared, out, ctx->d_counters.p);
+        else
+            powell_kernel<PW_THREADS_FEW, PW_CTAS_FEW><<<grid, PW_THREADS_FEW, smem, ctx->stream>>>(
+                d_jobs, (int) round_jobs.size(), ctx->d_pool.p, d_tb, d_works, seqbuf, seqcap, seq_shared, out, ctx->d_counters.p);
         CK(cudaGetLastError());
         ctx->launches++;
         CK(cudaMemcpyAsync(status.data(), ctx->d_status.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

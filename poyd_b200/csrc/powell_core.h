@@ -102,6 +102,7 @@ struct Work {
     int Alen, Blen, Clen;
     int R, D, cab, cac, Wd;      // D = 2 R + 1; Wd a power of two
     Entry *U;                    // D * D * NS * Wd
+    int *snap;                   // D * D * NS: top() saved before a strided step of the first pass
     int *top, *prev;             // D * D * NS: newest computed cost of the cell (NEGBIG: none), and the same one level earlier
     int *keycnt;                 // keycap = 2 * (maxlevels + 1) + 1 key counters, then one partial sum per thread (<= 1024)
     int keycap;
@@ -114,6 +115,7 @@ struct Work {
     // --- scalars shared by the group (written by thread 0 between barriers, or by atomics)
     int status, nres, nstack;
     int changed, fr, lo_ab, hi_ab, lo_ac, hi_ac, nlist, win_k1, win_base;
+    int s_lo_ab, s_hi_ab, s_lo_ac, s_hi_ac;
     long long costOffset;
     long long ncalc;             // cells computed (statistics)
     long long st_sweeps, st_sweep_cells, st_levels, st_tops;  // statistics (thread 0)
@@ -383,6 +385,12 @@ struct Engine {
 
     // All cells the reference computes for the top-level calls Ukk(root, T, .): relax, list, compute in cost order.
     PW_HD void top_level(int T, int r0, int r1, int inc) const {
+        relax(T, r0, r1, inc);
+        if (w->status) return;
+        compute_new(T);
+    }
+    // The demand closure of top level T, `inc` costs after the previous one.
+    PW_HD void relax(int T, int r0, int r1, int inc) const {
         if (T - sCost >= w->maxlevels) { if (PW_TID == 0) w->status = PW_ECAP; PW_SYNC(); return; }
         if (PW_TID == 0) w->st_tops++;
         bump(inc);
@@ -399,7 +407,9 @@ struct Engine {
             if (!w->changed || w->status) break;
             PW_SYNC();
         }
-        if (w->status) return;
+    }
+    // The cells between prev() and top(), computed in order of their cost.
+    PW_HD void compute_new(int T) const {
         const int nkeys = 2 * (T - sCost + 1);
         for (int k = PW_TID; k < nkeys; k += PW_NT) w->keycnt[k] = 0;
         PW_SYNC();
@@ -453,6 +463,54 @@ struct Engine {
             }
             k0 = k1;
         }
+    }
+
+    // Demand state saved / restored around a strided step of the first pass (see run()).
+    PW_HD void snapshot_save() const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int x = xi(lo_ab + q / nac, lo_ac + q % nac, st);
+            w->snap[x] = w->top[x];
+        }
+        if (PW_TID == 0) { w->s_lo_ab = lo_ab; w->s_hi_ab = hi_ab; w->s_lo_ac = lo_ac; w->s_hi_ac = hi_ac; }
+        PW_SYNC();
+    }
+    PW_HD void snapshot_restore() const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;  // the larger, current region
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        PW_SYNC();
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int ab = lo_ab + q / nac, ac = lo_ac + q % nac;
+            const int x = xi(ab, ac, st);
+            const bool saved = ab >= w->s_lo_ab && ab <= w->s_hi_ab && ac >= w->s_lo_ac && ac <= w->s_hi_ac;
+            w->top[x] = saved ? w->snap[x] : NEGBIG;
+            w->prev[x] = w->top[x];
+        }
+        PW_SYNC();
+        if (PW_TID == 0) { w->lo_ab = w->s_lo_ab; w->hi_ab = w->s_hi_ab; w->lo_ac = w->s_lo_ac; w->hi_ac = w->s_hi_ac; }
+        PW_SYNC();
+    }
+    // Largest U among the cells between prev() and top() -- already computed (replay of a strided step) -- into w->fr.
+    PW_HD void scan_new() const {
+        const int lo_ab = w->lo_ab, hi_ab = w->hi_ab, lo_ac = w->lo_ac, hi_ac = w->hi_ac;
+        const int nac = hi_ac - lo_ac + 1, total = (hi_ab - lo_ab + 1) * nac * NS;
+        for (int k = PW_TID; k < total; k += PW_NT) {
+            const int st = k % NS, q = k / NS;
+            const int ab = lo_ab + q / nac, ac = lo_ac + q % nac;
+            const int x = xi(ab, ac, st);
+            const int hi = w->top[x];
+            if (hi == NEGBIG) continue;
+            const int pv = w->prev[x];
+            const int lo = (pv == NEGBIG) ? lower(ab, ac) : pv + 1;
+            if (lo > hi) continue;
+            const Entry &e = cell(x, hi);  // U grows with the cost on a diagonal: the top cell of the range holds the maximum
+            if (e.tag != (int32_t) (hi + w->costOffset)) { w->status = PW_EWINDOW; continue; }
+            if (e.dist > w->fr) PW_ATOMIC_MAX(&w->fr, (int) e.dist);
+        }
+        PW_SYNC();
     }
 
     // Start of a pass: the preset start cell and an empty demand state.  Thread 0, between barriers.
@@ -620,12 +678,32 @@ struct Engine {
         int d = -1;
         for (bool done = false; !done;) {
             if (CPonDist) {
-                d++;
-                top_level(d, rf, -1, 1);
+                // A strided step first.  If furthestReached is still short of |A| / 2 after it, it was short after every top
+                // level inside the step as well.  Otherwise the step is replayed level by level on the values just computed
+                // (relaxation only) to find the level at which the reference places its check-point; the demand state is then
+                // exactly the one of that level, and the cells above it are computed again with the check-point in force.
+                const int d0 = d, dn = d + PW_STRIDE, fr0 = w->fr;
+                snapshot_save();
+                top_level(dn, rf, -1, PW_STRIDE);
                 if (w->status) return -1;
-                if (w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
-                PW_TRACE("pass1 d=%d fr=%d best=%d nlist=%d CPcost=%d\n", d, w->fr, best(finalab, finalac, d, false), w->nlist, CPcost);
-                done = best(finalab, finalac, d, false) >= Alen;
+                bool hit = w->fr >= Alen / 2;  // ... or the end of A is reached inside the step (it can be without any computed
+                for (int c = d0 + 1; c <= dn && !hit; c++)  // cell: identical sequences end on the preset start cell)
+                    hit = best(finalab, finalac, c, false) >= Alen;
+                if (!hit) { d = dn; continue; }
+                snapshot_restore();
+                if (PW_TID == 0) w->fr = fr0;
+                PW_SYNC();
+                for (d = d0 + 1; d <= dn; d++) {  // the reference's order per level: compute, place the check-point, test the end
+                    relax(d, rf, -1, 1);
+                    if (w->status) return -1;
+                    scan_new();
+                    if (w->status) return -1;
+                    if (w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
+                    done = best(finalab, finalac, d, false) >= Alen;
+                    if (done || !CPonDist) break;
+                }
+                if (d > dn) { if (PW_TID == 0) w->status = PW_EWINDOW; PW_SYNC(); return -1; }  // cannot happen
+                PW_TRACE("pass1 replay stopped at d=%d fr=%d CPcost=%d done=%d\n", d, w->fr, CPcost, (int) done);
             } else {
                 const int dn = d + PW_STRIDE;
                 top_level(dn, rf, -1, PW_STRIDE);

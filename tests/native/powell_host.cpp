@@ -42,11 +42,11 @@ extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned cha
     const size_t nx = (size_t) w.D * w.D * NS;
     std::vector<Entry> U(nx * Wd);
     memset(U.data(), 0xff, U.size() * sizeof(Entry));
-    std::vector<int> top(nx, NEGBIG), prev(nx, NEGBIG);
+    std::vector<int> top(nx, NEGBIG), prev(nx, NEGBIG), snap(nx, NEGBIG);
     w.maxlevels = 2 * (w.Alen + w.Blen + w.Clen) * (ge > mm ? ge : mm) + 6 * go + 16;
     std::vector<int> keycnt(2 * (w.maxlevels + 1) + 1 + 1024), list(4 * nx);
     w.keycap = 2 * (w.maxlevels + 1) + 1;
-    w.U = U.data(); w.top = top.data(); w.prev = prev.data(); w.keycnt = keycnt.data(); w.list = list.data();
+    w.U = U.data(); w.top = top.data(); w.prev = prev.data(); w.snap = snap.data(); w.keycnt = keycnt.data(); w.list = list.data();
     w.listcap = (int) (2 * nx);
     const int cap = w.Alen + w.Blen + w.Clen + 1;
     std::vector<uint8_t> ra(cap), rb(cap), rc(cap);
