@@ -657,6 +657,91 @@ def run_cube_workload(args, rank, local_rank, D):
     return res
 
 
+def _powell_triples(count, n, p, seed):
+    """`count` triples (a, two mutated copies of a), length n, substitution / indel rate p: what readjust_3d sees at an
+    interior vertex (two children and the parent's sequence)."""
+    rng = np.random.default_rng(seed)
+    bases = np.array([1, 2, 4, 8], np.uint8)
+
+    def mutate(a):
+        r = rng.random(len(a) - 1)
+        out = [16]
+        for x, q in zip(a[1:], r):
+            if q < p / 3:
+                continue
+            if q < 2 * p / 3:
+                out.append(int(rng.choice(bases)))
+            out.append(int(rng.choice(bases)) if q < p else int(x))
+        return np.array(out, np.uint8)
+
+    seqs = []
+    for _ in range(count):
+        a = np.concatenate([[16], rng.choice(bases, size=n)]).astype(np.uint8)
+        seqs += [a, mutate(a), mutate(a)]
+    return seqs
+
+
+def _powell_ref_worker(job):
+    """One process of the CPU arm: the compiled reference's powell_3D_align on its share of the sample."""
+    import ctypes as C
+
+    seqs, costs = job
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libpoyref.so"))
+    u8 = C.POINTER(C.c_uint8)
+    out = []
+    for k in range(0, len(seqs), 3):
+        a, b, c = seqs[k:k + 3]
+        cap = len(a) + len(b) + len(c)
+        rows = [np.zeros(cap, np.uint8) for _ in range(3)]
+        n = C.c_int(0)
+        out.append(lib.camlrt_powell(a.ctypes.data_as(u8), len(a), b.ctypes.data_as(u8), len(b), c.ctypes.data_as(u8), len(c), *costs,
+                                     *[r.ctypes.data_as(u8) for r in rows], C.byref(n)))
+    return out
+
+
+def run_powell_workload(args, rank, local_rank, D, cores):
+    """Powell's three-sequence affine aligner (readjust_3d's aligner), 300 bp triples at 3 % divergence,
+    through poyb200_batch_powell_3 with host buffers in and out (rows + median).  Only a one-shot entry point exists."""
+    from poyd_b200 import cost_matrix as CM, sequence as S
+
+    cm = CM.nucleotides(1, 2, 3)
+    count = args.triples
+    seqs = _powell_triples(count, 300, 0.03, seed=70 + rank)
+    pool = S.SeqPool(seqs)
+    triples = np.arange(3 * count, dtype=np.int32).reshape(-1, 3)
+    al = S.Align3(cm, CM.of_two_dim(cm), device=local_rank)
+    al.align_3_powell_inter(pool, triples[:8])
+    D.barrier()
+    l0 = al.launch_count()
+    t0 = time.perf_counter()
+    g = al.align_3_powell_inter(pool, triples)
+    sec = D.max(time.perf_counter() - t0)
+    n_all = D.sum(float(count))
+    res = {"workload": "8f #3: Powell 3-D affine Ukkonen aligner (powell_3D_align behind readjust_3d), 300 bp DNA triples, 3 % "
+                       "substitutions + indels, costs (1, 3, 2), rows + median", "kernel": "powell_kernel<256,2>",
+           "triples_per_gpu_per_step": count, "value": n_all / sec, "unit": "triples/s", "ms_per_step": sec * 1e3,
+           "gpu_launches": int(al.launch_count() - l0), "mean_cost": float(g.cost.mean()), "errors": int((g.status != 0).sum()),
+           "e2e": {"value": n_all / sec, "unit": "triples/s", "ms_per_step": sec * 1e3, "outputs": "cost, three rows, median (host buffers)"},
+           "cost_checksum": int(g.cost.astype(np.int64).sum())}
+    if not args.skip_cpu and D.world == 1 and os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libpoyref.so")):
+        import multiprocessing as mp
+
+        procs = cores + 1
+        per = 6
+        sample = seqs[: 3 * per * procs]
+        jobs = [(sample[3 * per * k: 3 * per * (k + 1)], (1, 3, 2)) for k in range(procs)]
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(procs) as pl:
+            outs = pl.map(_powell_ref_worker, jobs)
+        dt = time.perf_counter() - t0
+        flat = [c for o in outs for c in o]
+        res["cpu_baseline"] = {"value": len(flat) / dt, "unit": "triples/s", "cores": cores, "processes": procs, "kind": "reference",
+                               "sample": f"first {len(flat)} triples over {procs} processes, {dt:.1f} s",
+                               "same_costs_as_gpu": bool(np.array_equal(np.array(flat), g.cost[: len(flat)]))}
+    al.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -801,6 +886,7 @@ def main():
             blocks[name] = r
             del pool2, pairs2
         blocks["triples300"] = run_cube_workload(args, rank, local_rank, D)
+        blocks["powell300"] = run_powell_workload(args, rank, local_rank, D, cores)
         args.steps, args.warmup = saved
 
     # ---- N > 1: the two multi-GPU paths ----------------------------------------------------------------------------------------

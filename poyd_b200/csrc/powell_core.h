@@ -675,25 +675,40 @@ struct Engine {
         // would have seen after each of them.  Afterwards only "which cost reaches the end first" matters, the values do not
         // depend on the stepping, and the closure is advanced PW_STRIDE costs at a time (a few cells past the final cost get
         // computed that the reference never asks for; nothing reads them).
-        int d = -1;
+        int d = -1, stride = PW_STRIDE;
         for (bool done = false; !done;) {
+            // A strided step asks for a few cells the reference never computes; if that alone pushes the closure onto the
+            // border of the diagonal box, the step is undone and the rest of the pass is stepped level by level.
+            const int d0 = d, dn = d + stride, fr0 = w->fr;
+            if (stride > 1) snapshot_save();
+            top_level(dn, rf, -1, stride);
+            if (w->status == PW_EBOX && stride > 1) {
+                snapshot_restore();
+                if (PW_TID == 0) w->status = PW_OK;
+                PW_SYNC();
+                stride = 1;
+                continue;
+            }
+            if (w->status) return -1;
             if (CPonDist) {
-                // A strided step first.  If furthestReached is still short of |A| / 2 after it, it was short after every top
-                // level inside the step as well.  Otherwise the step is replayed level by level on the values just computed
-                // (relaxation only) to find the level at which the reference places its check-point; the demand state is then
-                // exactly the one of that level, and the cells above it are computed again with the check-point in force.
-                const int d0 = d, dn = d + PW_STRIDE, fr0 = w->fr;
-                snapshot_save();
-                top_level(dn, rf, -1, PW_STRIDE);
-                if (w->status) return -1;
+                // If furthestReached is still short of |A| / 2 after the step, it was short after every top level inside it as
+                // well.  Otherwise the step is replayed level by level on the values just computed (relaxation only) to find
+                // the level at which the reference places its check-point; the demand state is then exactly the one of that
+                // level, and the cells above it are computed again with the check-point in force.
                 bool hit = w->fr >= Alen / 2;  // ... or the end of A is reached inside the step (it can be without any computed
                 for (int c = d0 + 1; c <= dn && !hit; c++)  // cell: identical sequences end on the preset start cell)
                     hit = best(finalab, finalac, c, false) >= Alen;
                 if (!hit) { d = dn; continue; }
+                if (stride == 1) {  // the reference's order per level: compute, place the check-point, test the end
+                    d = dn;
+                    if (w->fr >= Alen / 2) { CPcost = d + 1; CPonDist = false; }
+                    done = best(finalab, finalac, d, false) >= Alen;
+                    continue;
+                }
                 snapshot_restore();
                 if (PW_TID == 0) w->fr = fr0;
                 PW_SYNC();
-                for (d = d0 + 1; d <= dn; d++) {  // the reference's order per level: compute, place the check-point, test the end
+                for (d = d0 + 1; d <= dn; d++) {
                     relax(d, rf, -1, 1);
                     if (w->status) return -1;
                     scan_new();
@@ -705,10 +720,7 @@ struct Engine {
                 if (d > dn) { if (PW_TID == 0) w->status = PW_EWINDOW; PW_SYNC(); return -1; }  // cannot happen
                 PW_TRACE("pass1 replay stopped at d=%d fr=%d CPcost=%d done=%d\n", d, w->fr, CPcost, (int) done);
             } else {
-                const int dn = d + PW_STRIDE;
-                top_level(dn, rf, -1, PW_STRIDE);
-                if (w->status) return -1;
-                for (int c = d + 1; c <= dn && !done; c++)
+                for (int c = d0 + 1; c <= dn && !done; c++)
                     if (best(finalab, finalac, c, false) >= Alen) { d = c; done = true; }
                 if (!done) d = dn;
             }
