@@ -137,6 +137,7 @@ typedef struct poyb200_config {
                                           2 aff_fast_kernel + traceback kernel for pairs without gap bits, the full ring instance
                                           for the others (default: the fastest combination measured, profiles/README.md) */
     int32_t allow_rows;                /* 0: full linear matrices take the diagonal-stripe kernels too (no lin_rows_kernel); default 1 */
+    int32_t small_ring_pairs;          /* use_ring = 2 only: calls of at most this many pairs run as use_ring = 1 (latency); 0 = never */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 

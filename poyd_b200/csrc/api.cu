@@ -96,6 +96,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->trace = 0;
     cfg->dir_budget_bytes = 0;
     cfg->allow_rows = 1;
+    cfg->small_ring_pairs = 0;
 }
 
 extern "C" int poyb200_create_ex(int device, const poyb200_config *user, poyb200_ctx **out) {
@@ -267,7 +268,7 @@ static int *next_counter(poyb200_ctx *ctx) {
     return ctx->d_counters.p + ctx->counter_next++;
 }
 static int reset_counters(poyb200_ctx *ctx) {
-    if (ctx->cfg.use_ring == 2 && ctx->staged && (ctx->mode == MODE_ALIGN_AFF)) {
+    if (ctx->ring_mode == 2 && ctx->staged && (ctx->mode == MODE_ALIGN_AFF)) {
         CK(ctx->d_walked.reserve(ctx->tasks.size() + 16));
         CK(cudaMemsetAsync(ctx->d_walked.p, 0, ctx->tasks.size() + 16, ctx->stream));
     }
@@ -279,12 +280,12 @@ static int reset_counters(poyb200_ctx *ctx) {
 
 // True when the pairs of this class are filled AND walked by the ring kernels (no separate traceback launch).
 static bool ring_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
-    return affine && ctx->cfg.use_ring == 1 && ring_has_shape(klass);
+    return affine && ctx->ring_mode == 1 && ring_has_shape(klass);
 }
 // use_ring = 2: pairs WITHOUT gap bits take aff_fast_kernel + the traceback kernel, the batches it declines take the full
 // ring instance (fill + walk); the traceback kernel skips what the ring instance walked (OutPtrs::walked).
 static bool mixed_class(const poyb200_ctx *ctx, uint32_t klass, bool affine) {
-    return affine && ctx->cfg.use_ring == 2 && ring_has_shape(klass) && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0;
+    return affine && ctx->ring_mode == 2 && ring_has_shape(klass) && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0;
 }
 
 static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, const Task *d_tasks, int n, const OutPtrs &out,
@@ -697,6 +698,10 @@ static int stage_impl(poyb200_ctx *ctx, int mode, const poyb200_batch *b, bool u
     if (mode < 0 || mode > 3) return fail(ctx, POYB200_EINVAL, "bad mode");
     cudaSetDevice(ctx->device);
     ctx->staged = false;
+    // small calls (a dependency level of a tree build): the ring kernels walk each pair from shared memory right after its
+    // fill instead of a second kernel chasing the band through L2 -- lower latency, lower throughput
+    ctx->ring_mode = ctx->cfg.use_ring;
+    if (ctx->cfg.use_ring == 2 && ctx->cfg.small_ring_pairs > 0 && b->n_pairs <= ctx->cfg.small_ring_pairs) ctx->ring_mode = 1;
     int rc = plan(ctx, mode, b);
     if (rc) return rc;
     ctx->mode = mode;
@@ -759,7 +764,7 @@ static int run_chunk(poyb200_ctx *ctx, size_t ci) {
     ctx->cur_dir = bufs[ci % nbuf];
     OutPtrs out{ctx->d_costs.p, ctx->d_out[0].p, ctx->d_out[1].p, ctx->d_out[2].p, ctx->d_out[3].p,
                 ctx->d_outlen.p, ctx->dstride, ctx->hb.want, ctx->d_bits[0].p, ctx->d_bits[1].p, ctx->d_bits[2].p, ctx->bstride,
-                (bt && affine && ctx->cfg.use_ring == 2) ? ctx->d_walked.p : nullptr};
+                (bt && affine && ctx->ring_mode == 2) ? ctx->d_walked.p : nullptr};
     if (two && ci >= (size_t) nbuf) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb[ci - nbuf], 0));  // the buffer is free again
     if (ctx->cfg.timing) CK(cudaEventRecord(ctx->chunk_ev[4 * ci], ctx->stream));
     // one fill launch per kernel class present in the chunk; the classes whose fill kernel does not walk its own pairs

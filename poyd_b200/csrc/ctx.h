@@ -100,6 +100,7 @@ struct poyb200_ctx {
     int state_stride = 0;
     int stripe_seq_bytes = 16;
     poyb200_config cfg{};  // every tunable of the context (include/poyb200.h); fixed at creation
+    int ring_mode = 2;     // cfg.use_ring as it applies to the call being staged (small calls may take the ring kernels)
     // Shard view (poyb200_multi_*, multi.cu): the batch's `pool` pointer is the caller's pool + view_lo and holds only the
     // bytes this shard's pairs reference; seq_off[] stays the caller's array, so view_lo is subtracted per pair and the
     // sequences are validated per pair instead of per pool entry.

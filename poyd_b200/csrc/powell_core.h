@@ -675,10 +675,12 @@ struct Engine {
         // would have seen after each of them.  Afterwards only "which cost reaches the end first" matters, the values do not
         // depend on the stepping, and the closure is advanced PW_STRIDE costs at a time (a few cells past the final cost get
         // computed that the reference never asks for; nothing reads them).
-        int d = -1, stride = PW_STRIDE;
+        int d = -1;
+        bool single = false;
         for (bool done = false; !done;) {
             // A strided step asks for a few cells the reference never computes; if that alone pushes the closure onto the
-            // border of the diagonal box, the step is undone and the rest of the pass is stepped level by level.
+            // border of the diagonal box, the step is undone (only its relaxation has run) and one level is stepped instead.
+            const int stride = single ? 1 : PW_STRIDE;
             const int d0 = d, dn = d + stride, fr0 = w->fr;
             if (stride > 1) snapshot_save();
             top_level(dn, rf, -1, stride);
@@ -686,10 +688,11 @@ struct Engine {
                 snapshot_restore();
                 if (PW_TID == 0) w->status = PW_OK;
                 PW_SYNC();
-                stride = 1;
+                single = true;
                 continue;
             }
             if (w->status) return -1;
+            single = false;
             if (CPonDist) {
                 // If furthestReached is still short of |A| / 2 after the step, it was short after every top level inside it as
                 // well.  Otherwise the step is replayed level by level on the values just computed (relaxation only) to find
