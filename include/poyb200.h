@@ -138,6 +138,8 @@ typedef struct poyb200_config {
                                           for the others (default: the fastest combination measured, profiles/README.md) */
     int32_t allow_rows;                /* 0: full linear matrices take the diagonal-stripe kernels too (no lin_rows_kernel); default 1 */
     int32_t small_ring_pairs;          /* use_ring = 2 only: calls of at most this many pairs run as use_ring = 1 (latency); 0 = never */
+    int32_t dir6;                      /* use_ring = 2, stripe shape (5, 8): direction band of five 6-bit codes per 32-bit word (half the
+                                          bytes of the 8-byte chunks); default 1 */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 

@@ -67,14 +67,17 @@ __device__ __forceinline__ int lds_u8_seq(uint32_t a) {
     return v;
 }
 
-template <int K, int G, bool BT>
+// D6: the K = 5 direction codes of a step go into ONE 32-bit word, 6 bits each -- END_BLOCK, which is set in every cell of a
+// pair without gap bits, is left out and put back by the reader (TF_DIR6) -- so the band is half as large.
+template <int K, int G, bool BT, bool D6 = false>
 struct AffFast {
     // P = ring slots = double steps per unrolled block.  K + 1 columns are live in a step and the next row / column
     // is fetched one step ahead into the slot that just died, so K + 1 slots do.  Instruction-cache footprint decides the
     // speed of this kernel: a block is 6 double steps x 10 cells x ~26 instructions x 16 B = 25 KB for K = 5, and
     // nothing else may be large -- a first version whose boundary phases were unrolled the same way (88 KB per block)
     // ran at half the speed with 57 % "no instruction" stalls (profiles/).
-    static constexpr int Q = 2 * K, P = K + 1, BL = (K <= 4) ? 4 : 8;
+    static_assert(!D6 || K == 5, "6-bit packing is for five codes per word");
+    static constexpr int Q = 2 * K, P = K + 1, BL = (K <= 4 || D6) ? 4 : 8;
 
     int cb[Q], ev[Q], eh[Q];
     int Rv[P], Cv[P];       // 4 * cost[si][gap], 4 * prepend[sj]
@@ -120,7 +123,8 @@ struct AffFast {
         int byte = 0;
         if (BT) {
             const int fk = min(min(neh, nev), fma_add(ncb, one, one));  // ASSIGN_MINIMUM :2251-2280 (one = TAG_CB)
-            const int flags = fma_add((ehl < t) ? AB_ENDB : (AB_ENDB | AB_ENDH), one, (evu < t2) ? 0 : AB_ENDV);
+            constexpr int EB = D6 ? 0 : AB_ENDB;
+            const int flags = fma_add((ehl < t) ? EB : (EB | AB_ENDH), one, (evu < t2) ? 0 : AB_ENDV);
             byte = ((fk * 4 + (ck - ncb)) & 15) | flags;
         }
         cb[q] = ncb; ev[q] = nev; eh[q] = neh;
@@ -129,6 +133,13 @@ struct AffFast {
 
     // K direction bytes -> two words, by multiply-adds (FMA pipe)
     __device__ __forceinline__ void pack(const int (&by)[K], uint32_t (&w)[2]) {
+        if (D6) {
+            int a = by[K - 1];
+#pragma unroll
+            for (int m = K - 2; m >= 0; m--) a = a * 64 + by[m];
+            w[0] = (uint32_t) a;
+            return;
+        }
         constexpr int N0 = K < 4 ? K : 4;
         int a = by[N0 - 1];
 #pragma unroll
@@ -205,7 +216,7 @@ struct AffFast {
 };
 
 // seq_bytes as for aff_stripe_kernel.  slow_list / slow_count receive the batches this kernel declines.
-template <int K, int G, bool BT>
+template <int K, int G, bool BT, bool D6 = false>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     aff_fast_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm, const uint8_t *__restrict__ pool, uint8_t *__restrict__ dir,
                     int *__restrict__ out_cost, int seq_bytes, int nslots, int *work_counter, int *slow_list, int *slow_count, int keep_mask,
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     // keep_mask = ~3 and one = 1 arrive as arguments so that they live in registers (see AffFast::cell, fma_add)
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
-    using S_t = AffFast<K, G, BT>;
+    using S_t = AffFast<K, G, BT, D6>;
     constexpr int BL = S_t::BL, P = S_t::P;
     extern __shared__ __align__(16) uint8_t smem[];
     int2 *s_tabR = reinterpret_cast<int2 *>(smem);
@@ -330,6 +341,16 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
                 if (BT) {
                     const int te = 2 * u + d0, s2 = 2 * u - sbase;  // s2 = te - tshift
                     if (u >= u_first && u <= u_last) {
+                        if (D6) {  // the stripe sweep produced bytes: repack five codes into one word
+                            uint32_t we = 0, wo = 0;
+#pragma unroll
+                            for (int m = 0; m < K; m++) {
+                                we |= ((de[m >> 2] >> (8 * (m & 3))) & 63u) << (6 * m);
+                                wo |= ((dod[m >> 2] >> (8 * (m & 3))) & 63u) << (6 * m);
+                            }
+                            de[0] = we;
+                            dod[0] = wo;
+                        }
                         if (te >= 0) store_dir<BL>(dbase + (((size_t) (s2 >> 3) * G + lane) * 8 + (s2 & 7)) * BL, de);
                         if (te + 1 <= nr + nc) store_dir<BL>(dbase + (((size_t) ((s2 + 1) >> 3) * G + lane) * 8 + ((s2 + 1) & 7)) * BL, dod);
                     }
@@ -375,13 +396,13 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
 }
 
 #ifdef POYB200_DEFINE_AFF_FAST  // the translation unit that owns these kernels (k_aff_fast.cu)
-template <int K, int G>
+template <int K, int G, bool D6 = false>
 static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
                                      int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
                                      cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const int nbatches = (n + GPW - 1) / GPW;
-    auto kern = bt ? aff_fast_kernel<K, G, true> : aff_fast_kernel<K, G, false>;
+    auto kern = bt ? aff_fast_kernel<K, G, true, D6> : aff_fast_kernel<K, G, false, false>;
     size_t smem = 0;
     int nslots = 1, per_sm = 1;
     cudaError_t e = stage_ring_config(kern, FAST_TABLE_BYTES, (size_t) STRIPE_WARPS * GPW * 2 * (seq_bytes + fast_operand_pad(K, G)),
@@ -396,7 +417,9 @@ static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM 
 
 cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
                                       int *cost, int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
-                                      cudaStream_t stream) {
+                                      bool dir6, cudaStream_t stream) {
+    if (dir6 && klass == 1)  // tasks flagged TF_DIR6 by the planner: the (5, 8) shape with the traceback kernel as reader
+        return fast_launch_shape<5, 8, true>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
     switch (klass - 1) {
         case 0: return fast_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
         case 1: return fast_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);

@@ -97,6 +97,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->dir_budget_bytes = 0;
     cfg->allow_rows = 1;
     cfg->small_ring_pairs = 0;
+    cfg->dir6 = 1;
 }
 
 extern "C" int poyb200_create_ex(int device, const poyb200_config *user, poyb200_ctx **out) {
@@ -331,7 +332,8 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
-                                        seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt, ctx->stream);
+                                        seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt,
+                                        bt && klass == 1 && ctx->cfg.dir6 && mixed_class(ctx, klass, affine), ctx->stream);
             ctx->launches++;
             CK(e);
             list = ctx->d_slow_list.p;
@@ -543,6 +545,12 @@ static int plan(poyb200_ctx *ctx, int mode, const poyb200_batch *b) {
             if (bt && (ring_class(ctx, t.klass, affine) || mixed_class(ctx, t.klass, affine)))
                 pt.ring_slot = std::max(pt.ring_slot, ((size_t) dir_bytes(t) + 127) & ~(size_t) 127);
             else pt.maxW = std::max(pt.maxW, W);
+            // default mode, shape (5, 8): aff_fast_kernel writes five 6-bit codes per word for the traceback kernel (the pairs
+            // it declines are walked by the ring kernel from its own scratch slots, sized above with 8-byte chunks)
+            if (bt && t.klass == 1 && mixed_class(ctx, t.klass, affine) && ctx->cfg.dir6) {
+                t.BL = 4;
+                t.flags |= TF_DIR6;
+            }
             pt.maxcap = std::max<long long>(pt.maxcap, (long long) la + lb + 2);
             pt.klass_or |= t.klass;
             pt.klass_and &= t.klass;

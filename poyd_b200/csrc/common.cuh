@@ -35,6 +35,7 @@ constexpr uint32_t TF_ROWS_ARE_B = 1;  // operand b sits on the rows: swap the a
 constexpr uint32_t TF_FULL = 2;        // linear: full matrix (algn_fill_plane), no edge rules
 constexpr uint32_t TF_SWAPED = 4;      // linear traceback tie flag (backtrack_2d `swaped`)
 constexpr uint32_t TF_DIR2 = 8;        // direction band holds 2-bit resolved moves (linear stripe kernels)
+constexpr uint32_t TF_DIR6 = 32;       // affine band of aff_fast_kernel<5, 8, .., true>: five 6-bit codes per 32-bit word (no END_BLOCK bit: always set)
 constexpr uint32_t TF_ROWMAJ = 16;     // direction band in row-major tiles: lane = j / twoK owns twoK columns (lin_rows_kernels.cuh)
 
 struct Task {

@@ -217,9 +217,10 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
     make_tables(tb, mm, go, ge);
     int Wd = 16;
     while (Wd < 4 * tb.maxSingleStep + 2 * go + 8) Wd *= 2;
+    // no alignment costs more than gapping every element once; the cost fields of a cell are 16 bits wide, so a triple whose
+    // cost would pass 32 000 ends with status PW_ECAP (the reference's own INFINITY is 5 000, ukkCommon.h:41)
     const long long lv = 2ll * maxsum * std::max(ge, mm) + 6ll * go + 16;
-    if (lv > 30000) return fail(ctx, POYB200_EINVAL, "costs too large for the 16-bit cost fields of the Powell kernel");
-    const int maxlevels = (int) lv, rescap = maxsum + 1, seqcap = (maxlen + 16) & ~15;
+    const int maxlevels = (int) std::min<long long>(lv, 32000), rescap = maxsum + 1, seqcap = (maxlen + 16) & ~15;
 
     CK(ctx->d_pool.reserve(b->pool_bytes + 64));
     CK(ctx->d_costs.reserve((size_t) n + 1));

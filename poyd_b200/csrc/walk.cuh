@@ -58,9 +58,10 @@ struct BandBytes {
     const uint8_t *dbase;
     uint32_t G, twoK, BL, recip;
     int dbase_d, tshift;
+    bool dir6;  // TF_DIR6: BL = 4, five 6-bit codes per word, END_BLOCK implied
     uint64_t tile_bytes;
     __device__ __forceinline__ BandBytes(const Task &t, const uint8_t *base)
-        : dbase(base), G(t.G), twoK(t.twoK), BL(t.BL), dbase_d(t.dbase), tshift(t.tshift) {
+        : dbase(base), G(t.G), twoK(t.twoK), BL(t.BL), dbase_d(t.dbase), tshift(t.tshift), dir6((t.flags & TF_DIR6) != 0) {
         tile_bytes = (uint64_t) t.G * 8 * t.BL;
         // dd / twoK == (dd * recip) >> 16 for dd < 16384: twoK is 8..16 for the stripe kernels (stripes <= 512 diagonals) and
         // 0xFFFF for the generic ones, where the quotient is 0 for every dd the 16384-element cap allows
@@ -71,6 +72,11 @@ struct BandBytes {
     __device__ __forceinline__ int fetch(int i, int j) const {
         const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
         const uint32_t lane = (dd * recip) >> 16, m = (dd - lane * twoK) >> 1;
+        if (dir6) {
+            const uint64_t widx = ((((uint64_t) (T >> 3) * G + lane) << 3) + (T & 7)) * 4;
+            if (widx >= 2 * tile_bytes) prefetch_l1(dbase + widx - 2 * tile_bytes);
+            return (int) ((__ldg(reinterpret_cast<const uint32_t *>(dbase + widx)) >> (6 * m)) & 63u) | AB_ENDB;
+        }
         const uint64_t idx = ((((uint64_t) (T >> 3) * G + lane) << 3) + (T & 7)) * BL + m;
         // the direction line needed two tiles (8 diagonal moves) further on is requested early, so that the common case --
         // a run of matches along one diagonal -- finds it in L1

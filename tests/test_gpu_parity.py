@@ -398,7 +398,7 @@ def test_maximum_lengths_take_the_generic_kernels(S, checker_factory):
     a = rnd(6000, 0.02)
     b = a.copy()
     b[1:][rng.random(6000) < 0.1] = 4
-    seqs = [a, b, rnd(16383), rnd(2500), rnd(900), rnd(5200, 0.02)]
+    seqs = [a, b, rnd(16383), rnd(2500), rnd(900), rnd(5200, 0.02), rnd(400)]
     pool = S.SeqPool(seqs)
     pairs = np.array([[0, 1], [3, 4], [4, 0], [5, 1]], np.int32)
     aff = CM.nucleotides(1, 2, 3)
@@ -408,7 +408,9 @@ def test_maximum_lengths_take_the_generic_kernels(S, checker_factory):
     al.close()
     lin = CM.default_nucleotides()
     al = S.Align(lin)
-    pairs = np.array([[0, 1], [3, 4], [2, 3], [1, 5]], np.int32)  # [2, 3]: 16384 x 2501, full matrix (l1 >= 1.5 l2)
+    # [2, 3]: 16384 x 2501, full matrix (l1 >= 1.5 l2), too wide for any register kernel; [2, 6]: 16384 x 401, full matrix
+    # in the column-striped kernel at the staging cap
+    pairs = np.array([[0, 1], [3, 4], [2, 3], [1, 5], [2, 6], [6, 2]], np.int32)
     dw = al.deltaw_for(pool, pairs)
     o = checker_factory(lin).batch(1, pool.pool, pool.off, pool.len, pairs, deltaw=dw, nthreads=4)
     assert_aligned_equal(al.align_2(pool, pairs, ALL), o, label="linear long")
@@ -733,6 +735,17 @@ def test_powell_3d_aligner_matches_the_reference(S):
             med = med3[rows[0], rows[1], rows[2]]
             want_med = np.concatenate([[16], med[med != 16]]).astype(np.uint8)
             assert np.array_equal(g.get("median", t), want_med), f"triple {t}: median"
+    # long operands (the sequences no longer fit the shared-memory staging: the kernel reads them from its HBM copy)
+    big = PU.dna(rng, 14000)
+    b2, c2 = big.copy(), big.copy()
+    b2[[700, 5000, 9000]] = [1, 2, 4]
+    c2 = np.delete(c2, [3000, 3001, 12000])
+    lp = S.SeqPool([big, b2, c2])
+    gl = al.align_3_powell(lp, np.array([[0, 1, 2]], np.int32), 1, 3, 2, want=1)
+    rc, rows = PU.ref_powell(ref, big, b2, c2, 1, 3, 2)
+    assert gl.status[0] == 0 and gl.cost[0] == rc
+    for k, name in enumerate(("aligned_1", "aligned_2", "aligned_3")):
+        assert np.array_equal(gl.get(name, 0), rows[k]), f"long triple: {name}"
     # align_3_powell_inter takes its three costs from the 2-D matrix: (1, 3, 2) here
     g2 = al.align_3_powell_inter(pool, triples[:8])
     g1 = al.align_3_powell(pool, triples[:8], 1, 3, 2, want=3)
