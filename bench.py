@@ -42,7 +42,7 @@ UNIT = "GCUPS"
 WORKLOADS = {
     # name: (description, mode, reference ops per cell, dominant kernel)
     "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
-                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_fast_kernel<5,8,true>"),
+                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_fast_kernel<5,8,true,true>"),
     "affine500_medianlike": ("configs[1], median-like operands: as affine500 plus 0.5% IUPAC ambiguities and 10% of positions "
                              "carrying the gap bit (what internal-node medians look like; exercises the block-diagonal "
                              "state)", 3, 50, "aff_ring_kernel<5,8,true,true>"),
