@@ -118,8 +118,11 @@ struct LinStripe {
 };
 
 // Shared memory: LUT (dim rows of dim + 1 ints), gaprow[dim], gapcol[dim], prep4[dim], tail4[dim], sequences.
+#ifndef LIN_STRIPE_MIN_BLOCKS
+#define LIN_STRIPE_MIN_BLOCKS STRIPE_MIN_BLOCKS
+#endif
 template <int K, int G, bool BT>
-__global__ void __launch_bounds__(STRIPE_WARPS * 32, STRIPE_MIN_BLOCKS) lin_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
+__global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_STRIPE_MIN_BLOCKS) lin_stripe_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm,
                                                                           const uint8_t *__restrict__ pool,
                                                                           uint8_t *__restrict__ dir, int *__restrict__ out_cost,
                                                                           int seq_bytes, int nslots, int custom_tail, int *work_counter) {

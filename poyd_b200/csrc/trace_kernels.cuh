@@ -48,61 +48,8 @@ __global__ void __launch_bounds__(128) lin_traceback_kernel(const Task *__restri
     if (base >= ntasks) break;
     const int ti = base + (threadIdx.x & 31);
     if ((int) (threadIdx.x & 31) < wpw && ti < ntasks) {
-    const Task t = tasks[ti];
-    const uint8_t *s1 = pool + t.off_r, *s2 = pool + t.off_c;
-    const uint8_t *dbase = dir + t.dir_off;
-    const int dcap = (int) out.stride, gap = cm.gap;
-    const size_t row = (size_t) t.pair * out.stride;
-    const bool w_clo = out.want & 16;
-    const bool w_med = (out.want & 1) || w_clo, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
-    const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
-    const bool swaped = (t.flags & TF_SWAPED) != 0;
-    RevWriter med, wg, r1, r2;
-    RevBitWriter b1, b2, bw;
-    {
-        const size_t brow = w_bits ? (size_t) t.pair * out.bstride : 0;
-        b1.init((rows_b ? out.bits_b : out.bits_a) + brow, (int) out.bstride * 8);
-        b2.init((rows_b ? out.bits_a : out.bits_b) + brow, (int) out.bstride * 8);
-        bw.init(out.bits_wg + brow, (int) out.bstride * 8);
-    }
-    med.init(out.median + (w_med ? row : 0), dcap);
-    wg.init(out.medianwg + (w_wg ? row : 0), dcap);
-    r1.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
-    r2.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
-    int i = t.lr - 1, j = t.lc - 1, n = 0, nmed = 0;
-    const int second = swaped ? D_INSERT : D_DELETE;
-    // `while (end >= beg)` over the row-major matrix: stops after the ALIGN step out of cell (0, 0)
-    while (i >= 0 && j >= 0) {
-        const int m = dir_fetch(t, dbase, i, j);
-        int mv;
-        if (t.flags & TF_DIR2) {
-            // the stripe kernels resolved the tie already: 0 ALIGN, 1 the preferred gap move, 2 the other one
-            mv = (m == 0) ? D_ALIGN : (m == 1) ? second : (swaped ? D_DELETE : D_INSERT);
-        } else if (m & D_ALIGN) mv = D_ALIGN;
-        else if (m & second) mv = second;
-        else mv = swaped ? D_DELETE : D_INSERT;
-        int x, y;  // elements of s1 / s2 in this column
-        if (mv == D_ALIGN) { x = s1[i]; y = s2[j]; i--; j--; }
-        else if (mv == D_INSERT) { x = gap; y = s2[j]; j--; }
-        else { x = s1[i]; y = gap; i--; }
-        n++;
-        if (w_al) { r1.put(x); r2.put(y); }
-        const int ea = rows_b ? y : x, eb = rows_b ? x : y;  // caller's operand order
-        const int mm = cm_median(cm, ea, eb);
-        if (w_wg) wg.put(mm);
-        if (w_bits) { b1.put(x != gap); b2.put(y != gap); bw.put(mm != gap); }
-        if (w_clo) {
-            const int sel = closest_elem(cm, ea, eb);
-            if (sel != gap) { nmed++; med.put(sel); }
-        } else if (mm != gap) { nmed++; if (w_med) med.put(mm); }
-    }
-    nmed++;
-    if (w_med) { med.put(gap); med.flush(); }
-    if (w_wg) wg.flush();
-    if (w_al) { r1.flush(); r2.flush(); }
-    if (w_bits) { b1.flush(); b2.flush(); bw.flush(); }
-    int *ol = out.out_len + 4 * (size_t) t.pair;
-    ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
+        const Task t = tasks[ti];
+        lin_walk_pair(t, pool, LinBand(t, dir + t.dir_off), cm, out);
     }
     __syncwarp();
   }

@@ -222,4 +222,95 @@ __device__ __forceinline__ void aff_walk_pair(const Task &t, const uint8_t *__re
     ol[0] = w_clo ? nclo : nmed; ol[1] = nwg; ol[2] = nres; ol[3] = nres;
 }
 
+// ---- linear walk ------------------------------------------------------------------------------------------------------
+
+// The direction band of a linear pair in any of its formats (common.cuh dir_index / dir_fetch), with the addressing of
+// the pair resolved once: 32-bit arithmetic, the division by the lane width as a multiply.
+struct LinBand {
+    const uint8_t *dbase;
+    uint32_t G, twoK, BL, magic, flags;
+    int dbase_d, tshift;
+    __device__ __forceinline__ LinBand(const Task &t, const uint8_t *base)
+        : dbase(base), G(t.G), twoK(t.twoK), BL(t.BL), flags(t.flags), dbase_d(t.dbase), tshift(t.tshift) {
+        magic = (uint32_t) ((0x100000000ull + t.twoK - 1) / t.twoK);  // x / twoK == umulhi(x, magic) for x < 2^32 / twoK
+    }
+    // 2-bit resolved move (TF_DIR2: 0 ALIGN, 1 the preferred gap move, 2 the other) or the reference's mask of minima
+    __device__ __forceinline__ int fetch(int i, int j) const {
+        if (flags & TF_ROWMAJ) {
+            const uint32_t lane = __umulhi((uint32_t) j, magic), m = (uint32_t) j - lane * twoK;
+            const uint32_t w = ((((uint32_t) i >> 3) * G + lane) << 3) + ((uint32_t) i & 7);
+            return (int) ((__ldg(reinterpret_cast<const uint32_t *>(dbase) + w) >> (2 * m)) & 3u);
+        }
+        const uint32_t dd = (uint32_t) ((j - i) - dbase_d), T = (uint32_t) (i + j - tshift);
+        const uint32_t lane = __umulhi(dd, magic), m = (dd - lane * twoK) >> 1;
+        const uint32_t chunk = (((T >> 3) * G + lane) << 3) + (T & 7);
+        if (flags & TF_DIR2) return (int) ((__ldg(reinterpret_cast<const uint32_t *>(dbase) + chunk) >> (2 * m)) & 3u);
+        return __ldg(dbase + (size_t) chunk * BL + m);
+    }
+};
+
+// backtrack_2d, linear branch (src/algn.c:3606-3665), fused with algn_ancestor_2 (:4126-4147) and
+// algn_get_median_2d_with_gaps (:4024-4035), one thread per pair.  Every walker runs the same instructions; the move only
+// selects values (the walkers of a warp take different moves).
+__device__ __forceinline__ void lin_walk_pair(const Task &t, const uint8_t *__restrict__ pool, const LinBand band, const DevCM &cm,
+                                              const OutPtrs &out) {
+    const int dcap = (int) out.stride, gap = cm.gap;
+    const size_t row = (size_t) t.pair * out.stride;
+    const bool w_clo = out.want & 16;
+    const bool w_med = (out.want & 1) || w_clo, w_wg = out.want & 2, w_al = out.want & 4, w_bits = out.want & 8;
+    const bool rows_b = (t.flags & TF_ROWS_ARE_B) != 0;
+    const bool swaped = (t.flags & TF_SWAPED) != 0;
+    const bool dir2 = (t.flags & TF_DIR2) != 0;
+    RevWriter med, wg, r1, r2;
+    RevBitWriter b1, b2, bw;
+    {
+        const size_t brow = w_bits ? (size_t) t.pair * out.bstride : 0;
+        b1.init((rows_b ? out.bits_b : out.bits_a) + brow, (int) out.bstride * 8);
+        b2.init((rows_b ? out.bits_a : out.bits_b) + brow, (int) out.bstride * 8);
+        bw.init(out.bits_wg + brow, (int) out.bstride * 8);
+    }
+    med.init(out.median + (w_med ? row : 0), dcap);
+    wg.init(out.medianwg + (w_wg ? row : 0), dcap);
+    r1.init((rows_b ? out.al_b : out.al_a) + (w_al ? row : 0), dcap);
+    r2.init((rows_b ? out.al_a : out.al_b) + (w_al ? row : 0), dcap);
+    int i = t.lr - 1, j = t.lc - 1, n = 0, nmed = 0;
+    SeqBack si, sj;
+    si.init(pool, pool + t.off_r, i);
+    sj.init(pool, pool + t.off_c, j);
+    int ic = si.get(i), jc = sj.get(j);
+    const int second = swaped ? D_INSERT : D_DELETE, third = swaped ? D_DELETE : D_INSERT;
+    // `while (end >= beg)` over the row-major matrix: stops after the ALIGN step out of cell (0, 0)
+    while ((i | j) >= 0) {
+        const int m = band.fetch(i, j);
+        int mv;
+        if (dir2) mv = (m == 0) ? D_ALIGN : (m == 1) ? second : third;  // the stripe kernels resolved the tie already
+        else mv = (m & D_ALIGN) ? D_ALIGN : (m & second) ? second : third;
+        const bool isI = mv == D_INSERT, isD = mv == D_DELETE;
+        const int x = isI ? gap : ic, y = isD ? gap : jc;  // elements of s1 / s2 in this column
+        n++;
+        if (w_al) { r1.put(x); r2.put(y); }
+        const int ea = rows_b ? y : x, eb = rows_b ? x : y;  // caller's operand order
+        const int mm = cm_median(cm, ea, eb);
+        if (w_wg) wg.put(mm);
+        if (w_bits) { b1.put(x != gap); b2.put(y != gap); bw.put(mm != gap); }
+        if (w_clo) {
+            const int sel = closest_elem(cm, ea, eb);
+            if (sel != gap) { nmed++; med.put(sel); }
+        } else if (mm != gap) {
+            nmed++;
+            if (w_med) med.put(mm);
+        }
+        i -= !isI;
+        j -= !isD;
+        if ((i | j) >= 0) { ic = si.get(i); jc = sj.get(j); }
+    }
+    nmed++;
+    if (w_med) { med.put(gap); med.flush(); }
+    if (w_wg) wg.flush();
+    if (w_al) { r1.flush(); r2.flush(); }
+    if (w_bits) { b1.flush(); b2.flush(); bw.flush(); }
+    int *ol = out.out_len + 4 * (size_t) t.pair;
+    ol[0] = nmed; ol[1] = n; ol[2] = n; ol[3] = n;
+}
+
 }  // namespace poyb200

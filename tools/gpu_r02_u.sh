@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round 2, GPU call U: branch-free linear traceback (walk.cuh lin_walk_pair) -- parity and the three linear workloads.
+mkdir -p gpurun_out
+( time timeout 1800 python -m pytest tests -m gpu -x -q ) > gpurun_out/r02u_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r02u_pytest.log
+for wl in linear500 protein300 protein300_band16; do
+  timeout 300 python bench.py --workload $wl --pairs 262144 --skip-cpu --headline-only > gpurun_out/r02u_$wl.json 2> gpurun_out/r02u_tmp.err; echo -n "$wl rc=$? "
+  python -c "
+import json,sys; d=json.load(open(sys.argv[1])); print(round(d['value'],1), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value'],1), round(d['e2e_dos_median']['value'],1), d['phase_ms'])" gpurun_out/r02u_$wl.json
+done
+POYB200_CONFIG="chunk_pairs=1048576" timeout 600 ncu --set full --import-source on --clock-control none -k regex:lin_traceback_kernel -c 1 -o gpurun_out/r02u_lintb python bench.py --workload linear500 --pairs 131072 --steps 1 --warmup 1 --skip-cpu --headline-only > gpurun_out/r02u_ncu.log 2>&1; echo "ncu rc=$?"
