@@ -224,6 +224,11 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     ctx->custom_tail = 0;
     for (size_t a2 = 0; a2 < dim; a2++)
         if (cm->tail_cost[a2] != cm->cost[(a2 << cm->lcm) + cm->gap]) ctx->custom_tail = 1;
+    // default first-row / first-column costs (prepend[b] = cost(gap, b), tail[a] = cost(a, gap)): row 0 and column 0 then
+    // come out of the ordinary recurrence, and the linear kernels skip their boundary phase (bit 1 of the flag they receive)
+    ctx->lin_natural = ctx->custom_tail ? 0 : 1;
+    for (size_t b2 = 0; b2 < dim; b2++)
+        if (cm->prepend_cost[b2] != cm->cost[((size_t) cm->gap << cm->lcm) + b2]) ctx->lin_natural = 0;
     ctx->hcm = *cm;
     ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
     ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
@@ -313,14 +318,14 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
     }
     if (klass >= KLASS_LINROW_BASE) {
         cudaError_t e = lin_rows_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
-                                        seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
+                                        seq_bytes, ctx->custom_tail | (ctx->lin_natural << 1), next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;
     }
     if (klass >= KLASS_LIN_BASE) {
         cudaError_t e = lin_stripe_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p,
-                                          ctx->sm_count, seq_bytes, ctx->custom_tail, next_counter(ctx), ctx->stream);
+                                          ctx->sm_count, seq_bytes, ctx->custom_tail | (ctx->lin_natural << 1), next_counter(ctx), ctx->stream);
         ctx->launches++;
         CK(e);
         return POYB200_OK;

@@ -107,6 +107,7 @@ struct poyb200_ctx {
     bool view = false;
     int64_t view_lo = 0;
     int custom_tail = 0;   // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
+    int lin_natural = 0;   // default prepend and tail costs: the first row and column follow from the ordinary recurrence
     int host_threads = 8;
     size_t chunk_pairs = 1u << 16;  // pairs per chunk (pipelining granularity of the one-shot calls); with three direction
                                     // buffers 65 536 and 131 072 give the same device time, and the smaller chunk lets the

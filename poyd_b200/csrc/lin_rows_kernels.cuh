@@ -86,6 +86,11 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_ROWS_MIN_BLOCKS) lin_ro
             V[c] = LIN_INF;
         }
         int left_prev = LIN_INF;
+        // default prepend / tail costs (bit 1 of custom_tail): row 0 and column 0 are what the ordinary cell computes from
+        // "no neighbour" inputs, given a diagonal seed that makes cell (0, 0) come out as 0 (ALIGN): no boundary variant
+        const bool natural = (custom_tail & 2) != 0;
+        if (natural && lane == 0)
+            left_prev = -*reinterpret_cast<const int *>(lut + s1[0] * lut_row_bytes + colp[0]);
         const int lane_f = nc / C, c_f = nc - lane_f * C;
         int t_end = valid ? nr + lane_f : -1;  // the lanes past column nc need not finish
 #pragma unroll
@@ -141,7 +146,13 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_ROWS_MIN_BLOCKS) lin_ro
             }
         };
         int tt = 0;
-        if (custom_tail) {
+        if (natural) {
+            for (; tt + 1 <= t_end; tt += 2) {
+                step(tt, std::false_type{}, std::false_type{});
+                step(tt + 1, std::false_type{}, std::false_type{});
+            }
+            if (tt <= t_end) step(tt, std::false_type{}, std::false_type{});
+        } else if (custom_tail & 1) {
             for (; tt < G && tt <= t_end; tt++) step(tt, std::true_type{}, std::true_type{});
             for (; tt <= t_end; tt++) step(tt, std::false_type{}, std::true_type{});
         } else {

@@ -92,8 +92,10 @@ struct LinStripe {
         return v;
     }
 
+    // mid_q >= 0: slot mid_q receives mid_val between the two halves (the seed of cell (0, 0) when that cell belongs to the
+    // odd half: placed any earlier it would leak into the cells outside the matrix that the even half computes)
     template <bool BND, bool ENDP>
-    __device__ __forceinline__ void double_step(int i0, int j0, uint32_t &de, uint32_t &dod) {
+    __device__ __forceinline__ void double_step(int i0, int j0, uint32_t &de, uint32_t &dod, int mid_q = -1, int mid_val = 0) {
         int in_l = __shfl_up_sync(0xffffffffu, M[Q - 1], 1, G);
         if (lane == 0) in_l = LIN_INF;
         de = 0;
@@ -104,6 +106,11 @@ struct LinStripe {
             const int v = cell<BND, ENDP>(q, i0 - m, j0 + m, (m == 0) ? in_l : M[q - 1], M[q + 1], M[q], R[m], C[m]);
             M[q] = v & ~3;
             if (BT) de |= (uint32_t) (v & 3) << (2 * m);
+        }
+        if (mid_q >= 0) {
+#pragma unroll
+            for (int q = 1; q < Q; q += 2)
+                if (q == mid_q) M[q] = mid_val;
         }
         int in_u = __shfl_down_sync(0xffffffffu, M[0], 1, G);
         if (lane == G - 1) in_u = LIN_INF;
@@ -205,9 +212,15 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_STRIPE_MIN_BLOCKS) lin_
             int u = u_begin;
             int i0 = u - lane * K, j0 = u + d0 + lane * K;
             S.init_windows(i0, j0);
-            int u_b = max(G * K, 1 - d0);  // from here on every lane has i >= 1 and j >= 1
+            // default prepend / tail costs (bit 1 of custom_tail): row 0 and column 0 are what the ordinary cell computes from
+            // "no neighbour" inputs once cell (0, 0) is seeded through its diagonal input: no boundary phase at all
+            const bool natural = (custom_tail & 2) != 0;
+            const int dd0 = -d0, lane0 = dd0 / Q, q0 = dd0 - lane0 * Q;  // the slot of diagonal 0 (if dd0 >= 0)
+            int seed = 0;
+            if (natural) seed = -*reinterpret_cast<const int *>(S.lut + S.s1[0] * S.lut_row_bytes + S.s2[0] * 4);
+            int u_b = natural ? (int) 0x80000000 : max(G * K, 1 - d0);  // from here on every lane has i >= 1 and j >= 1
             // first double step in which some lane can touch the last column: j0 + K >= nc for the last lane
-            int u_e = custom_tail ? (nc - d0 - G * K) : 0x7fffffff;
+            int u_e = (custom_tail & 1) ? (nc - d0 - G * K) : 0x7fffffff;
 #pragma unroll
             for (int o = G; o < 32; o <<= 1) {
                 u_b = max(u_b, __shfl_xor_sync(0xffffffffu, u_b, o));
@@ -235,6 +248,23 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, LIN_STRIPE_MIN_BLOCKS) lin_
             for (; u <= u_end; u++) {
                 uint32_t de, dod;
                 const bool bnd = u < u_b, endp = u >= u_e;
+                if (natural && __any_sync(0xffffffffu, u == u_first)) {  // (the groups of a warp may start at different steps)
+                    // the double step that holds cell (0, 0): on its even half when d0 is even (seed placed before the step),
+                    // on its odd half otherwise (seed placed between the halves)
+                    const bool mine = u == u_first && dd0 >= 0 && lane == lane0;
+                    if (mine && !(q0 & 1)) {
+#pragma unroll
+                        for (int q = 0; q < Q; q += 2)
+                            if (q == q0) S.M[q] = seed;
+                    }
+                    const int mid_q = (mine && (q0 & 1)) ? q0 : -1;
+                    if (endp) S.template double_step<false, true>(i0, j0, de, dod, mid_q, seed);
+                    else S.template double_step<false, false>(i0, j0, de, dod, mid_q, seed);
+                    emit(de, dod);
+                    i0++; j0++;
+                    S.slide_windows(i0, j0);
+                    continue;
+                }
                 if (bnd && endp) S.template double_step<true, true>(i0, j0, de, dod);
                 else if (bnd) S.template double_step<true, false>(i0, j0, de, dod);
                 else if (endp) S.template double_step<false, true>(i0, j0, de, dod);
