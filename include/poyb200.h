@@ -124,7 +124,7 @@ typedef struct poyb200_config {
     int32_t allow_noeb;                /* 0: no no-gap-bit variant of aff_stripe_kernel either; default 1 */
     int32_t overlap_traceback;         /* 0: traceback on the compute stream, one direction buffer; default 1 */
     int32_t dir_buffers;               /* 2 or 3 direction-band buffers; default 3 */
-    int32_t traceback_threads_per_sm;  /* resident traceback walkers per SM; default 512 */
+    int32_t traceback_threads_per_sm;  /* resident traceback walkers per SM; default 256 */
     int32_t traceback_block;           /* 32, 64 or 128 threads per traceback CTA; default 128 */
     int32_t traceback_priority;        /* 1: the traceback stream outranks the fill stream; default 1 */
     int32_t chunk_pairs;               /* pairs per chunk of a one-shot call (pipelining granularity); default 65536 */

@@ -87,7 +87,7 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->use_ring = 2;
     cfg->overlap_traceback = 1;
     cfg->dir_buffers = 3;
-    cfg->traceback_threads_per_sm = 512;
+    cfg->traceback_threads_per_sm = 256;  // measured with the round-2 kernels: 256 -> 799, 512 -> 768, 128 -> 765, 1024 -> 696 GCUPS (configs[1])
     cfg->traceback_block = 128;
     cfg->traceback_priority = 1;
     cfg->chunk_pairs = 1 << 16;
