@@ -72,3 +72,18 @@ extern "C" int pw_host_align(const unsigned char *s1, int l1, const unsigned cha
     *rlen = w.nres + 1;
     return cost;
 }
+
+// make_tables() laid out like the globals of ukkCommon.c (:46-59), for the test that compares them with setup()'s.
+extern "C" void pw_host_tables(int mm, int go, int ge, int *neighbours, int *contCost, int *secondCost, int *transCost /* 27 x 27 */,
+                               int *numStates, int *maxSingleStep) {
+    Tables tb;
+    make_tables(tb, mm, go, ge);
+    *numStates = NS;
+    *maxSingleStep = tb.maxSingleStep;
+    for (int s = 0; s < NS; s++) {
+        neighbours[s] = tb.da[s] + 2 * tb.db[s] + 4 * tb.dc[s];
+        contCost[s] = tb.cont[s];
+        secondCost[s] = tb.second[s];
+        for (int t = 0; t < NS; t++) transCost[s * 27 + t] = tb.trans[s][t];
+    }
+}

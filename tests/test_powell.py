@@ -47,10 +47,25 @@ def host_powell(host, a, b, c, mm, go, ge):
         return cost, [r[: n.value] for r in rows], st.value
 
 
-def test_tables_match_setup():
-    """ukkCommon.c setup(): 16 states, MMM first, the largest single step for (1, 3, 2) is MDD entered with two openings."""
-    # (exercised through the alignments below; here only the invariants a reader can check by hand)
-    assert len(PU.COSTS) == 5
+def test_tables_match_setup(host, ref):
+    """make_tables() against the globals the reference's own setup() leaves behind (src/ukkCommon.c:46-59, 247-350): the 16
+    states in its order, their neighbour steps, continuation / second costs, the transition matrix, maxSingleStep."""
+    a = np.array([16, 1, 2, 4], np.uint8)
+    for mm, go, ge in PU.COSTS:
+        PU.ref_powell(ref, a, a, a, mm, go, ge)  # runs setup() for these costs
+        I27 = C.c_int * 27
+        got = {k: I27() for k in ("neighbours", "contCost", "secondCost")}
+        trans = (C.c_int * (27 * 27))()
+        ns, mss = C.c_int(0), C.c_int(0)
+        host.pw_host_tables(mm, go, ge, got["neighbours"], got["contCost"], got["secondCost"], trans, C.byref(ns), C.byref(mss))
+        assert ns.value == C.c_int.in_dll(ref, "numStates").value == 16
+        assert mss.value == C.c_int.in_dll(ref, "maxSingleStep").value, (mm, go, ge)
+        for k, arr in got.items():
+            want = I27.in_dll(ref, k)
+            assert list(arr)[:16] == list(want)[:16], (k, (mm, go, ge))
+        want_t = (C.c_int * (27 * 27)).in_dll(ref, "transCost")
+        for s1 in range(16):
+            assert list(trans)[s1 * 27: s1 * 27 + 16] == list(want_t)[s1 * 27: s1 * 27 + 16], (s1, (mm, go, ge))
 
 
 def test_restatement_matches_the_reference(host, ref):
