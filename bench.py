@@ -710,7 +710,7 @@ def run_powell_workload(args, rank, local_rank, D, cores):
     pool = S.SeqPool(seqs)
     triples = np.arange(3 * count, dtype=np.int32).reshape(-1, 3)
     al = S.Align3(cm, CM.of_two_dim(cm), device=local_rank)
-    al.align_3_powell_inter(pool, triples[:8])
+    al.align_3_powell_inter(pool, triples)  # warm-up at full size: the workspaces stay with the context
     D.barrier()
     l0 = al.launch_count()
     t0 = time.perf_counter()

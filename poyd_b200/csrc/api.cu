@@ -168,6 +168,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     ctx->tasks.release();
     ctx->tasks_tmp.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
+    ctx->d_pw_arena.release(); ctx->d_pw_seq.release();
     for (auto &b : ctx->d_out) b.release();
     for (auto &b : ctx->d_bits) b.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);

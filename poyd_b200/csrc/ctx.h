@@ -128,6 +128,7 @@ struct poyb200_ctx {
     DevBuf<int> d_cost3, d_ring, d_status;
     DevBuf<uint8_t> d_median3;
     DevBuf<Task3> d_tasks3;
+    DevBuf<uint8_t> d_pw_arena, d_pw_seq;  // Powell kernel: per-CTA workspaces, kept between calls (powell.cu)
     // stats
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

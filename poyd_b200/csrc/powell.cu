@@ -264,14 +264,11 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
         const int ctas = many ? PW_CTAS_MANY : PW_CTAS_FEW;
         int grid = (int) std::min<size_t>(std::min<size_t>(round_jobs.size(), (size_t) ctx->sm_count * ctas), std::max<size_t>(1, budget / per_cta));
         if (per_cta > budget) return fail(ctx, POYB200_ENOMEM, "Powell kernel: one workspace exceeds the memory budget");
-        uint8_t *arena = nullptr, *seqbuf = nullptr;
-        Work *d_works = nullptr;
-        CK(cudaMalloc(&arena, lay.total * (size_t) grid));
-        guard.p.push_back(arena);
-        CK(cudaMalloc(&seqbuf, 3 * (size_t) seqcap * grid));
-        guard.p.push_back(seqbuf);
-        CK(cudaMalloc(&d_works, sizeof(Work) * (size_t) grid));
-        guard.p.push_back(d_works);
+        // the workspaces stay with the context between calls (allocating tens of GB costs more than aligning the triples)
+        CK(ctx->d_pw_arena.reserve(lay.total * (size_t) grid));
+        CK(ctx->d_pw_seq.reserve(3 * (size_t) seqcap * grid + sizeof(Work) * (size_t) grid + 256));
+        uint8_t *arena = ctx->d_pw_arena.p, *seqbuf = ctx->d_pw_seq.p;
+        Work *d_works = reinterpret_cast<Work *>(ctx->d_pw_seq.p + ((3 * (size_t) seqcap * grid + 255) & ~(size_t) 255));
         std::vector<Work> hw((size_t) grid);
         for (int g = 0; g < grid; g++) {
             Work &w = hw[g];
@@ -322,6 +319,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
             CK(cudaMemcpy2DAsync(dst[k] + (b->out_stride - wbytes), (size_t) b->out_stride, ctx->d_out[k].p + (dstride - wbytes), (size_t) dstride,
                                  wbytes, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_pw_arena.cap > ((size_t) 32 << 30)) ctx->d_pw_arena.release();  // an unusually large box: do not sit on it
     ctx->staged = false;
     return POYB200_OK;
 }
