@@ -319,7 +319,7 @@ extern "C" int poyb200_batch_powell_3(poyb200_ctx *ctx, const poyb200_batch3 *b,
             CK(cudaMemcpy2DAsync(dst[k] + (b->out_stride - wbytes), (size_t) b->out_stride, ctx->d_out[k].p + (dstride - wbytes), (size_t) dstride,
                                  wbytes, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_pw_arena.cap > ((size_t) 32 << 30)) ctx->d_pw_arena.release();  // an unusually large box: do not sit on it
+    if (ctx->d_pw_arena.cap > ((size_t) 48 << 30)) ctx->d_pw_arena.release();  // an unusually large box: do not sit on it
     ctx->staged = false;
     return POYB200_OK;
 }
