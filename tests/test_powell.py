@@ -89,6 +89,8 @@ def test_restatement_on_longer_and_unequal_triples(host, ref):
     cases.append((a, a[:40].copy(), PU.mutate(rng, a, 0.05)))     # very different lengths: the final diagonal is far out
     cases.append((a, a.copy(), a.copy()))                          # identical: cost 0, one run of matches
     cases.append((PU.dna(rng, 1), PU.dna(rng, 1), PU.dna(rng, 1)))
+    e, s4 = np.array([16], np.uint8), np.array([16, 1, 2, 4], np.uint8)  # empty operands (readjust_3d never passes them; same anyway)
+    cases += [(e, s4, s4), (s4, e, s4), (s4, s4, e), (e, e, e), (e, e, s4)]
     for k, (a, b, c) in enumerate(cases):
         mm, go, ge = PU.COSTS[k % len(PU.COSTS)]
         rc, rr = PU.ref_powell(ref, a, b, c, mm, go, ge)
