@@ -93,6 +93,52 @@ class DOS:
         return out, cost, worst
 
 
+def select_one(seq: np.ndarray, cm) -> np.ndarray:
+    """``Sequence.select_one`` (src/sequence.ml:1149-1156): for combination alphabets every element collapses to its lowest
+    bit; other alphabets are returned unchanged."""
+    if not cm.combine():
+        return seq
+    v = seq.astype(np.int32)
+    return (v & -v).astype(np.uint8)
+
+
+def readjust_3d(dos: "DOS", al3: "S.Align3", pool: S.SeqPool, ch1, ch2, parent, mine):
+    """``SeqCS.DOS.readjust (`ThreeD _) h ch1 ch2 parent mine`` (src/seqCS.ml:680-727) for every vertex k, batched: the vertices
+    with three non-empty neighbours go through ``Sequence.Align.readjust_3d`` (Powell's aligner, one GPU batch), the ones
+    with an empty neighbour through the pairwise median of the other two (one batch per pairing), the rest are copies.
+    Returns (changed[n], list of sequences, cost[n])."""
+    ch1, ch2, parent, mine = (np.asarray(x, np.int32) for x in (ch1, ch2, parent, mine))
+    n = len(mine)
+    e1 = np.array([dos._empty(pool, i) for i in ch1])
+    e2 = np.array([dos._empty(pool, i) for i in ch2])
+    ep = np.array([dos._empty(pool, i) for i in parent])
+    res = [None] * n
+    cost = np.zeros(n, np.int64)
+    full = np.nonzero(~e1 & ~e2 & ~ep)[0]
+    if len(full):
+        c, seqs, _ = al3.readjust_3d(pool, np.stack([ch1[full], ch2[full], mine[full], parent[full]], axis=1))
+        for q, k in enumerate(full):
+            res[k], cost[k] = seqs[q], c[q]
+    for k in range(n):  # | true, true, _ -> ch1 | true, _, true -> ch1 | _, true, true -> ch2
+        if e1[k] and (e2[k] or ep[k]):
+            res[k] = pool.seq(int(ch1[k])).copy()
+        elif e2[k] and ep[k]:
+            res[k] = pool.seq(int(ch2[k])).copy()
+    # one empty neighbour: `algn` of the other two (the affine median, or align_2 + median_2), then select_one
+    for mask, x, y in ((~e1 & ~e2 & ep, ch1, ch2), (~e1 & e2 & ~ep, ch1, parent), (e1 & ~e2 & ~ep, ch2, parent)):
+        idx = np.nonzero(mask)[0]
+        if not len(idx):
+            continue
+        pairs = np.stack([x[idx], y[idx]], axis=1)
+        rows, lens = al3.full_median_2(pool, pairs)
+        c = al3.cost_2(pool, pairs)
+        for q, k in enumerate(idx):
+            res[k] = select_one(rows[q, rows.shape[1] - int(lens[q]):].copy(), al3.cm)
+            cost[k] = int(c[q])
+    changed = np.array([not np.array_equal(res[k], pool.seq(int(mine[k]))) for k in range(n)], bool)
+    return changed, res, cost
+
+
 class Union:
     def __init__(self, al: S.Align):
         self.dos = DOS(al)

@@ -480,6 +480,27 @@ class Aligned3:
         return buf[t, buf.shape[1] - n:]
 
 
+def readjust_3d_classify(pool: "SeqPool", quads, gap: int) -> np.ndarray:
+    """The branch ``Sequence.Align.readjust_3d`` takes for every row (s1, s2, m, p) (src/sequence.ml:1117-1129): 0 keep m
+    (all four lengths say nothing can change), 1 return s2 (s1 empty), 2 return s1 (s2 empty), 3 return p (p empty),
+    4 align (s1, s2, p).  `is_empty` = every element is the gap (src/sequence.ml:442-449)."""
+    quads = np.asarray(quads, np.int32).reshape(-1, 4)
+    out = np.full(len(quads), 4, np.int8)
+    for k, (s1, s2, m, p) in enumerate(quads):
+        l1, l2, lm, lp = (int(pool.len[i]) for i in (s1, s2, m, p))
+        if l1 == l2 and lm == lp and l1 == lm:
+            out[k] = 0
+            continue
+        e1, e2, ep = (bool(np.all(pool.seq(int(i)) == gap)) for i in (s1, s2, p))
+        if e1 and not e2:
+            out[k] = 1
+        elif e2 and not e1:
+            out[k] = 2
+        elif ep:
+            out[k] = 3
+    return out
+
+
 class Align3(Align):
     """``Sequence.Align.align_3`` / ``cost_3`` / ``median_3`` (src/sequence.ml:727-762, 871-893, 934-947) over a batch
     of triples, with the reference's cube semantics as executed."""
@@ -548,6 +569,36 @@ class Align3(Align):
         res.lens = np.ascontiguousarray(lens2[:, 0])
         res.median_lens = np.ascontiguousarray(lens2[:, 1])
         return res
+
+    def readjust_3d(self, pool: SeqPool, quads, first_gap: bool = True):
+        """``Sequence.Align.readjust_3d ?first_gap s1 s2 m cm cm3 p`` (src/sequence.ml:1116-1139) for every row
+        (s1, s2, m, p) of `quads`: the early exits on the host, everything else as ONE batch of Powell alignments of
+        (s1, s2, p).  Returns (cost[n], list of the n new sequences, changed[n])."""
+        quads = np.ascontiguousarray(quads, dtype=np.int32).reshape(-1, 4)
+        n = len(quads)
+        what = readjust_3d_classify(pool, quads, self.cm.gap)
+        cost = np.zeros(n, np.int64)
+        res: List[Optional[np.ndarray]] = [None] * n
+        for k in np.nonzero(what != 4)[0]:
+            res[k] = pool.seq(int(quads[k, (2, 1, 0, 3)[what[k]]])).copy()  # 0: m, 1: s2, 2: s1, 3: p
+        todo = np.nonzero(what == 4)[0]
+        if len(todo):
+            tri = quads[todo][:, (0, 1, 3)]
+            work = pool
+            if not first_gap:  # prepend_char s gap on all three, del_first_char on the result (:1132-1138)
+                used = np.unique(tri)
+                seqs = [np.concatenate([[self.cm.gap], pool.seq(int(i))]).astype(np.uint8) for i in used]
+                work = SeqPool(seqs)
+                tri = np.searchsorted(used, tri).astype(np.int32)
+            g = self.align_3_powell_inter(work, tri, want=2)
+            if g.status.any():
+                raise PoyB200Error(f"powell_3D_align: status {g.status[g.status != 0][:4]} (5 = an element without a base)")
+            for q, k in enumerate(todo):
+                m = g.get("median", q).copy()
+                res[k] = m if first_gap else m[1:]
+                cost[k] = int(g.cost[q])
+        changed = np.array([not np.array_equal(res[k], pool.seq(int(quads[k, 2]))) for k in range(n)], bool)
+        return cost, res, changed
 
     def align_3_powell_inter(self, pool: SeqPool, triples, want: int = 3) -> Aligned3:
         """``Sequence.Align.align_3_powell_inter`` (src/sequence.ml:1089-1114): mismatch, gap opening and gap extension

@@ -746,6 +746,43 @@ def test_powell_3d_aligner_matches_the_reference(S):
     assert gl.status[0] == 0 and gl.cost[0] == rc
     for k, name in enumerate(("aligned_1", "aligned_2", "aligned_3")):
         assert np.array_equal(gl.get(name, 0), rows[k]), f"long triple: {name}"
+    # Sequence.Align.readjust_3d (src/sequence.ml:1116-1139) and SeqCS.DOS.readjust in `ThreeD mode (src/seqCS.ml:680-727):
+    # copies for the trivial rows, Powell + the 3-D median for the others, both values of first_gap
+    from poyd_b200 import seqcs
+
+    e = np.array([16], np.uint8)
+    x, y, z = cases[0]
+    rp = S.SeqPool([e, x, y, z, x.copy()])
+    quads = np.array([[1, 4, 1, 4], [0, 2, 3, 1], [1, 0, 3, 2], [1, 2, 3, 0], [1, 2, 1, 3], [2, 3, 1, 1]], np.int32)
+    what = S.readjust_3d_classify(rp, quads, 16)
+    assert list(what[:4]) == [0, 1, 2, 3]
+    for fg in (True, False):
+        rcost, rseq, rch = al.readjust_3d(rp, quads, first_gap=fg)
+        assert list(rcost[:4]) == [0, 0, 0, 0]
+        assert np.array_equal(rseq[0], x) and np.array_equal(rseq[1], y) and np.array_equal(rseq[2], x) and np.array_equal(rseq[3], e)
+        assert list(rch[:4]) == [False, not np.array_equal(z, y), not np.array_equal(z, x), not np.array_equal(z, e)]
+        for k in (4, 5):
+            if what[k] != 4:  # (all four lengths equal by chance)
+                continue
+            s1, s2, mm_, pp = (rp.seq(int(i)) for i in quads[k])
+            ops = [s1, s2, pp] if fg else [np.concatenate([[16], v]).astype(np.uint8) for v in (s1, s2, pp)]
+            rc, rows = PU.ref_powell(ref, *ops, 1, 3, 2)
+            med = med3[rows[0], rows[1], rows[2]]
+            want = np.concatenate([[16], med[med != 16]]).astype(np.uint8)
+            if not fg:
+                want = want[1:]
+            assert rcost[k] == rc and np.array_equal(rseq[k], want), (fg, k)
+            assert rch[k] == (not np.array_equal(want, mm_))
+    dos = seqcs.DOS(al)
+    ch, seqs, cst = seqcs.readjust_3d(dos, al, rp, [1, 0, 1, 0], [2, 2, 0, 0], [3, 3, 3, 3], [1, 1, 1, 1])
+    rc, rows = PU.ref_powell(ref, x, y, z, 1, 3, 2)
+    med = med3[rows[0], rows[1], rows[2]]
+    if what[4] == 4:
+        assert cst[0] == rc and np.array_equal(seqs[0], np.concatenate([[16], med[med != 16]]).astype(np.uint8))
+    pm = al.align_affine_3(rp, np.array([[2, 3], [1, 3]], np.int32), 1)  # one empty child: the pairwise median with the parent
+    assert cst[1] == pm.cost[0] and np.array_equal(seqs[1], seqcs.select_one(pm.get("median", 0), cm))
+    assert cst[2] == pm.cost[1] and np.array_equal(seqs[2], seqcs.select_one(pm.get("median", 1), cm))
+    assert cst[3] == 0 and np.array_equal(seqs[3], e) and ch[3]  # both children empty: ch1
     # align_3_powell_inter takes its three costs from the 2-D matrix: (1, 3, 2) here
     g2 = al.align_3_powell_inter(pool, triples[:8])
     g1 = al.align_3_powell(pool, triples[:8], 1, 3, 2, want=3)

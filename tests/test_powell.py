@@ -105,3 +105,21 @@ def test_element_without_a_base_is_an_error(host):
     b = np.array([16, 1, 2, 4], np.uint8)
     _, _, st = host_powell(host, a, b, b, 1, 3, 2)
     assert st == 5
+
+
+def test_readjust_3d_branches():
+    """The host part of Sequence.Align.readjust_3d (src/sequence.ml:1117-1129): which rows return a copy and which align."""
+    from poyd_b200 import sequence as S
+
+    e = np.array([16], np.uint8)
+    a, b, c = np.array([16, 1, 2, 4], np.uint8), np.array([16, 1, 2], np.uint8), np.array([16, 1, 2, 4, 8], np.uint8)
+    gg = np.array([16, 16], np.uint8)  # two gaps: empty as well (is_empty looks at every element)
+    pool = S.SeqPool([e, a, b, c, a.copy(), gg])
+    quads = np.array([[1, 4, 1, 4],   # four equal lengths: keep m
+                      [0, 1, 2, 3],   # s1 empty: s2
+                      [1, 5, 2, 3],   # s2 empty: s1
+                      [1, 2, 3, 0],   # p empty: p
+                      [1, 2, 3, 3],   # nothing empty, lengths differ: align
+                      [0, 5, 2, 3]],  # s1 and s2 both empty, p not: the reference falls through to the aligner
+                     np.int32)
+    assert list(S.readjust_3d_classify(pool, quads, 16)) == [0, 1, 2, 3, 4, 4]
