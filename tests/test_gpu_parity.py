@@ -756,23 +756,26 @@ def test_powell_3d_aligner_matches_the_reference(S):
     quads = np.array([[1, 4, 1, 4], [0, 2, 3, 1], [1, 0, 3, 2], [1, 2, 3, 0], [1, 2, 1, 3], [2, 3, 1, 1]], np.int32)
     what = S.readjust_3d_classify(rp, quads, 16)
     assert list(what[:4]) == [0, 1, 2, 3]
-    for fg in (True, False):
-        rcost, rseq, rch = al.readjust_3d(rp, quads, first_gap=fg)
-        assert list(rcost[:4]) == [0, 0, 0, 0]
-        assert np.array_equal(rseq[0], x) and np.array_equal(rseq[1], y) and np.array_equal(rseq[2], x) and np.array_equal(rseq[3], e)
-        assert list(rch[:4]) == [False, not np.array_equal(z, y), not np.array_equal(z, x), not np.array_equal(z, e)]
-        for k in (4, 5):
-            if what[k] != 4:  # (all four lengths equal by chance)
-                continue
-            s1, s2, mm_, pp = (rp.seq(int(i)) for i in quads[k])
-            ops = [s1, s2, pp] if fg else [np.concatenate([[16], v]).astype(np.uint8) for v in (s1, s2, pp)]
-            rc, rows = PU.ref_powell(ref, *ops, 1, 3, 2)
-            med = med3[rows[0], rows[1], rows[2]]
-            want = np.concatenate([[16], med[med != 16]]).astype(np.uint8)
-            if not fg:
-                want = want[1:]
-            assert rcost[k] == rc and np.array_equal(rseq[k], want), (fg, k)
-            assert rch[k] == (not np.array_equal(want, mm_))
+    rcost, rseq, rch = al.readjust_3d(rp, quads)
+    assert list(rcost[:4]) == [0, 0, 0, 0]
+    assert np.array_equal(rseq[0], x) and np.array_equal(rseq[1], y) and np.array_equal(rseq[2], x) and np.array_equal(rseq[3], e)
+    assert list(rch[:4]) == [False, not np.array_equal(z, y), not np.array_equal(z, x), not np.array_equal(z, e)]
+    for k in (4, 5):
+        if what[k] != 4:  # (all four lengths equal by chance)
+            continue
+        s1, s2, mm_, pp = (rp.seq(int(i)) for i in quads[k])
+        rc, rows = PU.ref_powell(ref, s1, s2, pp, 1, 3, 2)
+        med = med3[rows[0], rows[1], rows[2]]
+        want = np.concatenate([[16], med[med != 16]]).astype(np.uint8)
+        assert rcost[k] == rc and np.array_equal(rseq[k], want), k
+        assert rch[k] == (not np.array_equal(want, mm_))
+    # first_gap = false is for sequences stored WITHOUT the leading gap: it is prepended for the aligner and dropped from
+    # the result (src/sequence.ml:1132-1138); a second gap in front of a stored one is an element without a base
+    bare = S.SeqPool([x[1:].copy(), y[1:].copy(), z[1:].copy(), x[2:].copy()])
+    c0, s0, _ = al.readjust_3d(bare, np.array([[0, 1, 3, 2]], np.int32), first_gap=False)
+    rc, rows = PU.ref_powell(ref, x, y, z, 1, 3, 2)
+    med = med3[rows[0], rows[1], rows[2]]
+    assert c0[0] == rc and np.array_equal(s0[0], med[med != 16].astype(np.uint8))
     dos = seqcs.DOS(al)
     ch, seqs, cst = seqcs.readjust_3d(dos, al, rp, [1, 0, 1, 0], [2, 2, 0, 0], [3, 3, 3, 3], [1, 1, 1, 1])
     rc, rows = PU.ref_powell(ref, x, y, z, 1, 3, 2)
