@@ -140,6 +140,9 @@ typedef struct poyb200_config {
     int32_t small_ring_pairs;          /* use_ring = 2 only: calls of at most this many pairs run as use_ring = 1 (latency); 0 = never */
     int32_t dir6;                      /* use_ring = 2, stripe shape (5, 8): direction band of five 6-bit codes per 32-bit word (half the
                                           bytes of the 8-byte chunks); default 1 */
+    int32_t pair2;                     /* dir6 pairs without gap bits whose costs fit 16 bits: aff_x2_kernel, two pairs per lane group
+                                          (DPX 16x2 instructions), before aff_fast_kernel; default 1 */
+    int32_t pair2_min_pairs;           /* pair2 only for launches of at least this many pairs; default 0 */
 } poyb200_config;
 void poyb200_default_config(poyb200_config *cfg);
 

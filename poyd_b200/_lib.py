@@ -33,7 +33,8 @@ class Config(C.Structure):
     _fields_ = [("struct_bytes", C.c_uint32)] + [(n, C.c_int32) for n in (
         "force_generic", "allow_fast", "allow_noeb", "overlap_traceback", "dir_buffers", "traceback_threads_per_sm",
         "traceback_block", "traceback_priority", "chunk_pairs", "host_threads", "timing", "trace")] + [
-        ("dir_budget_bytes", C.c_int64), ("use_ring", C.c_int32), ("allow_rows", C.c_int32), ("small_ring_pairs", C.c_int32), ("dir6", C.c_int32)]
+        ("dir_budget_bytes", C.c_int64), ("use_ring", C.c_int32), ("allow_rows", C.c_int32), ("small_ring_pairs", C.c_int32), ("dir6", C.c_int32),
+        ("pair2", C.c_int32), ("pair2_min_pairs", C.c_int32)]
 
 
 def make_config(overrides=None) -> "Config":

@@ -60,6 +60,20 @@ __device__ __forceinline__ int fma_add(int a, int one, int b) {
     return v;
 #endif
 }
+// x += bits when a == b: a compare and ONE predicated add (the bits are clear in x, so the add is an OR that may go to
+// either pipe) instead of compare + select + combine
+template <int BITS>
+__device__ __forceinline__ void add_if_eq(int &x, int a, int b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(x) : "r"(a), "r"(b), "n"(BITS));
+}
+// min(a + b, c) in one instruction (VIADDMNMX)
+__device__ __forceinline__ int add_min(int a, int b, int c) { return __viaddmin_s32(a, b, c); }
+// FAST_CELL_V2 = 1: an A/B build of the cell with fewer instructions (20 instead of 24 per cell) but 14 of them on the
+// INT32 ALU pipe against 11.7 -- both pipes issue one warp instruction every two cycles, so the busier pipe decides and the
+// default stays 0 (see AffFast::cell)
+#ifndef FAST_CELL_V2
+#define FAST_CELL_V2 0
+#endif
 // staged operands change from pair to pair: volatile, so the load is neither hoisted nor merged across pairs
 __device__ __forceinline__ int lds_u8_seq(uint32_t a) {
     int v;
@@ -86,9 +100,15 @@ struct AffFast {
     int nr, nc, lane, keep;
     int one;       // 1, opaque (fma_add)
     int c_h, c_v;  // go4 (CB tag 0 -> EH tag 0), go4 + 2 (-> EV tag 2): registers, so the adds stay two-input
+    int c_d, c_o;  // FAST_CELL_V2: 3 - go4 (state -> tag A 3 candidate), go4 - 1 (tag-1 close-block value -> state)
     // per pair
     int u_last, lane_f;
     int *scr;  // shared, Q ints per group
+
+    // the close-block state of a cell that does not exist (left edge :2487-2494, diagonal dhi + 1 :2531-2535)
+    __device__ __forceinline__ int cb_high() const { return FAST_CELL_V2 ? HIGH4 + c_h : HIGH4; }
+    // 4 * CB with tag 0 out of the state
+    __device__ __forceinline__ int cb_plain(int q) const { return FAST_CELL_V2 ? cb[q] - c_h : cb[q]; }
 
     // Rows / columns past the end of an operand (a pair that finished while others of the warp still run, or the last
     // lanes of a stripe that overhangs the matrix) read the last code again: such cells are never used.
@@ -111,9 +131,34 @@ struct AffFast {
         for (int n = 0; n <= K; n++) load_col(n % P, j0 + n);
     }
 
-    // The close-block state is kept with tag 0 here (cb[] = 4 * CB): its consumers add their tag with the constant they
-    // add anyway, and the choice bits of the close-block minimum come out as a subtraction.
+    // The close-block state.
+    //   FAST_CELL_V2: cb[] = 4 * CB + 4 * gap_open, tag 0 -- the value BOTH gap openings start from -- so
+    //     * an extension state is one add and one fused add-min: min(ehl, cb_l + go) + Cv = min(ehl + Cv, (cb_l + go) + Cv);
+    //     * "the opening won" (END_HORIZONTAL / END_VERTICAL, ties included: `ehl < t` is false) is `new state == opening
+    //       candidate`, one compare whose predicate guards one add into the direction code -- no select, no combine;
+    //     * the tag-1 close-block value of ASSIGN_MINIMUM is (ck & ~3) | 1, one LOP3, and the next state one add from it.
+    //   otherwise (round 1 / round 2a cell, kept for A/B builds): cb[] = 4 * CB with tag 0, its consumers add their tag with
+    //   the constant they add anyway, and the choice bits of the close-block minimum come out as a subtraction.
     __device__ __forceinline__ int cell(int ehl, int cbl, int evu, int cbu, int q, int rs, int cs) {
+#if FAST_CELL_V2
+        const int xo = cbl + Cv[cs];                    // open horizontally: tag 0
+        const int neh = add_min(ehl, Cv[cs], xo);       // FILL_EXTEND_HORIZONTAL :1765-1787
+        const int yo = cbu + Rv[rs] + TAG_EV;           // open vertically: tag 2
+        const int nev = add_min(evu, Rv[rs], yo);       // FILL_EXTEND_VERTICAL :1813-1830
+        const int d = lds_s32(Rl[rs] + Cl[cs]);         // 4 * cost[si & 15][sj & 15]
+        const int ck = min(min(cb[q] + c_d, ev[q]), eh[q]) + d;  // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977 (tags A 3, V 2, H 0)
+        const int ncb1 = (ck & keep) | TAG_CB;
+        int byte = 0;
+        if (BT) {
+            const int fk = min(min(neh, nev), ncb1);    // ASSIGN_MINIMUM :2251-2280
+            constexpr int EB = D6 ? 0 : AB_ENDB;
+            byte = ((fk * 4 + (ck & 3)) & 15) | EB;
+            add_if_eq<AB_ENDH>(byte, neh, xo);
+            add_if_eq<AB_ENDV>(byte, nev, yo);
+        }
+        cb[q] = ncb1 + c_o; ev[q] = nev; eh[q] = neh;
+        return byte;
+#else
         const int t = cbl + c_h, t2 = cbu + c_v;
         const int neh = min(ehl, t) + Cv[cs];     // FILL_EXTEND_HORIZONTAL :1765-1787
         const int nev = min(evu, t2) + Rv[rs];    // FILL_EXTEND_VERTICAL :1813-1830
@@ -129,6 +174,7 @@ struct AffFast {
         }
         cb[q] = ncb; ev[q] = nev; eh[q] = neh;
         return byte;
+#endif
     }
 
     // K direction bytes -> two words, by multiply-adds (FMA pipe)
@@ -163,7 +209,7 @@ struct AffFast {
             // ---- even step: q = 2m, cell (i0 + p - m, j0 + p + m)
             int in_eh = __shfl_up_sync(0xffffffffu, eh[Q - 1], 1, G);
             int in_cb = __shfl_up_sync(0xffffffffu, cb[Q - 1], 1, G);
-            if (lane == 0) { in_eh = HIGH4 + TAG_EH; in_cb = HIGH4; }  // the left-edge cells (:2487, :2494)
+            if (lane == 0) { in_eh = HIGH4 + TAG_EH; in_cb = cb_high(); }  // the left-edge cells (:2487, :2494)
 #pragma unroll
             for (int m = 0; m < K; m++) {
                 const int q = 2 * m;
@@ -181,7 +227,7 @@ struct AffFast {
                 by[m] = cell(eh[q - 1], cb[q - 1], evu, cbu, q, (p - m + P) % P, (p + m + 1) % P);
                 if (m == K - 1) {
                     if (lane == G - 1) {  // diagonal dhi + 1: poisoned (:2531-2535)
-                        cb[q] = HIGH4; ev[q] = HIGH4 + TAG_EV; eh[q] = HIGH4 + TAG_EH;
+                        cb[q] = cb_high(); ev[q] = HIGH4 + TAG_EV; eh[q] = HIGH4 + TAG_EH;
                     }
                 }
             }
@@ -205,7 +251,7 @@ struct AffFast {
             if (__any_sync(0xffffffffu, uu == u_last)) {
                 if (uu == u_last && lane == lane_f) {
 #pragma unroll
-                    for (int q = 0; q < Q; q++) scr[q] = min(min(cb[q], eh[q]), ev[q]);
+                    for (int q = 0; q < Q; q++) scr[q] = min(min(cb_plain(q), eh[q]), ev[q]);
                 }
             }
             // ---- windows: row i0 + p + 1 and column j0 + p + K + 1 enter
@@ -219,9 +265,11 @@ struct AffFast {
 template <int K, int G, bool BT, bool D6 = false>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     aff_fast_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm, const uint8_t *__restrict__ pool, uint8_t *__restrict__ dir,
-                    int *__restrict__ out_cost, int seq_bytes, int nslots, int *work_counter, int *slow_list, int *slow_count, int keep_mask,
-                    int one) {
+                    int *__restrict__ out_cost, int seq_bytes, int nslots, int *work_counter, const int *__restrict__ batch_list,
+                    const int *__restrict__ batch_count, int *slow_list, int *slow_count, int keep_mask, int one) {
     // keep_mask = ~3 and one = 1 arrive as arguments so that they live in registers (see AffFast::cell, fma_add)
+    // batch_list / batch_count: the batches aff_x2_kernel declined (null: all batches)
+    if (batch_list != nullptr && *batch_count == 0) return;
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
     using S_t = AffFast<K, G, BT, D6>;
@@ -262,12 +310,12 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     const int nbatches = (ntasks + GPW - 1) / GPW;
 
     int slot = 0;
-    int batch = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+    int batch = fetch_batch(work_counter, nbatches, batch_list, batch_count);
     if (batch >= 0) ring.produce_task(0, tasks, ntasks, batch * GPW + grp, pool, 16);
     while (batch >= 0) {
         int next = -1;
         if (nslots == 2) {  // the operands of the next batch travel under this one
-            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            next = fetch_batch(work_counter, nbatches, batch_list, batch_count);
             if (next >= 0) ring.produce_task(slot ^ 1, tasks, ntasks, next * GPW + grp, pool, 16);
         }
         const int ti = batch * GPW + grp;
@@ -363,13 +411,17 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
                 A.slide_windows(i0, j0);
             }
 #pragma unroll
-            for (int q = 0; q < Q; q++) { S.cb[q] = A.cb[q] - TAG_CB; S.ev[q] = A.ev[q]; S.eh[q] = A.eh[q]; }
+            for (int q = 0; q < Q; q++) {
+                S.cb[q] = A.cb[q] - TAG_CB + (FAST_CELL_V2 ? 4 * cm.gap_open : 0);
+                S.ev[q] = A.ev[q]; S.eh[q] = A.eh[q];
+            }
         }
         if (u <= u_end) {
             S.si = smem_u32(my_seq); S.sj = smem_u32(my_seq + op_stride);
             S.tabR = smem_u32(s_tabR); S.tabC = smem_u32(s_tabC);
             S.nr = nr; S.nc = nc; S.lane = lane; S.keep = keep_mask; S.one = one;
             S.c_h = 4 * cm.gap_open; S.c_v = 4 * cm.gap_open + TAG_EV;
+            S.c_d = 3 - 4 * cm.gap_open; S.c_o = 4 * cm.gap_open - TAG_CB;
             S.u_last = u_last; S.lane_f = lane_f; S.scr = my_scr;
             S.init_windows(i0, j0);
             // local step of (double step u, even half) is 2u - sbase: fold the per-pair part into the pointer
@@ -386,7 +438,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
         __syncwarp();
         ring.release(slot);  // this lane's last read of the staged operands is behind it
         if (nslots == 1) {
-            next = fetch_batch(work_counter, nbatches, nullptr, nullptr);
+            next = fetch_batch(work_counter, nbatches, batch_list, batch_count);
             if (next >= 0) ring.produce_task(0, tasks, ntasks, next * GPW + grp, pool, 16);
         } else {
             slot ^= 1;
@@ -398,8 +450,8 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
 #ifdef POYB200_DEFINE_AFF_FAST  // the translation unit that owns these kernels (k_aff_fast.cu)
 template <int K, int G, bool D6 = false>
 static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
-                                     int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
-                                     cudaStream_t stream) {
+                                     int sm_count, int seq_bytes, int *work_counter, const int *batch_list, const int *batch_count,
+                                     int *slow_list, int *slow_count, cudaStream_t stream) {
     constexpr int GPW = 32 / G;
     const int nbatches = (n + GPW - 1) / GPW;
     auto kern = bt ? aff_fast_kernel<K, G, true, D6> : aff_fast_kernel<K, G, false, false>;
@@ -410,23 +462,23 @@ static cudaError_t fast_launch_shape(bool bt, const Task *d_tasks, int n, DevCM 
     if (e != cudaSuccess) return e;
     int blocks = std::min((nbatches + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, work_counter, slow_list, slow_count,
-                                                      ~3, 1);
+    kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, work_counter, batch_list, batch_count,
+                                                      slow_list, slow_count, ~3, 1);
     return cudaGetLastError();
 }
 
 cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir,
-                                      int *cost, int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count,
-                                      bool dir6, cudaStream_t stream) {
+                                      int *cost, int sm_count, int seq_bytes, int *work_counter, const int *batch_list,
+                                      const int *batch_count, int *slow_list, int *slow_count, bool dir6, cudaStream_t stream) {
     if (dir6 && klass == 1)  // tasks flagged TF_DIR6 by the planner: the (5, 8) shape with the traceback kernel as reader
-        return fast_launch_shape<5, 8, true>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
+        return fast_launch_shape<5, 8, true>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
     switch (klass - 1) {
-        case 0: return fast_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
-        case 1: return fast_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
-        case 2: return fast_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
-        case 3: return fast_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
-        case 4: return fast_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
-        case 5: return fast_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, slow_list, slow_count, stream);
+        case 0: return fast_launch_shape<5, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
+        case 1: return fast_launch_shape<6, 8>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
+        case 2: return fast_launch_shape<4, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
+        case 3: return fast_launch_shape<6, 16>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
+        case 4: return fast_launch_shape<4, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
+        case 5: return fast_launch_shape<6, 32>(bt, d_tasks, n, cm, pool, dir, cost, sm_count, seq_bytes, work_counter, batch_list, batch_count, slow_list, slow_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -98,6 +98,8 @@ extern "C" void poyb200_default_config(poyb200_config *cfg) {
     cfg->allow_rows = 1;
     cfg->small_ring_pairs = 0;
     cfg->dir6 = 1;
+    cfg->pair2 = 1;
+    cfg->pair2_min_pairs = 0;
 }
 
 extern "C" int poyb200_create_ex(int device, const poyb200_config *user, poyb200_ctx **out) {
@@ -164,7 +166,7 @@ extern "C" void poyb200_destroy(poyb200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->d_cost.release(); ctx->d_prepend.release(); ctx->d_tail.release(); ctx->d_median.release(); ctx->d_worst.release();
     ctx->d_pool.release(); ctx->d_dir.release(); ctx->d_tasks.release(); ctx->d_costs.release();
-    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release(); ctx->d_slow_list.release();
+    ctx->d_outlen.release(); ctx->d_lin_state.release(); ctx->d_aff_state.release(); ctx->d_counters.release(); ctx->d_slow_list.release(); ctx->d_slow_list2.release();
     ctx->tasks.release();
     ctx->tasks_tmp.release();
     ctx->d_cost3.release(); ctx->d_ring.release(); ctx->d_status.release(); ctx->d_median3.release(); ctx->d_tasks3.release();
@@ -230,6 +232,18 @@ extern "C" int poyb200_set_cm(poyb200_ctx *ctx, const poyb200_cm *cm) {
     ctx->lin_natural = ctx->custom_tail ? 0 : 1;
     for (size_t b2 = 0; b2 < dim; b2++)
         if (cm->prepend_cost[b2] != cm->cost[((size_t) cm->gap << cm->lcm) + b2]) ctx->lin_natural = 0;
+    // aff_x2_kernel (16-bit halves): the largest value its tables can hold -- cost[a & 15][b & 15], cost[a][gap] and
+    // prepend[a] for the 32 codes of a DNA matrix
+    ctx->x2_unit4 = 1 << 30;
+    if (cm->lcm >= 5 && dim >= 32) {
+        long long mx = 0;
+        bool ok = true;
+        auto see = [&](long long v) { if (v < 0) ok = false; mx = std::max(mx, v); };
+        for (size_t a2 = 0; a2 < 16; a2++)
+            for (size_t b2 = 0; b2 < 16; b2++) see(cm->cost[(a2 << cm->lcm) + b2]);
+        for (size_t a2 = 0; a2 < 32; a2++) { see(cm->cost[(a2 << cm->lcm) + cm->gap]); see(cm->prepend_cost[a2]); }
+        if (ok && mx < 4096) ctx->x2_unit4 = (int) (4 * std::max<long long>(mx, 1));
+    }
     ctx->hcm = *cm;
     ctx->hcm.cost = nullptr; ctx->hcm.median = nullptr; ctx->hcm.worst = nullptr;
     ctx->hcm.prepend_cost = nullptr; ctx->hcm.tail_cost = nullptr;
@@ -336,10 +350,23 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
         const int *list = nullptr, *count = nullptr;
         if (affine && ctx->cfg.allow_fast && ctx->cfg.allow_noeb && ctx->dcm.gap_open > 0 && fast_has_shape(klass)) {
             CK(ctx->d_slow_list.reserve((size_t) n + 8));  // grows only (one entry per batch would do)
+            const bool dir6 = bt && klass == 1 && ctx->cfg.dir6 && mixed_class(ctx, klass, affine);
+            // shape (5, 8), 6-bit band: two pairs per lane group on 16-bit halves first; the batches it declines (gap bits,
+            // spare diagonals, costs that could leave the 16-bit range) are listed for aff_fast_kernel
+            const int *list0 = nullptr, *count0 = nullptr;
+            if (dir6 && ctx->cfg.pair2 && ctx->x2_unit4 < (1 << 20) && n >= ctx->cfg.pair2_min_pairs) {
+                CK(ctx->d_slow_list2.reserve((size_t) n + 8));
+                int *cnt0 = next_counter(ctx);
+                cudaError_t e0 = x2_launch(d_tasks, n, ctx->dcm, ctx->x2_unit4, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
+                                           seq_bytes, next_counter(ctx), ctx->d_slow_list2.p, cnt0, ctx->stream);
+                ctx->launches++;
+                CK(e0);
+                list0 = ctx->d_slow_list2.p;
+                count0 = cnt0;
+            }
             int *cnt = next_counter(ctx);
             cudaError_t e = fast_launch(klass, bt, d_tasks, n, ctx->dcm, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,
-                                        seq_bytes, next_counter(ctx), ctx->d_slow_list.p, cnt,
-                                        bt && klass == 1 && ctx->cfg.dir6 && mixed_class(ctx, klass, affine), ctx->stream);
+                                        seq_bytes, next_counter(ctx), list0, count0, ctx->d_slow_list.p, cnt, dir6, ctx->stream);
             ctx->launches++;
             CK(e);
             list = ctx->d_slow_list.p;

@@ -92,7 +92,7 @@ struct poyb200_ctx {
     const uint8_t *cur_pool = nullptr;  // what the kernels read operands from: d_pool, or a device-resident store's pool
     bool device_store = false;          // operands live in a poyb200_store, results stay on the device (store_batch)
     DevBuf<Task> d_tasks;
-    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters, d_slow_list;
+    DevBuf<int> d_costs, d_outlen, d_lin_state, d_counters, d_slow_list, d_slow_list2;
     size_t counter_next = 0;  // work counters handed to launches of the current call (zeroed once per call)
     DevBuf<int4> d_aff_state;
     long long dstride = 0, bstride = 0;
@@ -106,6 +106,7 @@ struct poyb200_ctx {
     // sequences are validated per pair instead of per pool entry.
     bool view = false;
     int64_t view_lo = 0;
+    int x2_unit4 = 1 << 30;  // 4 * the largest table entry aff_x2_kernel can read (its 16-bit range guard)
     int custom_tail = 0;   // tail_cost[a] != cost[a][gap] for some a: the last-column rule is not a no-op
     int lin_natural = 0;   // default prepend and tail costs: the first row and column follow from the ordinary recurrence
     int host_threads = 8;

@@ -12,7 +12,11 @@ cudaError_t stripe_launch(uint32_t klass, bool affine, bool bt, const Task *d_ta
                           int *cost, int sm_count, int seq_bytes, int allow_noeb, int *work_counter, const int *batch_list,
                           const int *batch_count, cudaStream_t stream);
 cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, DevCM cm, const uint8_t *pool, uint8_t *dir, int *cost,
-                        int sm_count, int seq_bytes, int *work_counter, int *slow_list, int *slow_count, bool dir6, cudaStream_t stream);
+                        int sm_count, int seq_bytes, int *work_counter, const int *batch_list, const int *batch_count, int *slow_list,
+                        int *slow_count, bool dir6, cudaStream_t stream);
+// two pairs per lane group on 16-bit halves (aff_x2_kernels.cuh): shape (5, 8), 6-bit band; declines whole batches into slow_list
+cudaError_t x2_launch(const Task *d_tasks, int n, DevCM cm, int max_unit4, const uint8_t *pool, uint8_t *dir, int *cost, int sm_count,
+                      int seq_bytes, int *work_counter, int *slow_list, int *slow_count, cudaStream_t stream);
 // ring kernels (k_aff_ring.cu): fill + traceback of the pairs whose stripe has no spare diagonals.  ebf = false takes the
 // batches without gap bits and lists the others in slow_list; ebf = true takes everything it is given.
 size_t ring_scratch_bytes(int sm_count, size_t slot_bytes);

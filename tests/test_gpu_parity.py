@@ -796,3 +796,70 @@ def test_powell_3d_aligner_matches_the_reference(S):
     assert gb.status[0] == 5 and gb.status[1] == 0
     assert gb.cost[1] == PU.ref_powell(ref, *cases[0], 1, 3, 2)[0]
     al.close()
+
+
+def test_two_pairs_per_group_kernel(S, checker_factory):
+    """aff_x2_kernel (csrc/aff_x2_kernels.cuh: two alignments in the 16-bit halves of every register) against the compiled
+    reference, every output, and against the library with the kernel switched off (pair2 = 0):
+    * leaf-like 500 bp pairs, pair counts that leave a half-filled group, a lone batch and an odd number of batches;
+    * lengths from 80 to 500 in one launch (the two pairs of a lane group end at different steps);
+    * batches mixed with pairs carrying gap bits (declined two batches at a time and taken by the next kernels);
+    * a cost matrix too large for 16 bits (everything declined), one near the limit (long pairs declined, short ones taken)."""
+    from poyd_b200 import cost_matrix as CM, synth
+
+    def both(cm, pool, pairs, label, ref=True):
+        on = S.Align(cm, config={"pair2": 1})
+        off = S.Align(cm, config={"pair2": 0})
+        g1 = on.align_affine_3(pool, pairs, ALL)
+        g0 = off.align_affine_3(pool, pairs, ALL)
+        assert np.array_equal(g1.cost, g0.cost), f"{label}: cost differs from pair2 = 0 at {np.nonzero(g1.cost != g0.cost)[0][:8]}"
+        for name in ("median", "medianwg", "aligned_a", "aligned_b", "lens"):
+            assert np.array_equal(getattr(g1, name), getattr(g0, name)), f"{label}: {name} differs from pair2 = 0"
+        if ref:
+            o = checker_factory(cm).batch(3, pool.pool, pool.off, pool.len, pairs, nthreads=8)
+            assert_aligned_equal(g1, o, label=label)
+        on.close()
+        off.close()
+
+    cm = CM.nucleotides(1, 2, 3)
+    for n, seed in ((1, 5), (3, 6), (4, 7), (13, 8), (37, 9), (1000, 10)):
+        pool, pairs = synth.pair_batch(n, 500, seed=seed, min_len=450)
+        both(cm, pool, pairs, f"leaf-like, {n} pairs")
+    # other costs (gap opening 1 and 5, substitutions dearer than indels)
+    for name, cm2 in _affine_cases()[1:3]:
+        pool, pairs = synth.pair_batch(600, 500, seed=21, min_len=450)
+        both(cm2, pool, pairs, f"leaf-like, {name}")
+    # ragged lengths in one launch: same stripe shape (5, 8) needs |lr - lc| small, so shorten both operands together
+    rng = np.random.default_rng(4)
+    seqs = []
+    for k in range(800):
+        L = int(rng.integers(80, 500))
+        a = np.concatenate([[16], rng.choice(np.array([1, 2, 4, 8], np.uint8), L)]).astype(np.uint8)
+        b = a.copy()
+        sub = rng.random(L + 1) < 0.1
+        sub[0] = False
+        b[sub] = rng.choice(np.array([1, 2, 4, 8], np.uint8), int(sub.sum()))
+        cut = rng.integers(1, L, size=int(rng.integers(0, 6)))
+        b = np.delete(b, cut)
+        seqs += [a, b]
+    pool = S.SeqPool(seqs)
+    pairs = np.arange(1600, dtype=np.int32).reshape(-1, 2)
+    both(cm, pool, pairs, "ragged lengths")
+    # every eleventh pair carries gap bits: its double batch goes to aff_fast_kernel, its batch on to the ring kernel
+    pool, pairs = synth.pair_batch(900, 500, seed=31, min_len=450)
+    for p in range(5, 900, 11):
+        r = pool.seq(int(pairs[p, 1]))
+        r[7::13] |= 16
+    both(cm, pool, pairs, "mixed with gap bits")
+    # costs: 16-bit range exceeded (4 * 40 * 1000 > 20000) -> all declined; near the limit -> decided pair by pair
+    pool, pairs = synth.pair_batch(300, 500, seed=41, min_len=450)
+    both(CM.nucleotides(20, 40, 30), pool, pairs, "costs too large for 16 bits")
+    seqs = []
+    for k in range(300):
+        L = 300 if (k // 24) % 2 == 0 else 500
+        a = np.concatenate([[16], rng.choice(np.array([1, 2, 4, 8], np.uint8), L)]).astype(np.uint8)
+        b = a.copy()
+        b[3::9] = 1
+        seqs += [a, np.delete(b, [L // 2])]
+    pool = S.SeqPool(seqs)
+    both(CM.nucleotides(3, 6, 2), pool, np.arange(600, dtype=np.int32).reshape(-1, 2), "costs near the 16-bit limit")
