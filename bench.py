@@ -42,7 +42,7 @@ UNIT = "GCUPS"
 WORKLOADS = {
     # name: (description, mode, reference ops per cell, dominant kernel)
     "affine500": ("configs[1]: 1M DNA pairs 500 bp (10% subst, 2% indel), affine gaps (subst 1, indel 2, gap opening 3), "
-                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_fast_kernel<5,8,true,true>"),
+                  "align_affine_3 = fill + traceback + median/medianwg/aligned pair", 3, 50, "aff_x2_kernel<5,8>"),
     "affine500_medianlike": ("configs[1], median-like operands: as affine500 plus 0.5% IUPAC ambiguities and 10% of positions "
                              "carrying the gap bit (what internal-node medians look like; exercises the block-diagonal "
                              "state)", 3, 50, "aff_ring_kernel<5,8,true,true>"),
@@ -837,9 +837,11 @@ def main():
     add_g, mm_g, mix_g = al.int32_peak()
     f_ms = head["phase_ms"]["fill"]
     fill_s = f_ms * 1e-3
-    # launches per chunk: affine = aff_fast_kernel + the full ring instance over the declined list + traceback kernel;
-    # linear = fill + traceback
-    fill_launches = max(1, head["launches_per_step"] // (3 if wl_mode == 3 else 2))
+    # launches per chunk: affine = aff_x2_kernel (pair2, the default) + aff_fast_kernel over the batches it declined + the full
+    # ring instance over the batches that one declined + traceback kernel; linear = fill + traceback
+    from poyd_b200 import _lib as _L
+    per_chunk = (3 + (1 if _L.make_config(None).pair2 else 0)) if wl_mode == 3 else 2
+    fill_launches = max(1, head["launches_per_step"] // per_chunk)
     km = kernel_metrics().get(wl_kernel, {})
     clocks = head.pop("clocks", None)
     sm_hz = ((clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))) * 1e6

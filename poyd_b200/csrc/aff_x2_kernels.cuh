@@ -46,9 +46,31 @@ __device__ __forceinline__ uint32_t x2_narrow(int v) {
 // VIMNMX.S16x2 with two predicate outputs and two predicated adds: the pattern of __vibmin_s16x2 (crt/device_functions.hpp),
 // with the predicates consumed on the spot (as returned booleans they outlive the seven predicate registers, and the
 // compiler parks them in a bit mask: two more instructions each).
+// X2_FLAG_FMA: the predicated adds as multiply-adds by an opaque 1 (FMA pipe; the INT32 ALU pipe is the busier one)
+#ifndef X2_FLAG_FMA
+#define X2_FLAG_FMA 0
+#endif
+// double steps per unrolled block (a divisor of K + 1 = 6).  Measured on 524 288 pairs of configs[1], device-resident
+// (gpurun_out/r02x2s_*.json): 6 -> 972 GCUPS, 3 -> 1 023, 2 (with X2_FLAG_FMA) -> 1 010; X2_FLAG_FMA changes nothing (3: 1 013)
+#ifndef X2_UNROLL
+#define X2_UNROLL 3
+#endif
 template <uint32_t BITS>
-__device__ __forceinline__ uint32_t x2_min_flag(uint32_t a, uint32_t b, uint32_t &fwA, uint32_t &fwB) {
+__device__ __forceinline__ uint32_t x2_min_flag(uint32_t a, uint32_t b, uint32_t &fwA, uint32_t &fwB, uint32_t one) {
     uint32_t m;
+#if X2_FLAG_FMA
+    asm("{\n\t.reg .pred pu, pv;\n\t.reg .u16 rs0, rs1, rs2, rs3;\n\t"
+        "min.s16x2 %0, %3, %4;\n\t"
+        "mov.b32 {rs0, rs1}, %0;\n\t"
+        "mov.b32 {rs2, rs3}, %3;\n\t"
+        "setp.eq.s16 pv, rs0, rs2;\n\t"
+        "setp.eq.s16 pu, rs1, rs3;\n\t"
+        "@pv mad.lo.u32 %1, %6, %5, %1;\n\t"
+        "@pu mad.lo.u32 %2, %6, %5, %2;\n\t}"
+        : "=r"(m), "+r"(fwA), "+r"(fwB)
+        : "r"(a), "r"(b), "n"(BITS), "r"(one));
+#else
+    (void) one;
     asm("{\n\t.reg .pred pu, pv;\n\t.reg .u16 rs0, rs1, rs2, rs3;\n\t"
         "min.s16x2 %0, %3, %4;\n\t"
         "mov.b32 {rs0, rs1}, %0;\n\t"
@@ -59,12 +81,16 @@ __device__ __forceinline__ uint32_t x2_min_flag(uint32_t a, uint32_t b, uint32_t
         "@pu add.u32 %2, %2, %5;\n\t}"
         : "=r"(m), "+r"(fwA), "+r"(fwB)
         : "r"(a), "r"(b), "n"(BITS));
+#endif
     return m;
 }
 
 template <int K, int G>
 struct AffX2 {
     static constexpr int Q = 2 * K, P = K + 1, BL = 4;
+    // double steps per unrolled block: a whole ring turn (P) needs no register moves but is 32 KB of code, and the kernel then
+    // waits for instructions (ncu: "no instruction" 0.70 stalls per issue); a divisor of P rotates the windows at the end
+    static constexpr int UN = (P % X2_UNROLL == 0) ? X2_UNROLL : P;
     static_assert(K == 5, "6-bit packing is for five codes per word");
 
     uint32_t cb[Q], ev[Q], eh[Q];  // low half: pair A, high half: pair B.  cb = 4 * CB + 4 * gap_open (tag 0), see FAST_CELL_V2
@@ -73,6 +99,7 @@ struct AffX2 {
     uint32_t siA, sjA, siB, sjB, tabR, tabC;  // shared addresses
     int nrA, ncA, nrB, ncB, lane;
     uint32_t keep2;                 // 0xfffcfffc
+    uint32_t one;                   // 1, opaque (X2_FLAG_FMA)
     uint32_t c_d2, c_o2, cb_high2;  // 3 - go4 (state -> tag A 3 candidate), go4 - 1 (tag-1 value -> state), X2_HIGH + go4: per half
     int go4;
     // per pair
@@ -108,10 +135,10 @@ struct AffX2 {
         // every half is non-negative and below 2^15: plain 32-bit adds of non-negative halves never carry across
         const uint32_t xo = cbl + Cv[cs];                  // open horizontally: tag 0
         const uint32_t xe = ehl + Cv[cs];
-        const uint32_t neh = x2_min_flag<((uint32_t) AB_ENDH) << (6 * M)>(xo, xe, fwA, fwB);  // FILL_EXTEND_HORIZONTAL :1765-1787
+        const uint32_t neh = x2_min_flag<((uint32_t) AB_ENDH) << (6 * M)>(xo, xe, fwA, fwB, one);  // FILL_EXTEND_HORIZONTAL :1765-1787
         const uint32_t yo = cbu + Rv[rs] + x2_dup(TAG_EV);       // open vertically: tag 2
         const uint32_t ye = evu + Rv[rs];
-        const uint32_t nev = x2_min_flag<((uint32_t) AB_ENDV) << (6 * M)>(yo, ye, fwA, fwB);  // FILL_EXTEND_VERTICAL :1813-1830
+        const uint32_t nev = x2_min_flag<((uint32_t) AB_ENDV) << (6 * M)>(yo, ye, fwA, fwB, one);  // FILL_EXTEND_VERTICAL :1813-1830
         const uint32_t d = (uint32_t) (lds_s32(RlB[rs] + ClB[cs]) * 65536 + lds_s32(RlA[rs] + ClA[cs]));  // 4 * cost[si & 15][sj & 15]
         // FILL_CLOSE_BLOCK_DIAGONAL :1923-1977 (tags A 3, V 2, H 0); c_d2 is negative per half: only the SIMD add may take it
         const uint32_t m01 = __viaddmin_s16x2(cb[q], c_d2, ev[q]);
@@ -130,11 +157,21 @@ struct AffX2 {
         wB += (by[4] >> 16) * (1u << 24) + ((t23 >> 16) * 4096u + (t01 >> 16));
     }
 
-    // One block of P double steps starting at double step u (every lane at rows and columns >= 1), lane origin
+    template <class T>
+    static __device__ __forceinline__ void rotate(T (&a)[P]) {  // a[s] <- a[(s + UN) % P]
+        if (UN == P) return;
+        T t[P];
+#pragma unroll
+        for (int s_ = 0; s_ < P; s_++) t[s_] = a[(s_ + UN) % P];
+#pragma unroll
+        for (int s_ = 0; s_ < P; s_++) a[s_] = t[s_];
+    }
+
+    // One block of UN double steps starting at double step u (every lane at rows and columns >= 1), lane origin
     // (i0, j0A / j0B).  dptrA / dptrB as AffFast::block's dptr, per pair.
     __device__ __forceinline__ void block(int u, int i0, int j0A, int j0B, uint8_t *dptrA, uint8_t *dptrB) {
 #pragma unroll
-        for (int p = 0; p < P; p++) {
+        for (int p = 0; p < UN; p++) {
             uint32_t deA = 0, deB = 0, doA = 0, doB = 0;
             uint32_t by[K];
             // ---- even step: q = 2m, cell (i0 + p - m, j0 + p + m)
@@ -185,6 +222,9 @@ struct AffX2 {
             load_row((p + 1) % P, i0 + p + 1);
             load_col((p + K + 1) % P, j0A + p + K + 1, j0B + p + K + 1);
         }
+        if (UN != P) {  // the next block expects its rows / columns in the slots this one started with
+            rotate(Rv); rotate(Cv); rotate(RlA); rotate(RlB); rotate(ClA); rotate(ClB);
+        }
     }
 };
 
@@ -195,7 +235,7 @@ template <int K, int G>
 __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
     aff_x2_kernel(const Task *__restrict__ tasks, int ntasks, DevCM cm, const uint8_t *__restrict__ pool, uint8_t *__restrict__ dir,
                   int *__restrict__ out_cost, int seq_bytes, int nslots, int *work_counter, int *slow_list, int *slow_count,
-                  int max_unit4, uint32_t keep2) {
+                  int max_unit4, uint32_t keep2, uint32_t one) {
     // keep2 = 0xfffcfffc arrives as an argument so that it lives in a register (a LOP3 takes one immediate)
     constexpr int GPW = 32 / G;
     constexpr int Q = 2 * K;
@@ -279,7 +319,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
             // spare diagonals below dlo need the left-edge rule inside the stripe: not here
             decline |= valid[h] && (t[h].dlo - d0[h] > 0);
             // 16-bit range: no cell of the stripe, real or past the ends of the operands, may reach X2_REAL_MAX
-            decline |= valid[h] && (max_unit4 * (t[h].lr + t[h].lc + 2 * Q * G + 4 * P) + go4 + 64 >= X2_REAL_MAX);
+            decline |= valid[h] && (max_unit4 * (t[h].lr + t[h].lc + 2 * Q * G + 4 * P) + 2 * go4 + 64 >= X2_REAL_MAX);
             // gap bits beyond the leading element of either operand (scanned in shared memory, 4 bytes per load)
             if (valid[h]) {
                 for (int k = lane * 4; k < t[h].lr; k += G * 4) {
@@ -389,7 +429,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
             S.siB = smem_u32(seq[1]); S.sjB = smem_u32(seq[1] + op_stride);
             S.tabR = smem_u32(s_tabR); S.tabC = smem_u32(s_tabC);
             S.nrA = nr[0]; S.ncA = nc[0]; S.nrB = nr[1]; S.ncB = nc[1]; S.lane = lane;
-            S.go4 = go4; S.keep2 = keep2;
+            S.go4 = go4; S.keep2 = keep2; S.one = one;
             S.c_d2 = x2_dup((3 - go4) & 0xffff); S.c_o2 = x2_dup(go4 - TAG_CB); S.cb_high2 = x2_dup(X2_HIGH + go4);
             S.u_lastA = u_last[0]; S.u_lastB = u_last[1]; S.lane_fA = lane_f[0]; S.lane_fB = lane_f[1];
             S.scrA = my_scr; S.scrB = my_scr + FAST_SCR_INTS;
@@ -398,7 +438,7 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
             uint8_t *dptrA = dbase[0] + (ptrdiff_t) lane * 8 * BL - (ptrdiff_t) (sbase[0] >> 3) * (G * 8 * BL);
             uint8_t *dptrB = dbase[1] + (ptrdiff_t) lane * 8 * BL - (ptrdiff_t) (sbase[1] >> 3) * (G * 8 * BL);
             int i = i0, jA = j0A, jB = j0B;
-            for (; u <= u_end; u += P, i += P, jA += P, jB += P) S.block(u, i, jA, jB, dptrA, dptrB);
+            for (; u <= u_end; u += S_t::UN, i += S_t::UN, jA += S_t::UN, jB += S_t::UN) S.block(u, i, jA, jB, dptrA, dptrB);
         }
 
 #pragma unroll
@@ -427,6 +467,14 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
 }
 
 #ifdef POYB200_DEFINE_AFF_FAST  // the translation unit that owns these kernels (k_aff_fast.cu)
+// True when one staging slot for the CTA's 2 x 16 pairs of operands fits the shared memory of an SM, and pairs that long
+// could pass the 16-bit guard at all (api.cu asks before every launch: a chunk of long pairs skips this kernel).
+bool x2_usable(int seq_bytes, int max_unit4) {
+    constexpr int K = 5, G = 8, GPW = 32 / G;
+    const size_t ring1 = (size_t) STRIPE_WARPS * GPW * 2 * 2 * (seq_bytes + fast_operand_pad(K, G));
+    return X2_TABLE_BYTES + ring1 <= (size_t) 200 * 1024 && (long long) max_unit4 * 64 < X2_REAL_MAX;
+}
+
 // Shape (5, 8) with the 6-bit band only (the tasks the planner flagged TF_DIR6).
 cudaError_t x2_launch(const Task *d_tasks, int n, DevCM cm, int max_unit4, const uint8_t *pool, uint8_t *dir, int *cost, int sm_count,
                       int seq_bytes, int *work_counter, int *slow_list, int *slow_count, cudaStream_t stream) {
@@ -441,7 +489,7 @@ cudaError_t x2_launch(const Task *d_tasks, int n, DevCM cm, int max_unit4, const
     int blocks = std::min((ndouble + STRIPE_WARPS - 1) / STRIPE_WARPS, sm_count * per_sm);
     if (blocks < 1) blocks = 1;
     kern<<<blocks, STRIPE_WARPS * 32, smem, stream>>>(d_tasks, n, cm, pool, dir, cost, seq_bytes, nslots, work_counter, slow_list, slow_count,
-                                                      max_unit4, 0xfffcfffcu);
+                                                      max_unit4, 0xfffcfffcu, 1u);
     return cudaGetLastError();
 }
 #endif  // POYB200_DEFINE_AFF_FAST
