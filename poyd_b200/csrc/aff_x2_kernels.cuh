@@ -133,9 +133,9 @@ struct AffX2 {
     __device__ __forceinline__ uint32_t cell(uint32_t ehl, uint32_t cbl, uint32_t evu, uint32_t cbu, int q, int rs, int cs, uint32_t &fwA,
                                              uint32_t &fwB) {
         // every half is non-negative and below 2^15: plain 32-bit adds of non-negative halves never carry across
-        const uint32_t xo = cbl + Cv[cs];                  // open horizontally: tag 0
-        const uint32_t xe = ehl + Cv[cs];
-        const uint32_t neh = x2_min_flag<((uint32_t) AB_ENDH) << (6 * M)>(xo, xe, fwA, fwB, one);  // FILL_EXTEND_HORIZONTAL :1765-1787
+        // FILL_EXTEND_HORIZONTAL :1765-1787: opening (cbl = 4 CB + 4 go, tag 0) against extension (ehl, tag 0), then the
+        // column's gap cost -- both candidates take the same addend, so the comparison is made before it
+        const uint32_t neh = x2_min_flag<((uint32_t) AB_ENDH) << (6 * M)>(cbl, ehl, fwA, fwB, one) + Cv[cs];
         const uint32_t yo = cbu + Rv[rs] + x2_dup(TAG_EV);       // open vertically: tag 2
         const uint32_t ye = evu + Rv[rs];
         const uint32_t nev = x2_min_flag<((uint32_t) AB_ENDV) << (6 * M)>(yo, ye, fwA, fwB, one);  // FILL_EXTEND_VERTICAL :1813-1830
