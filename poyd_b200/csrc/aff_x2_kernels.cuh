@@ -469,10 +469,14 @@ __global__ void __launch_bounds__(STRIPE_WARPS * 32, FAST_MIN_BLOCKS)
 #ifdef POYB200_DEFINE_AFF_FAST  // the translation unit that owns these kernels (k_aff_fast.cu)
 // True when one staging slot for the CTA's 2 x 16 pairs of operands fits the shared memory of an SM, and pairs that long
 // could pass the 16-bit guard at all (api.cu asks before every launch: a chunk of long pairs skips this kernel).
-bool x2_usable(int seq_bytes, int max_unit4) {
+bool x2_usable(int seq_bytes, int max_unit4, int gap_open) {
     constexpr int K = 5, G = 8, GPW = 32 / G;
     const size_t ring1 = (size_t) STRIPE_WARPS * GPW * 2 * 2 * (seq_bytes + fast_operand_pad(K, G));
-    return X2_TABLE_BYTES + ring1 <= (size_t) 200 * 1024 && (long long) max_unit4 * 64 < X2_REAL_MAX;
+    if (X2_TABLE_BYTES + ring1 > (size_t) 200 * 1024) return false;
+    if ((long long) max_unit4 * 64 >= X2_REAL_MAX) return false;
+    // a cell that does not exist is worth X2_HIGH (+ the gap opening, + one or two table entries, + a tag): that must stay
+    // inside 15 bits, and inside the 4000 x2_narrow() keeps of a HIGH_NUM-based value of the boundary phase
+    return gap_open >= 0 && 4ll * gap_open + 2ll * max_unit4 + 16 < 4000;
 }
 
 // Shape (5, 8) with the 6-bit band only (the tasks the planner flagged TF_DIR6).

@@ -354,7 +354,7 @@ static int launch_fill(poyb200_ctx *ctx, uint32_t klass, bool affine, bool bt, c
             // shape (5, 8), 6-bit band: two pairs per lane group on 16-bit halves first; the batches it declines (gap bits,
             // spare diagonals, costs that could leave the 16-bit range) are listed for aff_fast_kernel
             const int *list0 = nullptr, *count0 = nullptr;
-            if (dir6 && ctx->cfg.pair2 && n >= ctx->cfg.pair2_min_pairs && x2_usable(seq_bytes, ctx->x2_unit4)) {
+            if (dir6 && ctx->cfg.pair2 && n >= ctx->cfg.pair2_min_pairs && x2_usable(seq_bytes, ctx->x2_unit4, ctx->dcm.gap_open)) {
                 CK(ctx->d_slow_list2.reserve((size_t) n + 8));
                 int *cnt0 = next_counter(ctx);
                 cudaError_t e0 = x2_launch(d_tasks, n, ctx->dcm, ctx->x2_unit4, ctx->cur_pool, ctx->cur_dir, ctx->d_costs.p, ctx->sm_count,

@@ -15,7 +15,7 @@ cudaError_t fast_launch(uint32_t klass, bool bt, const Task *d_tasks, int n, Dev
                         int sm_count, int seq_bytes, int *work_counter, const int *batch_list, const int *batch_count, int *slow_list,
                         int *slow_count, bool dir6, cudaStream_t stream);
 // two pairs per lane group on 16-bit halves (aff_x2_kernels.cuh): shape (5, 8), 6-bit band; declines whole batches into slow_list
-bool x2_usable(int seq_bytes, int max_unit4);
+bool x2_usable(int seq_bytes, int max_unit4, int gap_open);
 cudaError_t x2_launch(const Task *d_tasks, int n, DevCM cm, int max_unit4, const uint8_t *pool, uint8_t *dir, int *cost, int sm_count,
                       int seq_bytes, int *work_counter, int *slow_list, int *slow_count, cudaStream_t stream);
 // ring kernels (k_aff_ring.cu): fill + traceback of the pairs whose stripe has no spare diagonals.  ebf = false takes the
