@@ -47,10 +47,25 @@ def save(name, cm, pool, pairs, mode, deltaw=None):
     print(name, len(pairs), "pairs, cost sum", int(o["cost"].sum()))
 
 
+ONLY = set(sys.argv[1:])  # fixture names to (re)generate; none given = all
+
+
 def main():
     oracle.build(ref=True)
     assert oracle.Reference.available(), "the reference must be compiled here"
+    global save
+    save_all = save
+
+    def save(name, *a, **k):  # noqa: F811
+        if not ONLY or name in ONLY:
+            save_all(name, *a, **k)
+
     aff = CM.nucleotides(1, 2, 3)
+    # leaf-like pairs of the headline shape (no gap bits): the pairs aff_x2_kernel / aff_fast_kernel take; 44 pairs = eleven
+    # batches of four = five double batches of aff_x2_kernel and one with an empty half
+    pool, pairs = synth.pair_batch(44, 500, seed=7, min_len=450)
+    save("affine_cfg2_leaflike", aff, pool, pairs, 3)
+    save("affine_cfg2_leaflike_cost", aff, pool, pairs, 2)
     pool, pairs = synth.pair_batch(48, 500, seed=2, min_len=450, ambiguity=0.005, gap_ambiguity=0.10)
     save("affine_cfg2_medianlike", aff, pool, pairs, 3)
     save("affine_cfg2_medianlike_cost", aff, pool, pairs, 2)
