@@ -182,6 +182,21 @@ class Port3:
         return res + (d,) if want_dir else res
 
 
+    def align_3_intended(self, s1, s2, s3):
+        """The recurrence algn_fill_cube intends (po_cost_3_intended, SURVEY.md "3-D policy" (1)): a correct three-sequence
+        Needleman-Wunsch with the reference's candidate order.  Returns (cost, status, r1, r2, r3, median)."""
+        s1, s2, s3 = _u8(s1), _u8(s2), _u8(s3)
+        l1, l2, l3 = len(s1), len(s2), len(s3)
+        d = np.zeros(l1 * l2 * l3, np.uint8)
+        cost = self.L.po_cost_3_intended(C.byref(self.c), _p(s1, _u8p), l1, _p(s2, _u8p), l2, _p(s3, _u8p), l3, _p(d, _u8p))
+        cap = l1 + l2 + l3
+        r = [np.zeros(cap + 1, np.uint8) for _ in range(4)]
+        st = C.c_int(0)
+        n = self.L.po_backtrack_3_intended(C.byref(self.c), _p(d, _u8p), _p(s1, _u8p), l1, _p(s2, _u8p), l2, _p(s3, _u8p), l3,
+                                           _p(r[0], _u8p), _p(r[1], _u8p), _p(r[2], _u8p), _p(r[3], _u8p), C.byref(st))
+        return (cost, st.value, r[0][:n].copy(), r[1][:n].copy(), r[2][:n].copy(), r[3][:n].copy())
+
+
 class Reference3:
     """3-D cube through the compiled reference (algn_nw_3d + backtrack_3d + algn_get_median_3d)."""
 

@@ -627,6 +627,115 @@ int po_cost_3(const po_cm3 *c, const uint8_t *s1, int l1, const uint8_t *s2, int
     return res;
 }
 
+/* The recurrence algn_fill_cube INTENDS (SURVEY.md A12 and "3-D policy" (1)): the same seven candidates, in the same order
+ * and with the same strict `<` (P3 4, P1 1, P2 2, S3 32, S1 8, S2 16, SS 64; src/algn.c:2812-2857, 3039-3046), but read
+ * from the rows a three-sequence Needleman-Wunsch needs -- (i-1, j), (i-1, j-1), (i, j-1) -- instead of the lagging rows
+ * the compiled code reads.  Plane 0 and the cost expressions are the reference's own (they are correct as written).
+ * Checked against exhaustive enumeration and an independent memoised recursion in tests/test_cube_intended.py; the CUDA
+ * cube kernel reproduces the EXECUTED form (po_cost_3), this function documents what a corrected reference would return. */
+int po_cost_3_intended(const po_cm3 *c, const uint8_t *s1, int l1, const uint8_t *s2, int l2, const uint8_t *s3, int l3,
+                       uint8_t *dir) {
+    const int gap = c->gap;
+    size_t nrows = (size_t) l1 * l2;
+    int *M = (int *) malloc(sizeof(int) * nrows * (size_t) l3);
+    int *gg = (int *) malloc(sizeof(int) * (size_t) l3);
+    for (int k = 0; k < l3; k++) gg[k] = po_cost3(c, gap, gap, s3[k]);
+#define ROW(r) (M + (size_t) (r) * l3)
+#define DIR(r, k, v) do { if (dir) dir[(size_t) (r) * l3 + (k)] = (uint8_t) (v); } while (0)
+    ROW(0)[0] = 0; DIR(0, 0, 16);
+    for (int k = 1; k < l3; k++) { ROW(0)[k] = ROW(0)[k - 1] + gg[k]; DIR(0, k, 64); }
+    for (int j = 1; j < l2; j++) {  /* plane 0 (:2918-2962) */
+        int *mm = ROW(j), *prev = ROW(j - 1), b = s2[j];
+        int g0 = po_cost3(c, gap, b, s3[0]);
+        mm[0] = prev[0] + g0; DIR(j, 0, 1);
+        for (int k = 1; k < l3; k++) {
+            int v = prev[k] + g0, d = 1, t = prev[k - 1] + po_cost3(c, gap, b, s3[k]);
+            if (t < v) { v = t; d = 8; }
+            t = mm[k - 1] + gg[k];
+            if (t < v) { v = t; d = 64; }
+            mm[k] = v; DIR(j, k, d);
+        }
+    }
+    for (int i = 1; i < l1; i++) {
+        int a = s1[i];
+        int a0 = po_cost3(c, a, gap, s3[0]);
+        {   /* row (i, 0): only s1 and s3 can move (:2990-3013), from row (i-1, 0) */
+            size_t r = (size_t) i * l2;
+            int *mm = ROW(r), *U = ROW((size_t) (i - 1) * l2);
+            mm[0] = U[0] + a0; DIR(r, 0, 4);
+            for (int k = 1; k < l3; k++) {
+                int v = U[k] + a0, d = 4, t = U[k - 1] + po_cost3(c, a, gap, s3[k]);
+                if (t < v) { v = t; d = 32; }
+                t = gg[k] + mm[k - 1];
+                if (t < v) { v = t; d = 64; }
+                mm[k] = v; DIR(r, k, d);
+            }
+        }
+        for (int j = 1; j < l2; j++) {
+            size_t r = (size_t) i * l2 + j;
+            int b = s2[j];
+            int *mm = ROW(r);
+            const int *U = ROW((size_t) (i - 1) * l2 + j);        /* (i-1, j)   */
+            const int *D = ROW((size_t) (i - 1) * l2 + (j - 1));  /* (i-1, j-1) */
+            const int *P = ROW((size_t) i * l2 + (j - 1));        /* (i, j-1)   */
+            int s1gg = a0, gs2g = po_cost3(c, gap, b, s3[0]), s1s2g = po_cost3(c, a, b, s3[0]);
+            for (int k = 0; k < l3; k++) {
+                int v = U[k] + s1gg, d = 4, t = P[k] + gs2g;
+                if (t < v) { v = t; d = 1; }
+                t = D[k] + s1s2g;
+                if (t < v) { v = t; d = 2; }
+                if (k >= 1) {
+                    t = U[k - 1] + po_cost3(c, a, gap, s3[k]);
+                    if (t < v) { v = t; d = 32; }
+                    t = P[k - 1] + po_cost3(c, gap, b, s3[k]);
+                    if (t < v) { v = t; d = 8; }
+                    t = D[k - 1] + po_cost3(c, a, b, s3[k]);
+                    if (t < v) { v = t; d = 16; }
+                    t = mm[k - 1] + gg[k];
+                    if (t < v) { v = t; d = 64; }
+                }
+                mm[k] = v; DIR(r, k, d);
+            }
+        }
+    }
+    int res = ROW(nrows - 1)[l3 - 1];
+#undef ROW
+#undef DIR
+    free(M); free(gg);
+    return res;
+}
+
+/* backtrack_3d's walk (:3829-3905, same test order) over a direction cube of po_cost_3_intended, and the median
+ * algn_get_median_3d INTENDS (:4160-4173 with the pointers moving): one cm_get_median_3d per column.  Left aligned on return. */
+int po_backtrack_3_intended(const po_cm3 *c, const uint8_t *dir, const uint8_t *s1, int l1, const uint8_t *s2, int l2,
+                            const uint8_t *s3, int l3, uint8_t *r1, uint8_t *r2, uint8_t *r3, uint8_t *med, int *status) {
+    int cap = l1 + l2 + l3, n = 0, i1 = l1 - 1, i2 = l2 - 1, i3 = l3 - 1;
+    long long p = (long long) l1 * l2 * l3 - 1, plane = (long long) l2 * l3, line = l3;
+    uint8_t gap = (uint8_t) c->gap;
+    *status = 0;
+    while (p > 0) {
+        int v = dir[p], u1 = 0, u2 = 0, u3 = 0;
+        if (v & 16) { u1 = u2 = u3 = 1; p -= plane + line + 1; }
+        else if (v & 32) { u1 = u3 = 1; p -= plane + 1; }
+        else if (v & 8) { u2 = u3 = 1; p -= line + 1; }
+        else if (v & 4) { u1 = 1; p -= plane; }
+        else if (v & 64) { u3 = 1; p -= 1; }
+        else if (v & 1) { u2 = 1; p -= line; }
+        else { u1 = u2 = 1; p -= plane + line; }
+        if ((u1 && i1 < 1) || (u2 && i2 < 1) || (u3 && i3 < 1) || n >= cap) { *status = 1; return 0; }
+        n++;
+        r1[cap - n] = u1 ? s1[i1--] : gap;
+        r2[cap - n] = u2 ? s2[i2--] : gap;
+        r3[cap - n] = u3 ? s3[i3--] : gap;
+    }
+    if (i1 != 0 || i2 != 0 || i3 != 0) { *status = 1; return 0; }  /* every element but the leading gaps consumed */
+    memmove(r1, r1 + cap - n, n);
+    memmove(r2, r2 + cap - n, n);
+    memmove(r3, r3 + cap - n, n);
+    for (int k = 0; k < n; k++) med[k] = c->median3[(((r1[k] << c->lcm) + r2[k]) << c->lcm) + r3[k]];
+    return n;
+}
+
 /* backtrack_3d (:3829-3905) + algn_get_median_3d (:4160-4173).  Outputs need l1+l2+l3 (+1 for med) bytes, left aligned
  * on return.  *status = 1 (and nothing is produced) when the reference's walk would index a sequence below 0, which
  * the reference does not check. */
