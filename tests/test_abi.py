@@ -81,3 +81,27 @@ def test_ocaml_stubs_compile_against_reference_headers():
            "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + ref, "-I" + os.path.join(ROOT, "include"),
            os.path.join(ROOT, "stubs", "poyb200_stubs.c")]
     subprocess.check_call(cmd)
+
+
+def test_config_struct_matches_the_header_and_its_defaults():
+    """poyb200_config (include/poyb200.h) field by field against the ctypes mirror, and the documented defaults --
+    poyb200_default_config needs no device.  A caller built against an older header passes a shorter struct_bytes."""
+    from poyd_b200 import _lib
+
+    src = open(os.path.join(ROOT, "include", "poyb200.h")).read()
+    body = src[src.index("typedef struct poyb200_config {"):src.index("} poyb200_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:uint32_t|int32_t|int64_t)\s+([a-z0-9_]+)\s*;", body)
+    assert fields == [n for n, _ in _lib.Config._fields_], "poyd_b200/_lib.py Config out of sync with include/poyb200.h"
+    cfg = _lib.make_config(None)
+    assert cfg.struct_bytes == ctypes.sizeof(_lib.Config)
+    want = dict(force_generic=0, allow_fast=1, allow_noeb=1, use_ring=2, overlap_traceback=1, dir_buffers=3,
+                traceback_threads_per_sm=256, traceback_block=128, chunk_pairs=1 << 16, allow_rows=1, dir6=1, pair2=1,
+                pair2_min_pairs=0)
+    for k, v in want.items():
+        assert getattr(cfg, k) == v, (k, getattr(cfg, k), v)
+    assert _lib.make_config({"pair2": 0}).pair2 == 0
+    import pytest
+
+    with pytest.raises(KeyError):
+        _lib.make_config({"no_such_field": 1})
