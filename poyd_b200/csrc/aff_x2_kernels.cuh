@@ -10,7 +10,7 @@
 // two alignments with (almost) the instructions of one:
 //
 //   per TWO cells                       aff_fast_kernel (x 2)      here
-//   extension states (H, V)             2 x 10                     2 x (add, add, VIMNMX.S16x2 + 2 predicated adds) = 10
+//   extension states (H, V)             2 x 10                     H: VIMNMX.S16x2, add; V: 2 adds, VIMNMX.S16x2; + 4 predicated adds = 9
 //   cost[si][sj]                        2 x 2                      2 loads, 2 address adds, 1 merge               =  5
 //   close-block minimum, tag-1 value    2 x 5                      VIADDMNMX.S16x2, VIMNMX3.S16x2, add, LOP3, add =  5
 //   ASSIGN_MINIMUM, choice bits         2 x 4                      VIMNMX3.S16x2, 2 masks, 1 multiply-add         =  4
